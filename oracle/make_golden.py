@@ -1,0 +1,124 @@
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY; runs in the BUILD container only.
+
+Imports the reference's own `models/instant_nsr.py` from /root/reference (read-only, never
+copied), slots oracle/hashgrid.py in for the CUDA-only `_backend`
+(encoder/hashencoder/hashgrid.py:9,38 -- the kernel has no CPU path, hashencoder.cu:414-418),
+runs the reference `NeRFRenderer.run` on seeded synthetic inputs, checks that the
+restatement in oracle/nsr_oracle.py agrees with it, and writes small golden fixtures to
+tests/golden/*.npz.  /root/reference does not exist on the GPU box, so tests read only the
+committed fixtures.
+
+    python -m oracle.make_golden
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import hashgrid as ohg                      # noqa: E402
+from oracle.nsr_oracle import OracleNSR                 # noqa: E402
+from avatarcraft_b200.utils import synthetic as syn     # noqa: E402
+
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    for name in ("mcubes", "trimesh", "igl"):          # mesh export / plotting / warp only
+        sys.modules.setdefault(name, types.ModuleType(name))
+    be = types.SimpleNamespace(hash_encode_forward=ohg.hash_encode_forward,
+                               hash_encode_backward=ohg.hash_encode_backward)
+    for pkg in ("encoder.hashencoder.backend", "encoder.shencoder.backend"):
+        m = types.ModuleType(pkg)
+        m._backend = be
+        sys.modules[pkg] = m
+    sys.path.insert(0, REF)
+    warnings.simplefilter("ignore")
+    import models.instant_nsr as ref_nsr
+    return ref_nsr
+
+
+def ref_run(ref_nsr, sd, rays_o, rays_d, num_steps, upsample_steps, bound, training=False, seed=None, bg=None):
+    net = ref_nsr.NeRFNetwork()
+    net.load_state_dict(sd)
+    net.train(training)
+    if seed is not None:
+        torch.manual_seed(seed)
+    with torch.no_grad():
+        return net.run(rays_o[None], rays_d[None], num_steps, bound, upsample_steps, bg,
+                       cos_anneal_ratio=1.0, normal_epsilon_ratio=0.0, render_can=True,
+                       perturb_overwrite=training)
+
+
+def pack(out):
+    depth, weights, wsum, image, nmap, eik, _, color, alpha, z = out
+    return dict(depth=depth.reshape(-1).numpy(), weights=weights.numpy(), weight_sum=wsum.reshape(-1).numpy(),
+                rgb=image.reshape(-1, 3).numpy(), normal=nmap.numpy(), eikonal=np.float32(float(eik)),
+                pts_color=color.numpy(), pts_alpha=alpha.numpy(), z_vals=z.numpy())
+
+
+def compare(a, b, tag):
+    worst = 0.0
+    for k in a:
+        d = float(np.max(np.abs(np.asarray(a[k], dtype=np.float64) - np.asarray(b[k], dtype=np.float64))))
+        worst = max(worst, d)
+        print(f"  [{tag}] {k:12s} max|ref-oracle| = {d:.3e}")
+    return worst
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref_nsr = import_reference()
+    cases = [
+        # name, checkpoint kind, seed, image WxH, ray subsample stride, steps, upsample, training
+        ("c1_init_64x64_16p16", "init", 42, 64, 16, 16, 16, False),
+        ("c2_trained_256x256_64p64", "trained", 43, 256, 257, 64, 64, False),
+        ("c4_trained_256x256_32p32", "trained", 43, 256, 509, 32, 32, False),
+        ("c3_trained_jitter_64p64", "trained", 43, 256, 1021, 64, 64, True),
+    ]
+    for name, kind, seed, wh, stride, ns, us, training in cases:
+        sd = syn.synthetic_state_dict(kind, seed)
+        o, d = syn.pinhole_rays(syn.orbit_pose(30.0 if kind == "trained" else 0.0), wh, wh)
+        sel = torch.arange(0, o.shape[0], stride)
+        ro, rd = o[sel].contiguous(), d[sel].contiguous()
+        jitter = None
+        if training:
+            torch.manual_seed(1234)
+            jitter = torch.rand(ro.shape[0], ns)        # the reference's first rand draw (:162)
+        bg = None
+        out_ref = pack(ref_run(ref_nsr, sd, ro, rd, ns, us, 1.6, training, 1234 if training else None, bg))
+        out_orc = pack(OracleNSR(sd).run(ro, rd, ns, 1.6, us, bg, jitter=jitter))
+        worst = compare(out_ref, out_orc, name)
+        assert worst < 2e-5, f"oracle restatement disagrees with the reference on {name}: {worst}"
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), rays_o=ro.numpy(), rays_d=rd.numpy(),
+                            jitter=np.zeros(0, np.float32) if jitter is None else jitter.numpy(),
+                            num_steps=ns, upsample_steps=us, bound=np.float32(1.6), kind=kind, seed=seed,
+                            state_checksum=syn.state_checksum(sd), **out_ref)
+        print(f"wrote {name}.npz  rays={ro.shape[0]} wsum mean={out_ref['weight_sum'].mean():.4f}")
+
+    # hash-encoder fixture through the reference's own HashEncoder.forward wrapper
+    sd = syn.synthetic_state_dict("trained", 43)
+    net = ref_nsr.NeRFNetwork()
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(7)
+    x = (torch.rand(768, 3, generator=g) * 2 - 1) * 1.6
+    x[:8] = torch.tensor([[1.6, 1.6, 1.6], [-1.6, -1.6, -1.6], [0, 0, 0], [1.6, -1.6, 0.0],
+                          [1.7, 0, 0], [0, -1.61, 0], [0.1, 0.2, 0.3], [1.6, 0, 1.5999999]])
+    with torch.no_grad():
+        feats = net.encoder(x, 1.6)
+        sdf16 = net.forward_sdf(x, 1.6)
+    x01 = (x + 1.6) / (2 * 1.6)
+    _, ids = ohg.encode(x01, sd["encoder.embeddings"], sd["encoder.offsets"], net.encoder.per_level_scale, want_ids=True)
+    np.savez_compressed(os.path.join(GOLD, "hashgrid_trained_768.npz"), x=x.numpy(), feats=feats.numpy(),
+                        sdf16=sdf16.numpy(), corner_ids=ids.numpy(), state_checksum=syn.state_checksum(sd),
+                        scales=ohg.level_scales(16, np.log2(net.encoder.per_level_scale), 16))
+    print("wrote hashgrid_trained_768.npz")
+
+
+if __name__ == "__main__":
+    main()
