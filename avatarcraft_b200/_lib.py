@@ -1,0 +1,115 @@
+"""ctypes binding of libavatarcraft_b200.so (the C ABI declared in include/avatarcraft_b200.h).
+
+The library is the product: there is NO fallback.  If it is missing or fails to load, every
+operator raises -- a CPU or eager-torch path here would void the parity claims.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libavatarcraft_b200.so")
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
+              "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+
+AC_OK, AC_E_INVALID_ARG, AC_E_UNSUPPORTED, AC_E_CUDA, AC_E_WORKSPACE = 0, -1, -2, -3, -4
+MLP_BLOB_FLOATS = 9296
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_PKG, "csrc", s) for s in SOURCES]
+    deps = srcs + [os.path.join(_PKG, "csrc", h) for h in os.listdir(os.path.join(_PKG, "csrc")) if h.endswith(".cuh")]
+    deps.append(os.path.join(_ROOT, "include", "avatarcraft_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class NsrModel(ctypes.Structure):
+    _fields_ = [("embeddings", ctypes.c_void_p), ("offsets", ctypes.c_void_p), ("mlp_blob", ctypes.c_void_p),
+                ("variance", ctypes.c_void_p), ("log2_per_level_scale", ctypes.c_float),
+                ("base_resolution", ctypes.c_uint32)]
+
+
+class NsrRenderArgs(ctypes.Structure):
+    _fields_ = [("rays_o", ctypes.c_void_p), ("rays_d", ctypes.c_void_p),
+                ("bg_color", ctypes.c_void_p), ("jitter", ctypes.c_void_p), ("alpha_mask", ctypes.c_void_p),
+                ("n_rays", ctypes.c_uint32), ("num_steps", ctypes.c_uint32), ("upsample_steps", ctypes.c_uint32),
+                ("eikonal_segment", ctypes.c_uint32),
+                ("bound", ctypes.c_float), ("cos_anneal_ratio", ctypes.c_float), ("normal_epsilon_ratio", ctypes.c_float),
+                ("rgb", ctypes.c_void_p), ("depth", ctypes.c_void_p), ("weight_sum", ctypes.c_void_p),
+                ("normal", ctypes.c_void_p),
+                ("weights", ctypes.c_void_p), ("pts_color", ctypes.c_void_p), ("pts_alpha", ctypes.c_void_p),
+                ("z_vals", ctypes.c_void_p),
+                ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64)]
+
+
+_V, _U32, _F, _I = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int
+_SIGNATURES = {
+    "ac_version": (ctypes.c_char_p, []),
+    "ac_last_cuda_error": (ctypes.c_char_p, []),
+    "ac_launch_count": (ctypes.c_uint64, []),
+    "ac_hash_encode_forward": (_I, [_V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
+    "ac_hash_encode_backward": (_I, [_V, _V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
+    "ac_hash_level_scales": (_I, [_V, _U32, _F, _U32, _V]),
+    "ac_nsr_pack_mlp": (_I, [_V] * 13 + [_V]),
+    "ac_nsr_forward_sdf": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V]),
+    "ac_nsr_forward_color": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _U32, _V]),
+    "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
+    "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),
+    "ac_nsr_render": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrRenderArgs), _V]),
+    "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU or eager fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError here = the .so is stale w.r.t. the header
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    """Error convention of the reference ops: failures surface as RuntimeError
+    (TORCH_CHECK / std::runtime_error, encoder/hashencoder/src/hashencoder.cu:16-19,349,364)."""
+    if rc == AC_OK:
+        return
+    reason = {AC_E_INVALID_ARG: "invalid argument", AC_E_UNSUPPORTED: "unsupported D/C combination",
+              AC_E_CUDA: "CUDA error: " + lib().ac_last_cuda_error().decode(),
+              AC_E_WORKSPACE: "workspace too small"}.get(rc, f"error {rc}")
+    raise RuntimeError(f"{what}: {reason}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA fp32/int32 tensor (None -> NULL), with the reference's checks
+    (CHECK_CUDA / CHECK_CONTIGUOUS, hashencoder.cu:414-430)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("tensor must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,453 @@
+// nsr_kernels.cu -- fused Instant-NSR render core for sm_100a and its C ABI.
+//
+// Execution model: ONE WARP OWNS ONE RAY from the box intersection to the composited pixel.
+// All per-ray state (sorted depths, their SDF, CDF scratch) lives in a 2 KB shared-memory
+// slice private to the warp, so the kernel needs a single __syncthreads (after the MLP
+// weights and level table are staged) and otherwise only __syncwarp / shuffles.  The 128
+// section samples of a ray are visited 32 at a time in depth order, which lets the NeuS
+// transmittance be carried across iterations with a 5-step warp-shuffle product scan.
+// Compulsory HBM traffic is 24 B in + 32 B out per ray; the hash table (49 MB) is read
+// through L2/L1 with 8 B gathers.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/avatarcraft_b200.h"
+#include "launch_util.cuh"
+#include "nsr_device.cuh"
+
+using namespace acb;
+
+namespace {
+
+constexpr int kWarps = 8;                 // rays per CTA
+constexpr int kMaxT = 128;
+
+struct RenderParams {
+    const float2* table;
+    const int32_t* offsets;
+    const float* blob;
+    const float* variance;
+    float S;
+    uint32_t H;
+    ac_nsr_render_args a;
+    float* eik_partial;   // [n_rays][2]
+};
+
+__device__ __forceinline__ void stage_model(const float* __restrict__ blob, const int32_t* __restrict__ offsets,
+                                            float S, uint32_t H, float* sw, LevelMeta* lv) {
+    const float4* src = reinterpret_cast<const float4*>(blob);
+    float4* dst = reinterpret_cast<float4*>(sw);
+    for (int i = threadIdx.x; i < BLOB_FLOATS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(offsets, threadIdx.x, S, H, 3);
+    __syncthreads();
+}
+
+constexpr size_t kStageBytes = BLOB_FLOATS * sizeof(float) + kLevels * sizeof(LevelMeta);
+
+__global__ void __launch_bounds__(kWarps * 32) nsr_render_kernel(const RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(sw + BLOB_FLOATS);
+    float* rows = reinterpret_cast<float*>(lv + kLevels);
+    stage_model(p.blob, p.offsets, p.S, p.H, sw, lv);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ray = blockIdx.x * kWarps + warp;
+    if (ray >= p.a.n_rays) return;
+    float* zs = rows + warp * 4 * kMaxT;
+    float* sdfs = zs + kMaxT;
+    float* ta = sdfs + kMaxT;
+    float* tb = ta + kMaxT;
+
+    const float bound = p.a.bound;
+    const float2* __restrict__ table = p.table;
+    Ray r;
+    r.ox = p.a.rays_o[3 * ray + 0]; r.oy = p.a.rays_o[3 * ray + 1]; r.oz = p.a.rays_o[3 * ray + 2];
+    r.dx = p.a.rays_d[3 * ray + 0]; r.dy = p.a.rays_d[3 * ray + 1]; r.dz = p.a.rays_d[3 * ray + 2];
+    float near, far;
+    ray_box(r, bound, near, far);
+    const int N0 = (int)p.a.num_steps;
+    const float span = far - near;
+    const float sample_dist = span / (float)N0;               // keeps the COARSE count (:160)
+
+    // ---- coarse samples (:155-174) and their SDF (:178) ----
+    int T = N0;
+    for (int k = lane; k < N0; k += 32) {
+        float z = near + span * linspace01(k, N0);
+        if (p.a.jitter) z = z + (p.a.jitter[(size_t)ray * N0 + k] - 0.5f) * sample_dist;
+        zs[k] = z;
+        if (p.a.upsample_steps > 0) {
+            float x, y, zz;
+            ray_point(r, z, x, y, zz);
+            float o[1];
+            sdf_point<false>(table, lv, sw, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
+                             clampf(zz, -bound, bound), o);
+            sdfs[k] = o[0];
+        }
+    }
+    __syncwarp();
+
+    // ---- importance rounds (:182-184) ----
+    const int rounds = (int)p.a.upsample_steps / 16;
+    for (int i = 0; i < rounds; ++i) {
+        float z_new; int below, above;
+        importance_round(r, zs, sdfs, ta, tb, T, (float)(64 << i), lane, z_new, below, above);
+        float s_new = 0.0f;
+        const bool last = (i + 1 == rounds);
+        if (!last && lane < 16) {
+            float x, y, zz;
+            ray_point(r, z_new, x, y, zz);
+            float o[1];
+            sdf_point<false>(table, lv, sw, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
+                             clampf(zz, -bound, bound), o);
+            s_new = o[0];
+        }
+        int pos_old[4], pos_new;
+        merge_positions(zs, T, z_new, lane, pos_old, pos_new);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = lane + 32 * q;
+            if (k < T) { ta[pos_old[q]] = zs[k]; tb[pos_old[q]] = sdfs[k]; }
+        }
+        if (lane < 16) { ta[pos_new] = z_new; tb[pos_new] = s_new; }
+        __syncwarp();
+        float* t0 = zs; zs = ta; ta = t0;
+        float* t1 = sdfs; sdfs = tb; tb = t1;
+        T += 16;
+    }
+
+    // ---- render core (:186-299): 32 section samples per iteration, in depth order ----
+    const float inv_s = clampf(expf(p.variance[0] * 10.0f), 1e-6f, 1e6f);
+    const float eps = 0.005f * (1.0f - p.a.normal_epsilon_ratio);
+    const float car = p.a.cos_anneal_ratio;
+    float carry = 1.0f;                    // transmittance entering this block of 32 samples
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_nx = 0.f, acc_ny = 0.f, acc_nz = 0.f;
+    float acc_w = 0.f, acc_d = 0.f, eik_num = 0.f, eik_den = 0.f;
+    for (int k0 = 0; k0 < T; k0 += 32) {
+        const int k = k0 + lane;
+        const bool live = k < T;
+        float alpha = 0.f, col[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f}, zk = 0.f;
+        if (live) {
+            zk = zs[k];
+            const float delta = k < T - 1 ? zs[k + 1] - zk : sample_dist;
+            const float zmid = k < T - 1 ? zk + 0.5f * delta : zk;
+            float px, py, pz;
+            ray_point(r, zmid, px, py, pz);
+            px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
+            float o16[16];
+            sdf_point<true>(table, lv, sw, bound, px, py, pz, o16);
+            // central differences (:687-704); every shifted point is re-clamped
+            float g[3];
+#pragma unroll 1
+            for (int ax = 0; ax < 3; ++ax) {
+                float f2[2];
+#pragma unroll 1
+                for (int sg = 0; sg < 2; ++sg) {
+                    const float e = sg == 0 ? eps : -eps;
+                    const float qx = ax == 0 ? clampf(px + e, -bound, bound) : px;
+                    const float qy = ax == 1 ? clampf(py + e, -bound, bound) : py;
+                    const float qz = ax == 2 ? clampf(pz + e, -bound, bound) : pz;
+                    float o[1];
+                    sdf_point<false>(table, lv, sw, bound, qx, qy, qz, o);
+                    f2[sg] = o[0];
+                }
+                g[ax] = 0.5f * (f2[0] - f2[1]) / eps;
+            }
+            const float gn = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+            const float inv = 1e-5f + gn;
+            nrm[0] = g[0] / inv; nrm[1] = g[1] / inv; nrm[2] = g[2] / inv;
+            float cin[kColInPad];
+            cin[0] = px; cin[1] = py; cin[2] = pz; cin[3] = nrm[0]; cin[4] = nrm[1]; cin[5] = nrm[2];
+#pragma unroll
+            for (int q = 0; q < 15; ++q) cin[6 + q] = o16[1 + q];
+            cin[21] = cin[22] = cin[23] = 0.f;
+            color_mlp(sw, cin, col);
+            // NeuS alpha (:221-243)
+            const float cosv = r.dx * nrm[0] + r.dy * nrm[1] + r.dz * nrm[2];
+            const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);
+            const float hs = it * delta * 0.5f;
+            const float c0 = sigmoidf((o16[0] - hs) * inv_s), c1 = sigmoidf((o16[0] + hs) * inv_s);
+            alpha = clampf((c0 - c1 + 1e-5f) / (c0 + 1e-5f), 0.0f, 1.0f);
+            if (p.a.alpha_mask) alpha = alpha * p.a.alpha_mask[(size_t)ray * T + k];
+            // eikonal terms (:265-272)
+            const float pn = sqrtf(px * px + py * py + pz * pz);
+            if (pn < 1.2f) { eik_num += (gn - 1.0f) * (gn - 1.0f); eik_den += 1.0f; }
+        }
+        float blk;
+        const float tr = warp_excl_prod(live ? (1.0f - alpha + 1e-7f) : 1.0f, lane, blk) * carry;
+        carry *= blk;
+        const float w = alpha * tr;
+        if (live) {
+            acc_r += w * col[0]; acc_g += w * col[1]; acc_b += w * col[2];
+            acc_nx += w * nrm[0]; acc_ny += w * nrm[1]; acc_nz += w * nrm[2];
+            acc_w += w;
+            acc_d += w * clampf((zk - near) / span, 0.0f, 1.0f);
+            const size_t s = (size_t)ray * T + k;
+            if (p.a.weights) p.a.weights[s] = w;
+            if (p.a.pts_alpha) p.a.pts_alpha[s] = alpha;
+            if (p.a.z_vals) p.a.z_vals[s] = zk;
+            if (p.a.pts_color) { p.a.pts_color[3 * s] = col[0]; p.a.pts_color[3 * s + 1] = col[1]; p.a.pts_color[3 * s + 2] = col[2]; }
+        }
+    }
+    acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
+    acc_nx = warp_sum(acc_nx); acc_ny = warp_sum(acc_ny); acc_nz = warp_sum(acc_nz);
+    acc_w = warp_sum(acc_w); acc_d = warp_sum(acc_d);
+    eik_num = warp_sum(eik_num); eik_den = warp_sum(eik_den);
+    if (lane == 0) {
+        float bg[3] = {1.f, 1.f, 1.f};
+        if (p.a.bg_color) { bg[0] = p.a.bg_color[3 * ray]; bg[1] = p.a.bg_color[3 * ray + 1]; bg[2] = p.a.bg_color[3 * ray + 2]; }
+        const float rest = 1.0f - acc_w;
+        p.a.rgb[3 * ray + 0] = acc_r + rest * bg[0];
+        p.a.rgb[3 * ray + 1] = acc_g + rest * bg[1];
+        p.a.rgb[3 * ray + 2] = acc_b + rest * bg[2];
+        p.a.depth[ray] = acc_d;
+        p.a.weight_sum[ray] = acc_w;
+        p.a.normal[3 * ray + 0] = acc_nx; p.a.normal[3 * ray + 1] = acc_ny; p.a.normal[3 * ray + 2] = acc_nz;
+        p.eik_partial[2 * ray + 0] = eik_num;
+        p.eik_partial[2 * ray + 1] = eik_den;
+    }
+}
+
+// Deterministic reduction of the per-ray eikonal partials (:270-272), one block per segment.
+__global__ void __launch_bounds__(1024) eikonal_reduce_kernel(const float* __restrict__ partial, uint32_t n, uint32_t seg, float* out) {
+    __shared__ double s_num[32], s_den[32];
+    double num = 0.0, den = 0.0;
+    const uint32_t lo = blockIdx.x * seg, hi = min(n, lo + seg);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { num += partial[2 * i]; den += partial[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+    if ((threadIdx.x & 31) == 0) { s_num[threadIdx.x >> 5] = num; s_den[threadIdx.x >> 5] = den; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        num = s_num[threadIdx.x]; den = s_den[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+        if (threadIdx.x == 0) out[blockIdx.x] = (float)num / ((float)den + 1e-5f);
+    }
+}
+
+// ---- flat-point queries (NeRFNetwork.forward_sdf / forward_color / gradient) ----
+__global__ void __launch_bounds__(256) forward_sdf_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                          const float* __restrict__ blob, float S, uint32_t H,
+                                                          const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(sw + BLOB_FLOATS);
+    stage_model(blob, offsets, S, H, sw, lv);
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float o16[16];
+        sdf_point<true>(table, lv, sw, bound, x[3 * b], x[3 * b + 1], x[3 * b + 2], o16);
+        float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) fd_gradient_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                          const float* __restrict__ blob, float S, uint32_t H,
+                                                          const float* __restrict__ x, float* __restrict__ grad, uint32_t B,
+                                                          float bound, float eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(sw + BLOB_FLOATS);
+    stage_model(blob, offsets, S, H, sw, lv);
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const float px = x[3 * b], py = x[3 * b + 1], pz = x[3 * b + 2];
+#pragma unroll 1
+        for (int ax = 0; ax < 3; ++ax) {
+            float f2[2];
+#pragma unroll 1
+            for (int sg = 0; sg < 2; ++sg) {
+                const float e = sg == 0 ? eps : -eps;
+                float o[1];
+                sdf_point<false>(table, lv, sw, bound, clampf(ax == 0 ? px + e : px, -bound, bound),
+                                 clampf(ax == 1 ? py + e : py, -bound, bound), clampf(ax == 2 ? pz + e : pz, -bound, bound), o);
+                f2[sg] = o[0];
+            }
+            grad[3 * (size_t)b + ax] = 0.5f * (f2[0] - f2[1]) / eps;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) forward_color_kernel(const float* __restrict__ blob, const float* __restrict__ x,
+                                                            const float* __restrict__ n, const float* __restrict__ feat,
+                                                            float* __restrict__ rgb, uint32_t B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    const float4* src = reinterpret_cast<const float4*>(blob);
+    for (int i = threadIdx.x; i < BLOB_FLOATS / 4; i += blockDim.x) reinterpret_cast<float4*>(sw)[i] = __ldg(src + i);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;   // one point per thread: a grid-stride loop here
+    if (b >= B) return;                                         // lets nvcc hoist the weight rows into registers
+    float cin[kColInPad], c[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { cin[q] = x[3 * (size_t)b + q]; cin[3 + q] = n[3 * (size_t)b + q]; cin[21 + q] = 0.f; }
+#pragma unroll
+    for (int q = 0; q < 15; ++q) cin[6 + q] = feat[15 * (size_t)b + q];
+    color_mlp(sw, cin, c);
+    rgb[3 * (size_t)b] = c[0]; rgb[3 * (size_t)b + 1] = c[1]; rgb[3 * (size_t)b + 2] = c[2];
+}
+
+// weight-norm fold + pack: one warp per output row, w = v * (g / ||v||) (torch._weight_norm).
+struct PackLayer { const float* g; const float* v; const float* b; int rows, cols; int w_off, w_stride, w_transposed, b_off; };
+struct PackArgs { PackLayer layer[5]; float* blob; };
+
+__global__ void __launch_bounds__(256) pack_mlp_kernel(const PackArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int row = warp, li = 0;
+    while (li < 5 && row >= a.layer[li].rows) { row -= a.layer[li].rows; ++li; }
+    if (li >= 5) return;
+    const PackLayer L = a.layer[li];
+    float ss = 0.f;
+    for (int c = lane; c < L.cols; c += 32) { const float v = L.v[row * L.cols + c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float sc = L.g[row] / sqrtf(ss);
+    for (int c = lane; c < L.cols; c += 32) {
+        const float w = L.v[row * L.cols + c] * sc;
+        const int idx = L.w_transposed ? (L.w_off + c * L.w_stride + row) : (L.w_off + row * L.w_stride + c);
+        a.blob[idx] = w;
+    }
+    if (L.b && lane == 0) a.blob[L.b_off + row] = L.b[row];
+}
+
+__global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                             const float* __restrict__ z, const float* __restrict__ sdf, uint32_t n,
+                                                             uint32_t T, float inv_s, float* z_new_out, int32_t* bins, float* z_out,
+                                                             int32_t* order) {
+    __shared__ float rows[kWarps * 4 * kMaxT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ray = blockIdx.x * kWarps + warp;
+    if (ray >= n) return;
+    float* zs = rows + warp * 4 * kMaxT; float* sdfs = zs + kMaxT; float* ta = sdfs + kMaxT; float* tb = ta + kMaxT;
+    for (uint32_t k = lane; k < T; k += 32) { zs[k] = z[(size_t)ray * T + k]; sdfs[k] = sdf[(size_t)ray * T + k]; }
+    __syncwarp();
+    Ray r;
+    r.ox = rays_o[3 * ray]; r.oy = rays_o[3 * ray + 1]; r.oz = rays_o[3 * ray + 2];
+    r.dx = rays_d[3 * ray]; r.dy = rays_d[3 * ray + 1]; r.dz = rays_d[3 * ray + 2];
+    float zn; int below, above;
+    importance_round(r, zs, sdfs, ta, tb, (int)T, inv_s, lane, zn, below, above);
+    int pos_old[4], pos_new;
+    merge_positions(zs, (int)T, zn, lane, pos_old, pos_new);
+    const size_t ob = (size_t)ray * (T + 16);
+    if (lane < 16) {
+        z_new_out[(size_t)ray * 16 + lane] = zn;
+        bins[((size_t)ray * 16 + lane) * 2] = below; bins[((size_t)ray * 16 + lane) * 2 + 1] = above;
+        z_out[ob + pos_new] = zn; order[ob + pos_new] = (int32_t)T + lane;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t k = lane + 32 * q;
+        if (k < T) { z_out[ob + pos_old[q]] = zs[k]; order[ob + pos_old[q]] = (int32_t)k; }
+    }
+}
+
+int grid_for(uint32_t B, int block, int per_sm) {
+    int sms = acb::sm_count();
+    long want = ((long)B + block - 1) / block;
+    long cap = (long)sms * per_sm;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ac_nsr_pack_mlp(const float* sdf0_g, const float* sdf0_v, const float* sdf0_b, const float* sdf1_g,
+                    const float* sdf1_v, const float* sdf1_b, const float* col0_g, const float* col0_v,
+                    const float* col1_g, const float* col1_v, const float* col2_g, const float* col2_v,
+                    float* blob, void* stream) {
+    if (!sdf0_g || !sdf0_v || !sdf0_b || !sdf1_g || !sdf1_v || !sdf1_b || !col0_g || !col0_v || !col1_g ||
+        !col1_v || !col2_g || !col2_v || !blob)
+        return AC_E_INVALID_ARG;
+    PackArgs a;
+    a.layer[0] = {sdf0_g, sdf0_v, sdf0_b, 64, 35, OFF_W0, kSdfInPad, 0, OFF_B0};
+    a.layer[1] = {sdf1_g, sdf1_v, sdf1_b, 16, 64, OFF_W1T, 16, 1, OFF_B1};
+    a.layer[2] = {col0_g, col0_v, nullptr, 64, 21, OFF_C0, kColInPad, 0, 0};
+    a.layer[3] = {col1_g, col1_v, nullptr, 64, 64, OFF_C1, kHidden, 0, 0};
+    a.layer[4] = {col2_g, col2_v, nullptr, 3, 64, OFF_C2T, 4, 1, 0};
+    a.blob = blob;
+    // 211 weight rows -> 211 warps; padding columns are zeroed by the memset first.
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(blob, 0, BLOB_FLOATS * sizeof(float), st) != cudaSuccess) return acb::cuda_fail();
+    pack_mlp_kernel<<<(211 * 32 + 255) / 256, 256, 0, st>>>(a);
+    return acb::launched();
+}
+
+static int check_model(const ac_nsr_model* m) {
+    if (!m || !m->embeddings || !m->offsets || !m->mlp_blob) return AC_E_INVALID_ARG;
+    return AC_OK;
+}
+
+int ac_nsr_forward_sdf(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, void* stream) {
+    if (check_model(m) || !x || !out) return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(forward_sdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes); attr = true; }
+    forward_sdf_kernel<<<grid_for(B, 256, 4), 256, kStageBytes, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
+        m->base_resolution, x, out, B, bound);
+    return acb::launched();
+}
+
+int ac_nsr_fd_gradient(const ac_nsr_model* m, const float* x, float* grad, uint32_t B, float bound, float epsilon,
+                       void* stream) {
+    if (check_model(m) || !x || !grad) return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(fd_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes); attr = true; }
+    fd_gradient_kernel<<<grid_for(B, 256, 4), 256, kStageBytes, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
+        m->base_resolution, x, grad, B, bound, epsilon);
+    return acb::launched();
+}
+
+int ac_nsr_forward_color(const ac_nsr_model* m, const float* x, const float* normal, const float* geo_feat, float* rgb,
+                         uint32_t B, void* stream) {
+    if (!m || !m->mlp_blob || !x || !normal || !geo_feat || !rgb) return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    forward_color_kernel<<<(B + 255) / 256, 256, BLOB_FLOATS * sizeof(float), (cudaStream_t)stream>>>(
+        m->mlp_blob, x, normal, geo_feat, rgb, B);
+    return acb::launched();
+}
+
+uint64_t ac_nsr_render_workspace_bytes(uint32_t n_rays) { return (uint64_t)n_rays * 2 * sizeof(float) + 16; }
+
+int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stream) {
+    if (check_model(m) || !m->variance || !a) return AC_E_INVALID_ARG;
+    if (!a->rays_o || !a->rays_d || !a->rgb || !a->depth || !a->weight_sum || !a->normal || !a->eikonal || !a->workspace)
+        return AC_E_INVALID_ARG;
+    const uint32_t T = a->num_steps + a->upsample_steps;
+    if (a->num_steps < 2 || a->upsample_steps % 16 != 0 || T > (uint32_t)kMaxT) return AC_E_INVALID_ARG;
+    if (a->workspace_bytes < ac_nsr_render_workspace_bytes(a->n_rays)) return AC_E_WORKSPACE;
+    if (a->n_rays == 0) return AC_OK;
+    RenderParams p;
+    p.table = reinterpret_cast<const float2*>(m->embeddings);
+    p.offsets = m->offsets; p.blob = m->mlp_blob; p.variance = m->variance;
+    p.S = m->log2_per_level_scale; p.H = m->base_resolution;
+    p.a = *a;
+    p.eik_partial = reinterpret_cast<float*>(a->workspace);
+    const size_t smem = kStageBytes + (size_t)kWarps * 4 * kMaxT * sizeof(float);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(nsr_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    cudaStream_t st = (cudaStream_t)stream;
+    nsr_render_kernel<<<(a->n_rays + kWarps - 1) / kWarps, kWarps * 32, smem, st>>>(p);
+    int rc = acb::launched();
+    if (rc) return rc;
+    const uint32_t seg = a->eikonal_segment ? a->eikonal_segment : a->n_rays;
+    eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(p.eik_partial, a->n_rays, seg, a->eikonal);
+    return acb::launched();
+}
+
+int ac_nsr_debug_upsample(const float* rays_o, const float* rays_d, const float* z, const float* sdf, uint32_t n_rays,
+                          uint32_t T, float inv_s, float* z_new, int32_t* bins, float* z_out, int32_t* order, void* stream) {
+    if (!rays_o || !rays_d || !z || !sdf || !z_new || !bins || !z_out || !order) return AC_E_INVALID_ARG;
+    if (T < 2 || T + 16 > (uint32_t)kMaxT) return AC_E_INVALID_ARG;
+    if (n_rays == 0) return AC_OK;
+    debug_upsample_kernel<<<(n_rays + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, z, sdf, n_rays, T, inv_s, z_new, bins, z_out, order);
+    return acb::launched();
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+"""Instant-NSR model with the reference's API and checkpoint layout
+(models/instant_nsr.py: NeRFRenderer :90-475, NeRFNetwork :478-718), evaluated by the fused
+sm_100a kernels of libavatarcraft_b200.so.
+
+What differs from the reference, by design:
+  * `run` is ONE kernel launch per ray batch (plus a one-block eikonal reduction) instead of
+    ~250 eager launches; it returns the same 10-tuple.
+  * there is no CPU path: tensors must live on a CUDA device.
+State-dict keys/shapes are identical, so reference checkpoints load as is.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..encoder import get_encoder
+from ..utils.constant import DEFAULT_GEO_THRESH
+
+
+def near_far_from_bound(rays_o, rays_d, bound, type='cube'):
+    """Host/torch helper kept for API parity (models/instant_nsr.py:58-77); the fused kernel
+    computes the same intersection per ray in registers."""
+    radius = rays_o.norm(dim=-1, keepdim=True)
+    if type == 'sphere':
+        return radius - bound, radius + bound
+    t_lo = (-bound - rays_o) / (rays_d + 1e-15)
+    t_hi = (bound - rays_o) / (rays_d + 1e-15)
+    near = torch.minimum(t_lo, t_hi).max(dim=-1, keepdim=True)[0].clamp(min=0.05)
+    far = torch.maximum(t_lo, t_hi).min(dim=-1, keepdim=True)[0]
+    return near, far
+
+
+class SingleVarianceNetwork(nn.Module):
+    """exp(10 * variance), one learnable scalar (models/instant_nsr.py:720-726)."""
+
+    def __init__(self, init_val):
+        super().__init__()
+        self.register_parameter('variance', nn.Parameter(torch.tensor(init_val)))
+
+    def forward(self, x):
+        return torch.ones([len(x), 1], device=self.variance.device) * torch.exp(self.variance * 10.0)
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, cuda_ray=False, curvature_loss=False):
+        super().__init__()
+        if cuda_ray:
+            raise NotImplementedError("cuda_ray density-grid marching is dead code in the reference "
+                                      "(run_cuda is undefined, models/instant_nsr.py:362-363)")
+        if curvature_loss:
+            raise NotImplementedError("curvature_loss is never enabled by any reference entry point")
+        self.cuda_ray = cuda_ray
+        self.curvature_loss = curvature_loss
+
+    # ---- the fused render core -----------------------------------------------------------
+    def run(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio=1.0,
+            normal_epsilon_ratio=1.0, render_can=True, verts=None, faces=None, Ts=None,
+            perturb_overwrite: bool = False, use_mesh_guide: bool = True, jitter=None, per_sample_outputs=True,
+            eikonal_segment=0):
+        """Same contract as the reference (models/instant_nsr.py:133-299): rays [B=1,N,3] ->
+        (depth [1,N], weights [N,T], weights_sum [N,1], image [1,N,3], normal_map [N,3],
+         gradient_error, curvature_error, color [N,T,3], alpha [N,T], z_vals [N,T]).
+        `jitter` ([N,num_steps] in [0,1)) overrides the training-time torch.rand draw (:162);
+        `per_sample_outputs=False` skips the four [N,T,...] stores (they are then None);
+        `eikonal_segment=k` returns one eikonal mean per k consecutive rays (a [ceil(N/k)] tensor)."""
+        if not render_can:
+            raise NotImplementedError("warped (render_can=False) rendering is not wired yet")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self._needs_grad():
+            raise NotImplementedError("backward of the fused render core is not implemented yet")
+        B, N = rays_o.shape[:2]
+        rays_o = rays_o.reshape(-1, 3).float().contiguous()
+        rays_d = rays_d.reshape(-1, 3).float().contiguous()
+        n = rays_o.shape[0]
+        dev = rays_o.device
+        T = num_steps + upsample_steps
+        if self.training and perturb_overwrite and jitter is None:
+            jitter = torch.rand(n, num_steps, device=dev)
+        if jitter is not None:
+            jitter = jitter.to(dev, torch.float32).contiguous()
+        if bg_color is not None:
+            bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
+        model = self._device_model()
+        f32 = dict(device=dev, dtype=torch.float32)
+        rgb = torch.empty(n, 3, **f32); depth = torch.empty(n, **f32)
+        wsum = torch.empty(n, **f32); normal = torch.empty(n, 3, **f32)
+        n_seg = 1 if not eikonal_segment else (n + eikonal_segment - 1) // eikonal_segment
+        eik = torch.empty(n_seg, **f32)
+        weights = color = alpha = z_vals = None
+        if per_sample_outputs:
+            weights = torch.empty(n, T, **f32); color = torch.empty(n, T, 3, **f32)
+            alpha = torch.empty(n, T, **f32); z_vals = torch.empty(n, T, **f32)
+        L = _lib.lib()
+        ws_bytes = int(L.ac_nsr_render_workspace_bytes(n))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        a = _lib.NsrRenderArgs(
+            rays_o=rays_o.data_ptr(), rays_d=rays_d.data_ptr(),
+            bg_color=None if bg_color is None else bg_color.data_ptr(),
+            jitter=None if jitter is None else jitter.data_ptr(), alpha_mask=None,
+            n_rays=n, num_steps=num_steps, upsample_steps=upsample_steps, eikonal_segment=int(eikonal_segment),
+            bound=float(bound),
+            cos_anneal_ratio=float(cos_anneal_ratio), normal_epsilon_ratio=float(normal_epsilon_ratio),
+            rgb=rgb.data_ptr(), depth=depth.data_ptr(), weight_sum=wsum.data_ptr(), normal=normal.data_ptr(),
+            weights=None if weights is None else weights.data_ptr(),
+            pts_color=None if color is None else color.data_ptr(),
+            pts_alpha=None if alpha is None else alpha.data_ptr(),
+            z_vals=None if z_vals is None else z_vals.data_ptr(),
+            eikonal=eik.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws_bytes)
+        _lib.check(L.ac_nsr_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "ac_nsr_render")
+        return (depth.reshape(B, N), weights, wsum.reshape(n, 1), rgb.reshape(B, N, 3), normal,
+                eik.reshape(()) if n_seg == 1 else eik, 0.0,
+                color, alpha, z_vals)
+
+    def _needs_grad(self):
+        return getattr(self, "_grad_render", False)
+
+    def render(self, rays_o, rays_d, num_steps, bound, upsample_steps, staged=False, max_ray_batch=4096, bg_color=None,
+               cos_anneal_ratio=1.0, normal_epsilon_ratio=1.0, render_can=True, verts=None, faces=None, Ts=None,
+               perturb: bool = False, use_mesh_guide: bool = True, **kwargs):
+        """Result dict with the reference's ten keys (models/instant_nsr.py:358-408)."""
+        depth, weights, weight_sum, image, normal, gradient_error, curvature_error, pts_color, pts_alpha, z_vals = \
+            self.run(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio, normal_epsilon_ratio,
+                     render_can=render_can, verts=verts, faces=faces, Ts=Ts, perturb_overwrite=perturb,
+                     use_mesh_guide=use_mesh_guide, **kwargs)
+        return {'depth': depth, 'weights': weights, 'weight_sum': weight_sum, 'rgb': image, 'normal': normal,
+                'gradient_error': gradient_error, 'curvature_error': curvature_error, 'pts_color': pts_color,
+                'pts_alpha': pts_alpha, 'z_vals': z_vals}
+
+
+class NeRFNetwork(NeRFRenderer):
+    """Hash grid -> SDF MLP (35-64-16, softplus100, weight-norm, geometric init) -> colour MLP
+    (21-64-64-3) + NeuS variance.  Constructor arguments as in models/instant_nsr.py:479-493."""
+
+    def __init__(self, encoding="hashgrid", encoding_dir="sphere_harmonics", num_layers=2, hidden_dim=64,
+                 geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, bound=1.0, geometric_init=True,
+                 weight_norm=True, cuda_ray=False, include_input=True, curvature_loss=False, use_viewdirs=False):
+        super().__init__(cuda_ray, curvature_loss)
+        if (encoding not in ("hashgrid", "hash") or num_layers != 2 or hidden_dim != 64 or geo_feat_dim != 15
+                or num_layers_color != 3 or hidden_dim_color != 64 or not weight_norm or not include_input or use_viewdirs):
+            raise NotImplementedError("the fused kernels are specialised for the reference's only configuration "
+                                      "(models/instant_nsr.py:479-519)")
+        self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
+        self.include_input, self.use_viewdirs = include_input, use_viewdirs
+        self.num_layers_color, self.hidden_dim_color = num_layers_color, hidden_dim_color
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.encoder, self.in_dim = get_encoder(encoding, {
+            "in_dim": 3, "freq_multires": 6, "hash_num_levels": 16, "hash_level_dim": 2, "hash_base_resolution": 16,
+            "hash_per_level_scale": 1.3819, "hash_log2_hashmap_size": 19, "hash_desired_resolution": 2048})
+        dims = [self.in_dim + 3, hidden_dim, 1 + geo_feat_dim]
+        sdf_net = []
+        for l in range(2):
+            lin = nn.Linear(dims[l], dims[l + 1])
+            if geometric_init:               # SAL/IDR-style sphere init (models/instant_nsr.py:537-553)
+                nn.init.constant_(lin.bias, 0.0)
+                if l == 1:
+                    nn.init.normal_(lin.weight, mean=np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                else:
+                    nn.init.normal_(lin.weight[:, :3], 0.0, np.sqrt(2) / np.sqrt(dims[l + 1]))
+                    nn.init.constant_(lin.weight[:, 3:], 0.0)
+            sdf_net.append(nn.utils.weight_norm(lin))
+        self.sdf_net = nn.ModuleList(sdf_net)
+        self.encoder_dir = None
+        self.in_dim_color = geo_feat_dim + 6
+        cdims = [self.in_dim_color, hidden_dim_color, hidden_dim_color, 3]
+        self.color_net = nn.ModuleList([nn.utils.weight_norm(nn.Linear(cdims[l], cdims[l + 1], bias=False)) for l in range(3)])
+        self.deviation_net = SingleVarianceNetwork(0.3)
+        self.activation = nn.Softplus(beta=100)
+        self._blob = None
+        self._blob_key = None
+
+    # ---- packed parameters for the kernels -----------------------------------------------
+    def _device_model(self):
+        """ac_nsr_model view of the parameters; the weight-norm fold + pack kernel re-runs only
+        when a parameter changed (tensor version counters) or moved."""
+        ps = [self.sdf_net[0].weight_g, self.sdf_net[0].weight_v, self.sdf_net[0].bias,
+              self.sdf_net[1].weight_g, self.sdf_net[1].weight_v, self.sdf_net[1].bias,
+              self.color_net[0].weight_g, self.color_net[0].weight_v, self.color_net[1].weight_g,
+              self.color_net[1].weight_v, self.color_net[2].weight_g, self.color_net[2].weight_v]
+        emb = self.encoder.embeddings
+        if not emb.is_cuda:
+            raise RuntimeError("avatarcraft_b200 has no CPU path: move the model to a CUDA device")
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._blob is None or self._blob.device != emb.device or key != self._blob_key:
+            if self._blob is None or self._blob.device != emb.device:
+                self._blob = torch.empty(_lib.MLP_BLOB_FLOATS, device=emb.device, dtype=torch.float32)
+            args = [_lib.ptr(p.detach().contiguous()) for p in ps]
+            _lib.check(_lib.lib().ac_nsr_pack_mlp(*args, _lib.ptr(self._blob), _lib.stream_ptr()), "ac_nsr_pack_mlp")
+            self._blob_key = key
+        return _lib.NsrModel(embeddings=emb.data_ptr(), offsets=self.encoder.offsets.data_ptr(),
+                             mlp_blob=self._blob.data_ptr(), variance=self.deviation_net.variance.data_ptr(),
+                             log2_per_level_scale=float(np.log2(self.encoder.per_level_scale)),
+                             base_resolution=int(self.encoder.base_resolution))
+
+    # ---- point queries (reference: forward_sdf :627, forward_color :644, density :669, gradient :683) ----
+    @torch.no_grad()
+    def forward_sdf(self, x, bound):
+        x = x.reshape(-1, 3).float().contiguous()
+        out = torch.empty(x.shape[0], 16, device=x.device, dtype=torch.float32)
+        m = self._device_model()
+        _lib.check(_lib.lib().ac_nsr_forward_sdf(ctypes.byref(m), _lib.ptr(x), _lib.ptr(out), x.shape[0], float(bound),
+                                                 _lib.stream_ptr()), "ac_nsr_forward_sdf")
+        return out
+
+    @torch.no_grad()
+    def forward_color(self, x, d, n, geo_feat, bound):
+        x, n, geo_feat = (t.reshape(-1, t.shape[-1]).float().contiguous() for t in (x, n, geo_feat))
+        rgb = torch.empty(x.shape[0], 3, device=x.device, dtype=torch.float32)
+        m = self._device_model()
+        _lib.check(_lib.lib().ac_nsr_forward_color(ctypes.byref(m), _lib.ptr(x), _lib.ptr(n), _lib.ptr(geo_feat),
+                                                   _lib.ptr(rgb), x.shape[0], _lib.stream_ptr()), "ac_nsr_forward_color")
+        return rgb
+
+    def forward_variance(self):
+        return self.deviation_net(torch.zeros([1, 3]))[:, :1].clip(1e-6, 1e6)
+
+    def density(self, x, bound):
+        return self.forward_sdf(x, bound)[..., 0]
+
+    @torch.no_grad()
+    def finite_difference_normals_approximator(self, x, bound, epsilon=0.0005):
+        x = x.reshape(-1, 3).float().contiguous()
+        g = torch.empty_like(x)
+        m = self._device_model()
+        _lib.check(_lib.lib().ac_nsr_fd_gradient(ctypes.byref(m), _lib.ptr(x), _lib.ptr(g), x.shape[0], float(bound),
+                                                 float(epsilon), _lib.stream_ptr()), "ac_nsr_fd_gradient")
+        return g
+
+    def gradient(self, x, bound, epsilon=0.0005):
+        return self.finite_difference_normals_approximator(x, bound, epsilon)

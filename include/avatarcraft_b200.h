@@ -1,0 +1,149 @@
+/*
+ * avatarcraft_b200.h -- C ABI of libavatarcraft_b200.so (sm_100a).
+ *
+ * The drop-in boundary for the AvatarCraft hot path: every entry point takes plain
+ * device pointers, sizes and a CUDA stream (passed as void* = cudaStream_t); no torch or
+ * C++ types cross it.  The caller owns and allocates every buffer (as the reference's
+ * Python wrappers do, encoder/hashencoder/hashgrid.py:31-38,59-66); the library never
+ * allocates device memory.  Every function returns 0 on success or a negative AC_E_* code
+ * and never synchronises the stream.  All kernels are launched on `stream` and are
+ * CUDA-graph capturable.  Citations are file:line inside the reference repository
+ * (songrise/AvatarCraft @ 190a4bb).
+ */
+#ifndef AVATARCRAFT_B200_H
+#define AVATARCRAFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AC_OK 0
+#define AC_E_INVALID_ARG (-1)    /* NULL pointer, bad size (reference: TORCH_CHECK -> RuntimeError) */
+#define AC_E_UNSUPPORTED (-2)    /* D not in {2,3} / C not in {1,2,4,8} (hashencoder.cu:349,364)      */
+#define AC_E_CUDA (-3)           /* a CUDA launch failed; see ac_last_cuda_error()                     */
+#define AC_E_WORKSPACE (-4)      /* workspace too small                                                */
+
+/* Library identity: version string and the CUDA arch it was compiled for ("sm_100a"). */
+const char *ac_version(void);
+const char *ac_last_cuda_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t ac_launch_count(void);
+
+/* --------------------------------------------------------------------------------------
+ * Multi-resolution hash-grid encoder.  Replaces the pybind ops
+ *   hash_encode_forward  (encoder/hashencoder/src/hashencoder.h:13, hashencoder.cu:413-436)
+ *   hash_encode_backward (encoder/hashencoder/src/hashencoder.h:14, hashencoder.cu:439-470)
+ * with the same argument order and buffer layouts:
+ *   inputs [B,D] in [0,1]; embeddings [n_entries,C]; offsets [L+1] int32;
+ *   outputs [L,B,C]; dy_dx [B,L,D,C] (written only when calc_grad_inputs != 0);
+ *   grad [L,B,C]; grad_embeddings [n_entries,C] (accumulated into; caller zeroes);
+ *   grad_inputs [B,D].  S = log2(per_level_scale), H = base resolution.  fp32 only.
+ * corner_ids (optional, may be NULL) receives the table slot of every corner,
+ * [L,B,2^D] int32 (-1 for out-of-range inputs) -- the integer path parity tests pin.
+ * ------------------------------------------------------------------------------------ */
+int ac_hash_encode_forward(const float *inputs, const float *embeddings, const int32_t *offsets,
+                           float *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                           float S, uint32_t H, int calc_grad_inputs, float *dy_dx,
+                           int32_t *corner_ids, void *stream);
+int ac_hash_encode_backward(const float *grad, const float *inputs, const float *embeddings,
+                            const int32_t *offsets, float *grad_embeddings, uint32_t B, uint32_t D,
+                            uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                            const float *dy_dx, float *grad_inputs, void *stream);
+/* Per-level scale exp2f(l*S)*H-1 as evaluated ON THE DEVICE (hashencoder.cu:121); scales [L]. */
+int ac_hash_level_scales(float *scales, uint32_t L, float S, uint32_t H, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Spherical-harmonics direction encoder.  Replaces
+ *   sh_encode_forward  (encoder/shencoder/src/shencoder.h:11, shencoder.cu:387-393)
+ *   sh_encode_backward (encoder/shencoder/src/shencoder.h:14, shencoder.cu:395-400)
+ * inputs [B,3]; outputs [B,degree^2]; dy_dx [B,3,degree^2]; degree in 1..8.
+ * ------------------------------------------------------------------------------------ */
+int ac_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t degree,
+                         int calc_grad_inputs, float *dy_dx, void *stream);
+int ac_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, uint32_t D, uint32_t degree,
+                          const float *dy_dx, float *grad_inputs, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Instant-NSR model (models/instant_nsr.py:478-726): hash grid (L=16, C=2, D=3) +
+ * SDF MLP 35->64->16 (softplus beta=100) + colour MLP 21->64->64->3 (relu, sigmoid)
+ * + the single NeuS variance.
+ * ------------------------------------------------------------------------------------ */
+#define AC_NSR_MLP_BLOB_FLOATS 9296
+
+/* Folds weight-norm (w = g*v/||v||_row, models/instant_nsr.py:555-556,585-586) and packs
+ * the five layers into the blob the render kernels stage in shared memory.  Pointers are
+ * the state-dict tensors: sdf_net.{0,1}.{weight_g,weight_v,bias},
+ * color_net.{0,1,2}.{weight_g,weight_v}.  blob [AC_NSR_MLP_BLOB_FLOATS]. */
+int ac_nsr_pack_mlp(const float *sdf0_g, const float *sdf0_v, const float *sdf0_b,
+                    const float *sdf1_g, const float *sdf1_v, const float *sdf1_b,
+                    const float *col0_g, const float *col0_v, const float *col1_g, const float *col1_v,
+                    const float *col2_g, const float *col2_v, float *blob, void *stream);
+
+typedef struct ac_nsr_model {
+    const float *embeddings;   /* [n_entries,2] encoder.embeddings                              */
+    const int32_t *offsets;    /* [17] encoder.offsets (device)                                 */
+    const float *mlp_blob;     /* [AC_NSR_MLP_BLOB_FLOATS] from ac_nsr_pack_mlp                  */
+    const float *variance;     /* [1] deviation_net.variance (device scalar)                    */
+    float log2_per_level_scale;/* S (hashgrid.py:28)                                            */
+    uint32_t base_resolution;  /* H = 16                                                        */
+} ac_nsr_model;
+
+/* NeRFNetwork.forward_sdf (models/instant_nsr.py:627-642) on a flat list of points.
+ * x [B,3] in [-bound,bound] -> out [B,16] (col 0 sdf, cols 1..15 geometry features). */
+int ac_nsr_forward_sdf(const ac_nsr_model *model, const float *x, float *out, uint32_t B, float bound,
+                       void *stream);
+/* NeRFNetwork.forward_color (models/instant_nsr.py:644-663, use_viewdirs=False):
+ * x [B,3], normal [B,3], geo_feat [B,15] -> rgb [B,3]. */
+int ac_nsr_forward_color(const ac_nsr_model *model, const float *x, const float *normal,
+                         const float *geo_feat, float *rgb, uint32_t B, void *stream);
+/* NeRFNetwork.gradient / finite_difference_normals_approximator (:683-704): [B,3] -> [B,3]. */
+int ac_nsr_fd_gradient(const ac_nsr_model *model, const float *x, float *grad, uint32_t B, float bound,
+                       float epsilon, void *stream);
+
+/* The fused render core: NeRFRenderer.run (models/instant_nsr.py:133-299, render_can=True)
+ * for n_rays rays in one launch -- near/far, coarse samples, SDF queries, upsample_steps/16
+ * importance rounds (up_sample :410-459, sample_pdf :21-55, cat_z_vals :461-475), section
+ * mid-points, finite-difference normals, colour, NeuS alpha and front-to-back compositing.
+ *   rays_o, rays_d [n_rays,3].
+ *   bg_color: NULL (white, bg=1) or [n_rays,3].
+ *   jitter:   NULL (eval) or [n_rays,num_steps] uniform [0,1) replacing torch.rand (:162).
+ *   alpha_mask: NULL or [n_rays, num_steps+upsample_steps] (the warp path's mask, :245-248).
+ * Outputs (any of the per-sample pointers may be NULL to skip the store):
+ *   rgb [n,3], depth [n], weight_sum [n], normal [n,3]                (32 B per ray)
+ *   weights [n,T], pts_color [n,T,3], pts_alpha [n,T], z_vals [n,T]   (T = num_steps+upsample_steps)
+ *   eikonal [ceil(n_rays/eikonal_segment)]: sum(m*(|g|-1)^2)/(sum(m)+1e-5) (:265-272) over each
+ *     consecutive segment of `eikonal_segment` rays (0 = one segment = the whole launch).  The
+ *     reference's driver renders 4096-ray batches and adds their means (render_utils.py:556-575);
+ *     one launch with eikonal_segment = rays_per_batch reproduces that without 16 launches.
+ * workspace: >= ac_nsr_render_workspace_bytes(n_rays) bytes, 16 B aligned.
+ * Constraints: num_steps in [2,128], upsample_steps a multiple of 16, T <= 128. */
+typedef struct ac_nsr_render_args {
+    const float *rays_o, *rays_d;
+    const float *bg_color, *jitter, *alpha_mask;
+    uint32_t n_rays, num_steps, upsample_steps, eikonal_segment;
+    float bound, cos_anneal_ratio, normal_epsilon_ratio;
+    float *rgb, *depth, *weight_sum, *normal;
+    float *weights, *pts_color, *pts_alpha, *z_vals;
+    float *eikonal;
+    void *workspace;
+    uint64_t workspace_bytes;
+} ac_nsr_render_args;
+
+uint64_t ac_nsr_render_workspace_bytes(uint32_t n_rays);
+int ac_nsr_render(const ac_nsr_model *model, const ac_nsr_render_args *args, void *stream);
+
+/* Stage-level entry points used by the parity tests to pin the integer paths with
+ * identical inputs (same device functions the fused kernel runs):
+ * one importance round on given (z, sdf): z [n,T], sdf [n,T] -> z_new [n,16],
+ * bins [n,16,2] (below, above) int32, merged z_out [n,T+16], order [n,T+16] int32
+ * (source index into cat([z, z_new])). */
+int ac_nsr_debug_upsample(const float *rays_o, const float *rays_d, const float *z, const float *sdf,
+                          uint32_t n_rays, uint32_t T, float inv_s, float *z_new, int32_t *bins,
+                          float *z_out, int32_t *order, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVATARCRAFT_B200_H */

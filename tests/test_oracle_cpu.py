@@ -1,0 +1,135 @@
+"""CPU suite (-m "not gpu"): the oracle against the golden fixtures generated from the
+reference's own code, the host-side mirror of the reference API, and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import ROOT, load_golden, psnr, state_dict
+from oracle import hashgrid as ohg
+from oracle.nsr_oracle import OracleNSR
+from avatarcraft_b200.utils import synthetic as syn
+
+CASES = ["c1_init_64x64_16p16", "c2_trained_256x256_64p64", "c4_trained_256x256_32p32", "c3_trained_jitter_64p64"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_reference_fixture(name):
+    """oracle/nsr_oracle.py == the reference's NeRFRenderer.run (fixture written by
+    oracle/make_golden.py from /root/reference) on the same rays and checkpoint."""
+    g, sd = load_golden(name)
+    jit = torch.from_numpy(g["jitter"]) if g["jitter"].size else None
+    out = OracleNSR(sd).run(torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]), int(g["num_steps"]),
+                            float(g["bound"]), int(g["upsample_steps"]), jitter=jit)
+    depth, weights, wsum, image, nmap, eik, _, color, alpha, z = out
+    tol = 2e-6   # same torch build, same op order: agreement is at rounding level
+    np.testing.assert_allclose(z.numpy(), g["z_vals"], atol=tol)
+    np.testing.assert_allclose(image.reshape(-1, 3).numpy(), g["rgb"], atol=tol)
+    np.testing.assert_allclose(weights.numpy(), g["weights"], atol=tol)
+    np.testing.assert_allclose(alpha.numpy(), g["pts_alpha"], atol=tol)
+    np.testing.assert_allclose(color.numpy(), g["pts_color"], atol=tol)
+    np.testing.assert_allclose(nmap.numpy(), g["normal"], atol=tol)
+    np.testing.assert_allclose(depth.reshape(-1).numpy(), g["depth"], atol=tol)
+    np.testing.assert_allclose(float(eik), float(g["eikonal"]), rtol=1e-5)
+
+
+def test_hashgrid_oracle_against_reference_wrapper_fixture():
+    g, sd = load_golden("hashgrid_trained_768")
+    x = torch.from_numpy(g["x"])
+    m = OracleNSR(sd)
+    feats, ids = m.encode(x, 1.6, want_ids=True)
+    np.testing.assert_array_equal(ids.numpy(), g["corner_ids"])
+    np.testing.assert_array_equal(feats.numpy(), g["feats"])
+    np.testing.assert_allclose(m.forward_sdf(x, 1.6).numpy(), g["sdf16"], atol=1e-6)
+    # out-of-range rows (|x| > bound) encode to zero, ids -1 (hashencoder.cu:94-119)
+    oob = (x.abs() > 1.6).any(1).numpy()
+    assert oob.sum() == 2 and np.all(g["feats"][oob] == 0) and np.all(g["corner_ids"][:, oob] == -1)
+
+
+def test_hash_offsets_match_reference_table():
+    offs, pls = syn.hash_offsets()
+    assert offs.tolist() == [0, 4913, 18737, 51505, 136689, 352689, 876977, 1401265, 1925553, 2449841, 2974129,
+                             3498417, 4022705, 4546993, 5071281, 5595569, 6119857]
+    o2, p2 = ohg.grid_offsets()
+    assert o2.tolist() == offs.tolist() and abs(pls - p2) < 1e-15
+    sc = ohg.level_scales(16, np.log2(pls), 16)
+    assert sc[0] == 15.0 and abs(sc[15] - 2047.0) < 1e-3
+    # dense levels are 0..4 (level 4 has 60^3 = 216000 entries), hashed 5..15 (2^19 each)
+    sizes = np.diff(offs.numpy())
+    assert sizes[4] == 216000 and np.all(sizes[5:] == 2 ** 19)
+
+
+def test_oracle_backward_matches_autograd_of_forward():
+    """The table gradient of the C oracle equals d(sum(out*g))/d(table) by finite linearity:
+    the encoder is linear in the table, so backward(g) . t == forward(t) . g for any t."""
+    torch.manual_seed(3)
+    offs, pls = ohg.grid_offsets(num_levels=4, log2_hashmap_size=10, desired_resolution=64)
+    offs_t = torch.from_numpy(offs)
+    n = int(offs[-1])
+    B, L, C, D = 300, 4, 2, 3
+    x = torch.rand(B, D)
+    g = torch.randn(L, B, C)
+    t = torch.randn(n, C)
+    S = float(np.log2(pls))
+    out = torch.empty(L, B, C)
+    ohg.hash_encode_forward(x, t, offs_t, out, B, D, C, L, S, 16, False, None)
+    gt = torch.zeros(n, C)
+    ohg.hash_encode_backward(g, x, t, offs_t, gt, B, D, C, L, S, 16, False, None, None)
+    lhs, rhs = float((gt.double() * t.double()).sum()), float((out.double() * g.double()).sum())
+    assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(rhs))
+
+
+def test_state_dict_layout_matches_reference():
+    from avatarcraft_b200.models.instant_nsr import NeRFNetwork
+    net = NeRFNetwork()
+    sd = net.state_dict()
+    assert tuple(sd.keys()) == syn.STATE_KEYS
+    ref = state_dict("init", 42)
+    for k in syn.STATE_KEYS:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape) and sd[k].dtype == ref[k].dtype, k
+    assert sum(v.numel() for v in sd.values()) == 12248919
+    net.load_state_dict(ref)                                           # reference-layout checkpoints load as is
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libavatarcraft_b200.so loads without a GPU and exports what include/*.h declares."""
+    from avatarcraft_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "avatarcraft_b200.h")).read()
+    declared = set(re.findall(r"\b(ac_[a-z0-9_]+)\s*\(", hdr))
+    not_yet = {"ac_sh_encode_forward", "ac_sh_encode_backward"} - set(_lib.EXPORTED_SYMBOLS)
+    handle = ctypes.CDLL(_lib.build())
+    for name in sorted(declared - not_yet):
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) <= declared
+    assert b"sm_100a" in _lib.lib().ac_version()
+
+
+def test_product_path_has_no_cpu_fallback():
+    from avatarcraft_b200.models.instant_nsr import NeRFNetwork
+    net = NeRFNetwork()
+    o, d = syn.pinhole_rays(syn.orbit_pose(0.0), 4, 4)
+    with pytest.raises(RuntimeError):
+        net.render(o[None], d[None], num_steps=16, bound=1.6, upsample_steps=16)
+    with pytest.raises(RuntimeError):
+        net.encoder(torch.zeros(4, 3), 1.6)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "avatarcraft_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
+
+
+def test_synthetic_rays_match_reference_camera():
+    """Pinned against the value obtained by running the reference's cameras/ + shot_rays code
+    (SURVEY.md 8c): orbit view at +z, 8x8 image."""
+    o, d = syn.pinhole_rays(syn.orbit_pose(0.0), 8, 8)
+    np.testing.assert_allclose(o[0].numpy(), [0, 0, 1.7], atol=1e-6)
+    np.testing.assert_allclose(d[0].numpy(), [-0.4745, 0.4745, -0.7414], atol=1e-4)
+    assert o.dtype == torch.float32 and abs(float(d.norm(dim=1).mean()) - 1) < 1e-6
