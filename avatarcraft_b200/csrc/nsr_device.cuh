@@ -263,11 +263,10 @@ __device__ __forceinline__ void ray_box(const Ray& r, float bound, float& near, 
 }
 
 // One importance round on a warp-owned ray (up_sample :410-459, sample_pdf :21-55 det=True).
-// zs/sdfs hold T sorted depths and their SDF; ta/tb are T-float scratch rows.  On return lanes
-// 0..15 hold the 16 new depths (ascending) and the CDF bin (below, above) each fell in.
-__device__ __forceinline__ void importance_round(const Ray& r, const float* zs, const float* sdfs, float* ta,
-                                                 float* tb, int T, float inv_s, int lane, float& z_new,
-                                                 int& below, int& above) {
+// zs/sdfs hold T sorted depths and their SDF; ta/tb are T-float scratch rows.
+// Step 1: per-interval alpha into ta[0..T-2].
+__device__ __forceinline__ void interval_alpha(const Ray& r, const float* zs, const float* sdfs, float* ta, int T,
+                                               float inv_s, int lane) {
     const int nI = T - 1;
     for (int k = lane; k < nI; k += 32) {
         const float z0 = zs[k], z1 = zs[k + 1], s0 = sdfs[k], s1 = sdfs[k + 1];
@@ -287,6 +286,13 @@ __device__ __forceinline__ void importance_round(const Ray& r, const float* zs, 
         ta[k] = (c0 - c1 + 1e-5f) / (c0 + 1e-5f);
     }
     __syncwarp();
+}
+
+// Step 2: alpha (ta) -> weights -> pdf -> cdf (tb) -> 16 deterministic inverse-CDF samples.
+// On return lanes 0..15 hold the new depths (ascending) and the CDF bin (below, above) of each.
+__device__ __forceinline__ void importance_from_alpha(const float* zs, float* ta, float* tb, int T, int lane,
+                                                      float& z_new, int& below, int& above) {
+    const int nI = T - 1;
     // weights = alpha * exclusive_cumprod(1 - alpha + 1e-7); pdf numerators w + 1e-5
     float a[4], f[4];
     const int base = lane * 4;
@@ -339,6 +345,13 @@ __device__ __forceinline__ void importance_round(const Ray& r, const float* zs, 
         z_new = zb + t * (za - zb);
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void importance_round(const Ray& r, const float* zs, const float* sdfs, float* ta,
+                                                 float* tb, int T, float inv_s, int lane, float& z_new,
+                                                 int& below, int& above) {
+    interval_alpha(r, zs, sdfs, ta, T, inv_s, lane);
+    importance_from_alpha(zs, ta, tb, T, lane, z_new, below, above);
 }
 
 // Merge 16 new ascending depths (lanes 0..15) into the T sorted ones (torch.sort of the

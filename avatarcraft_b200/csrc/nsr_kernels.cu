@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(256) pack_mlp_kernel(const PackArgs a) {
 
 __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                              const float* __restrict__ z, const float* __restrict__ sdf, uint32_t n,
-                                                             uint32_t T, float inv_s, float* z_new_out, int32_t* bins, float* z_out,
-                                                             int32_t* order) {
+                                                             uint32_t T, float inv_s, const float* __restrict__ alpha_in, float* alpha_out,
+                                                             float* z_new_out, int32_t* bins, float* z_out, int32_t* order) {
     __shared__ float rows[kWarps * 4 * kMaxT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ray = blockIdx.x * kWarps + warp;
@@ -327,7 +327,11 @@ __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __rest
     r.ox = rays_o[3 * ray]; r.oy = rays_o[3 * ray + 1]; r.oz = rays_o[3 * ray + 2];
     r.dx = rays_d[3 * ray]; r.dy = rays_d[3 * ray + 1]; r.dz = rays_d[3 * ray + 2];
     float zn; int below, above;
-    importance_round(r, zs, sdfs, ta, tb, (int)T, inv_s, lane, zn, below, above);
+    interval_alpha(r, zs, sdfs, ta, (int)T, inv_s, lane);
+    if (alpha_out) for (uint32_t k = lane; k + 1 < T; k += 32) alpha_out[(size_t)ray * (T - 1) + k] = ta[k];
+    if (alpha_in) for (uint32_t k = lane; k + 1 < T; k += 32) ta[k] = alpha_in[(size_t)ray * (T - 1) + k];
+    __syncwarp();
+    importance_from_alpha(zs, ta, tb, (int)T, lane, zn, below, above);
     int pos_old[4], pos_new;
     merge_positions(zs, (int)T, zn, lane, pos_old, pos_new);
     const size_t ob = (size_t)ray * (T + 16);
@@ -441,12 +445,13 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
 }
 
 int ac_nsr_debug_upsample(const float* rays_o, const float* rays_d, const float* z, const float* sdf, uint32_t n_rays,
-                          uint32_t T, float inv_s, float* z_new, int32_t* bins, float* z_out, int32_t* order, void* stream) {
+                          uint32_t T, float inv_s, const float* alpha_in, float* alpha_out, float* z_new, int32_t* bins,
+                          float* z_out, int32_t* order, void* stream) {
     if (!rays_o || !rays_d || !z || !sdf || !z_new || !bins || !z_out || !order) return AC_E_INVALID_ARG;
     if (T < 2 || T + 16 > (uint32_t)kMaxT) return AC_E_INVALID_ARG;
     if (n_rays == 0) return AC_OK;
     debug_upsample_kernel<<<(n_rays + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, z, sdf, n_rays, T, inv_s, z_new, bins, z_out, order);
+        rays_o, rays_d, z, sdf, n_rays, T, inv_s, alpha_in, alpha_out, z_new, bins, z_out, order);
     return acb::launched();
 }
 

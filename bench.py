@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the AvatarCraft hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): render_canonical.py at 256x256, 64+64 samples per ray,
+hash-encoded NeuS (Instant-NSR), bound 1.6, white background, eval mode.  One STEP = one full
+frame = 65 536 rays through the complete `NeRFRenderer.run` semantics (1008 SDF evaluations
+and 128 colour evaluations per ray).  Synthetic "trained-like" checkpoint (seed 43) and the
+reference's canonical orbit camera; no dataset or checkpoint is available offline.
+
+Reported on ONE JSON line:
+  value     rays/s, whole job, rays already resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the reference-facing driver `render_instantnsr_naive` with
+            HOST (pinned) ray buffers: H2D of the rays and D2H of the rgb inside the timed region
+  roofline  dominant kernel (nsr_render_kernel): algorithmic gather bytes (SURVEY.md 8d:
+            1 032 192 B/ray + 56 B/ray compulsory + the 48.96 MB table once per launch) / measured
+            launch time vs the measured HBM peak; plus the MLP FLOP rate vs the tensor peak
+  cpu_baseline  the oracle port (oracle/nsr_oracle.py, all host threads) on a 4096-ray batch of
+            the same frame -- a reported baseline, not the target
+N > 1 (torchrun): every rank renders its own view of the orbit (weak scaling, no collective on
+the data path -- rays are independent); value = all ranks' rays / max-over-ranks time.
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: the
+reference's Python cannot travel to the GPU box and has no CPU hash kernel of its own) on the
+host cores, each step one 4096-ray batch of the same frame.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W_IMG = H_IMG = 256
+NUM_STEPS, UPSAMPLE_STEPS, BOUND = 64, 64, 1.6
+RAYS_PER_FRAME = W_IMG * H_IMG
+GATHER_BYTES_PER_RAY = 1008 * 16 * 8 * 8          # evals x levels x corners x 8 B
+COMPULSORY_BYTES_PER_RAY = 56
+TABLE_BYTES = 6119857 * 2 * 4
+MLP_FLOP_PER_RAY = 1008 * 6528 + 128 * 11264
+CPU_SAMPLE_RAYS = 4096
+WORKLOAD = "render_canonical 256x256, 64+64 samples/ray, hash-encoded NeuS (Instant-NSR), bound 1.6"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/bench_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [v for v in sm if v >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def frame_rays(view_index):
+    from avatarcraft_b200.utils import synthetic as syn
+    return syn.pinhole_rays(syn.orbit_pose(30.0 + 6.0 * view_index), W_IMG, H_IMG)
+
+
+def cpu_oracle_rate(n_rays, repeats=1):
+    """rays/s of the oracle port (torch CPU + C hash restatement, all host threads)."""
+    import torch
+    from avatarcraft_b200.utils import synthetic as syn
+    from oracle.nsr_oracle import OracleNSR
+    torch.set_num_threads(os.cpu_count())
+    m = OracleNSR(syn.synthetic_state_dict("trained", 43))
+    o, d = frame_rays(0)
+    sel = slice(RAYS_PER_FRAME // 2 - n_rays // 2, RAYS_PER_FRAME // 2 + n_rays // 2)   # central rows: rays that hit
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        m.run(o[sel], d[sel], NUM_STEPS, BOUND, UPSAMPLE_STEPS)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_rays / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_oracle_rate(256)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_oracle_rate(CPU_SAMPLE_RAYS)
+        t += dt
+    value = CPU_SAMPLE_RAYS * args.steps / t
+    sample = f"{CPU_SAMPLE_RAYS}-ray batch (central rows) of the 256x256 frame per step, 64+64 samples"
+    print(json.dumps({
+        "impl": "reference", "metric": "rays_per_sec_volume_render", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": CPU_SAMPLE_RAYS, "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from avatarcraft_b200 import _lib
+    from avatarcraft_b200.models.instant_nsr import NeRFNetwork
+    from avatarcraft_b200.utils import synthetic as syn
+    from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = _lib.lib()
+
+    net = NeRFNetwork()
+    net.load_state_dict(syn.synthetic_state_dict("trained", 43))
+    net = net.to(dev).eval()
+    o_h, d_h = frame_rays(rank)
+    o_pin, d_pin = o_h.pin_memory(), d_h.pin_memory()
+    rgb_pin = torch.empty(RAYS_PER_FRAME, 3).pin_memory()
+    o, d = o_h.to(dev), d_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step_resident():
+        return net.run(o[None], d[None], NUM_STEPS, BOUND, UPSAMPLE_STEPS, None, 1.0, 0.0, per_sample_outputs=False)
+
+    def step_e2e():
+        ro = o_pin.to(dev, non_blocking=True)
+        rd = d_pin.to(dev, non_blocking=True)
+        rgb, _ = render_instantnsr_naive(net, ro, rd, rays_per_batch=4096, render_can=True, perturb=False,
+                                         num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS, bound=BOUND)
+        rgb_pin.copy_(rgb, non_blocking=True)
+
+    def timed(fn, steps):
+        """Sum of per-step CUDA-event times on the current stream; L2 flushed before every step."""
+        total = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.ac_launch_count()
+    barrier()
+    ms = timed(step_resident, args.steps)
+    barrier()
+    launches = lib.ac_launch_count() - launches0
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        rays_total = RAYS_PER_FRAME * args.steps * world
+        value = rays_total / (ms * 1e-3)
+        e2e = rays_total / (ms_e2e * 1e-3)
+        launch_s = ms * 1e-3 / args.steps                     # one render launch per step (+ a 1-block reduce)
+        algo_bytes = RAYS_PER_FRAME * (GATHER_BYTES_PER_RAY + COMPULSORY_BYTES_PER_RAY) + TABLE_BYTES
+        achieved = algo_bytes / launch_s / 1e9
+        tflops = RAYS_PER_FRAME * MLP_FLOP_PER_RAY / launch_s / 1e12
+        cpu_rate, cpu_dt = cpu_oracle_rate(CPU_SAMPLE_RAYS)
+        prof = os.path.join(ROOT, "profiles", "r01_render_kernel_traffic.json")
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
+        line = {
+            "metric": "rays_per_sec_volume_render", "value": value, "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": RAYS_PER_FRAME, "num_steps": NUM_STEPS,
+                       "upsample_steps": UPSAMPLE_STEPS, "sdf_evals_per_ray": 1008, "color_evals_per_ray": 128,
+                       "checkpoint": "synthetic trained-like seed 43", "parallelism": f"ray-shard x{world} (one view per rank)",
+                       "l2": "flushed before every timed step (256 MiB memset); per-step CUDA events summed"},
+            "roofline": {"bound": "hbm", "kernel": "nsr_render_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                         "peak_source": pk["source"], "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "algorithmic gather bytes (no reuse) per SURVEY.md 8(d); gathers are served from L1/L2, "
+                                 "so frac may exceed 1 -- see traffic (ncu dram bytes) and profiles/",
+                         "mlp_tflops": tflops, "mlp_frac_of_bf16_peak": tflops / pk["bf16_tflops"]},
+            "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{CPU_SAMPLE_RAYS}-ray batch (central rows) of the same frame, {cpu_dt:.1f} s"},
+            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 2 * RAYS_PER_FRAME * 12,
+                    "d2h_bytes_per_step": RAYS_PER_FRAME * 12, "ms_per_step": ms_e2e / args.steps,
+                    "api": "avatarcraft_b200.utils.render_utils.render_instantnsr_naive (pinned host rays in, pinned host rgb out)"},
+            "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 20:
+            args.steps = 3
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

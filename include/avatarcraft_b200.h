@@ -138,10 +138,12 @@ int ac_nsr_render(const ac_nsr_model *model, const ac_nsr_render_args *args, voi
  * identical inputs (same device functions the fused kernel runs):
  * one importance round on given (z, sdf): z [n,T], sdf [n,T] -> z_new [n,16],
  * bins [n,16,2] (below, above) int32, merged z_out [n,T+16], order [n,T+16] int32
- * (source index into cat([z, z_new])). */
+ * (source index into cat([z, z_new])).  alpha_out (optional) [n,T-1] receives the section
+ * alphas; alpha_in (optional) [n,T-1] REPLACES them before the pdf/cdf/search, so the
+ * integer path can be compared on bit-identical weights. */
 int ac_nsr_debug_upsample(const float *rays_o, const float *rays_d, const float *z, const float *sdf,
-                          uint32_t n_rays, uint32_t T, float inv_s, float *z_new, int32_t *bins,
-                          float *z_out, int32_t *order, void *stream);
+                          uint32_t n_rays, uint32_t T, float inv_s, const float *alpha_in, float *alpha_out,
+                          float *z_new, int32_t *bins, float *z_out, int32_t *order, void *stream);
 
 #ifdef __cplusplus
 }

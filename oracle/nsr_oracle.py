@@ -107,7 +107,7 @@ class OracleNSR:
         return b_lo + (u - c_lo) / den * (b_hi - b_lo), (lo, hi)
 
     # ---- one importance round (models/instant_nsr.py:410-459) -----------------------------
-    def up_sample(self, rays_o, rays_d, z, sdf, n_importance, inv_s):
+    def up_sample(self, rays_o, rays_d, z, sdf, n_importance, inv_s, trace=None):
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]
         r = torch.linalg.norm(pts, ord=2, dim=-1)
         inside = (r[:, :-1] < 1.0) | (r[:, 1:] < 1.0)               # unit sphere, not `bound`
@@ -120,6 +120,8 @@ class OracleNSR:
         c0 = torch.sigmoid((mid - slope * d * 0.5) * inv_s)
         c1 = torch.sigmoid((mid + slope * d * 0.5) * inv_s)
         alpha = (c0 - c1 + 1e-5) / (c0 + 1e-5)                        # NOT clipped here
+        if trace is not None:
+            trace["alpha"] = alpha
         trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
         return self.sample_pdf_det(z, alpha * trans, n_importance)
 
