@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libavatarcraft_b200.so")
-SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu"]
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -66,6 +66,7 @@ _SIGNATURES = {
     "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
     "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),
     "ac_nsr_render": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrRenderArgs), _V]),
+    "ac_nsr_debug_tc_layer": (_I, [_V, _V, _V, _V]),
     "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V, _V, _V]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/avatarcraft_b200.h"
 #include "launch_util.cuh"
@@ -347,6 +348,10 @@ __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __rest
     }
 }
 
+}  // namespace
+namespace acb { int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStream_t st); }
+namespace {
+
 int grid_for(uint32_t B, int block, int per_sm) {
     int sms = acb::sm_count();
     long want = ((long)B + block - 1) / block;
@@ -426,6 +431,15 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
     if (a->num_steps < 2 || a->upsample_steps % 16 != 0 || T > (uint32_t)kMaxT) return AC_E_INVALID_ARG;
     if (a->workspace_bytes < ac_nsr_render_workspace_bytes(a->n_rays)) return AC_E_WORKSPACE;
     if (a->n_rays == 0) return AC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t seg = a->eikonal_segment ? a->eikonal_segment : a->n_rays;
+    static const bool use_simt = [] { const char* e = getenv("AC_RENDER_IMPL"); return e && e[0] == 's'; }();
+    if (!use_simt) {   // tensor-core kernel (default); AC_RENDER_IMPL=simt keeps the SIMT kernel for A/B debugging
+        int rc = acb::launch_render_tc(m, a, st);
+        if (rc) return rc;
+        eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(reinterpret_cast<float*>(a->workspace), a->n_rays, seg, a->eikonal);
+        return acb::launched();
+    }
     RenderParams p;
     p.table = reinterpret_cast<const float2*>(m->embeddings);
     p.offsets = m->offsets; p.blob = m->mlp_blob; p.variance = m->variance;
@@ -435,11 +449,9 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
     const size_t smem = kStageBytes + (size_t)kWarps * 4 * kMaxT * sizeof(float);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(nsr_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    cudaStream_t st = (cudaStream_t)stream;
     nsr_render_kernel<<<(a->n_rays + kWarps - 1) / kWarps, kWarps * 32, smem, st>>>(p);
     int rc = acb::launched();
     if (rc) return rc;
-    const uint32_t seg = a->eikonal_segment ? a->eikonal_segment : a->n_rays;
     eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(p.eik_partial, a->n_rays, seg, a->eikonal);
     return acb::launched();
 }

@@ -145,6 +145,10 @@ int ac_nsr_debug_upsample(const float *rays_o, const float *rays_d, const float 
                           uint32_t n_rays, uint32_t T, float inv_s, const float *alpha_in, float *alpha_out,
                           float *z_new, int32_t *bins, float *z_out, int32_t *order, void *stream);
 
+/* Unit test of the tensor-core layer in isolation: feats [128,32] fp32 x (sdf layer 0 feature
+ * columns)^T -> out [128,64] pre-activations WITHOUT bias / xyz terms (3xTF32 tcgen05.mma). */
+int ac_nsr_debug_tc_layer(const float *feats, const float *mlp_blob, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
