@@ -268,11 +268,47 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             T += 16;
         }
 
-        // ---- render core (:186-299): 32 section samples per iteration, in depth order ----
+        // ---- render core (:186-299) ----
+        // Section samples are processed in halves of 64.  For each half, first the 6 x 64 finite-
+        // difference points (:687-704) are evaluated with lanes packed as (sample, direction): the
+        // six +-eps neighbours of a sample sit within 0.003 of each other, so on every level coarser
+        // than ~10 they fall in the same grid cell and the warp's gather collapses to a handful of
+        // cache lines (the L1 tag stage, one line per cycle, is what bounds this kernel).  Their SDF
+        // values are parked in three scratch rows; then the half's two 32-sample blocks are shaded
+        // in depth order (lane = sample), carrying the transmittance across blocks.
+        if (zs != reinterpret_cast<float*>(smem + SM_ROWS) + warp * 4 * kMaxT) {   // park the depths in row 0
+            float* row0 = reinterpret_cast<float*>(smem + SM_ROWS) + warp * 4 * kMaxT;
+            for (int k = lane; k < Ttot; k += 32) row0[k] = zs[k];
+            __syncwarp();
+            zs = row0;
+        }
+        float* fd = zs + kMaxT;            // rows 1..3: 384 floats = 64 samples x 6 directions
+        sdfs = zs + kMaxT; ta = zs + 2 * kMaxT; tb = zs + 3 * kMaxT;
         float carry = 1.0f;
         float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_nx = 0.f, acc_ny = 0.f, acc_nz = 0.f;
         float acc_w = 0.f, acc_d = 0.f, eik_num = 0.f, eik_den = 0.f;
-        for (int k0 = 0; k0 < Ttot; k0 += 32) {
+        for (int h0 = 0; h0 < Ttot; h0 += 64) {
+            const int nS = min(64, Ttot - h0);
+            for (int q0 = 0; q0 < 6 * nS; q0 += 32) {
+                const int q = min(q0 + lane, 6 * nS - 1);
+                const int sI = q / 6, dir = q - 6 * sI;
+                const int k = h0 + sI;
+                const float zk = zs[k];
+                const float zmid = k < Ttot - 1 ? zk + 0.5f * (zs[k + 1] - zk) : zk;
+                float px, py, pz;
+                ray_point(r, zmid, px, py, pz);
+                px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
+                const float e = (dir & 1) ? -eps : eps;
+                const int ax = dir >> 1;
+                const float qx = ax == 0 ? clampf(px + e, -bound, bound) : px;
+                const float qy = ax == 1 ? clampf(py + e, -bound, bound) : py;
+                const float qz = ax == 2 ? clampf(pz + e, -bound, bound) : pz;
+                float o[1];
+                group_sdf_eval<false>(g, table, lv, sw, bound, qx, qy, qz, o);
+                if (q0 + lane < 6 * nS) fd[q] = o[0];
+            }
+            __syncwarp();
+            for (int k0 = h0; k0 < h0 + nS; k0 += 32) {
             const bool live = k0 + lane < Ttot;
             const int k = min(k0 + lane, Ttot - 1);
             const float zk = zs[k];
@@ -284,20 +320,11 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             float o16[16];
             group_sdf_eval<true>(g, table, lv, sw, bound, px, py, pz, o16);
             float gr[3];
-#pragma unroll 1
-            for (int ax = 0; ax < 3; ++ax) {
-                float f2[2];
-#pragma unroll 1
-                for (int sg = 0; sg < 2; ++sg) {
-                    const float e = sg == 0 ? eps : -eps;
-                    const float qx = ax == 0 ? clampf(px + e, -bound, bound) : px;
-                    const float qy = ax == 1 ? clampf(py + e, -bound, bound) : py;
-                    const float qz = ax == 2 ? clampf(pz + e, -bound, bound) : pz;
-                    float o[1];
-                    group_sdf_eval<false>(g, table, lv, sw, bound, qx, qy, qz, o);
-                    f2[sg] = o[0];
-                }
-                gr[ax] = 0.5f * (f2[0] - f2[1]) / eps;
+            {
+                const float* f6 = fd + 6 * (k - h0);
+                gr[0] = 0.5f * (f6[0] - f6[1]) / eps;
+                gr[1] = 0.5f * (f6[2] - f6[3]) / eps;
+                gr[2] = 0.5f * (f6[4] - f6[5]) / eps;
             }
             const float gn = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
             const float inv = 1e-5f + gn;
@@ -335,7 +362,9 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                     if (p.a.pts_color) { p.a.pts_color[3 * s] = col[0]; p.a.pts_color[3 * s + 1] = col[1]; p.a.pts_color[3 * s + 2] = col[2]; }
                 }
             }
-        }
+            }   // 32-sample block
+            __syncwarp();
+        }       // 64-sample half
         acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
         acc_nx = warp_sum(acc_nx); acc_ny = warp_sum(acc_ny); acc_nz = warp_sum(acc_nz);
         acc_w = warp_sum(acc_w); acc_d = warp_sum(acc_d);
