@@ -62,6 +62,7 @@ _SIGNATURES = {
     "ac_hash_level_scales": (_I, [_V, _U32, _F, _U32, _V]),
     "ac_nsr_pack_mlp": (_I, [_V] * 13 + [_V]),
     "ac_nsr_forward_sdf": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V]),
+    "ac_nsr_sdf_backward": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V, _V, _V, _V, _V]),
     "ac_nsr_forward_color": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _U32, _V]),
     "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
     "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),

@@ -32,6 +32,40 @@ def near_far_from_bound(rays_o, rays_d, bound, type='cube'):
     return near, far
 
 
+class _SdfQuery(torch.autograd.Function):
+    """Differentiable NeRFNetwork.forward_sdf on a flat point list.  Forward: ac_nsr_forward_sdf.
+    Backward: ac_nsr_sdf_backward (fused recompute + hash-table scatter + layer deltas), then four
+    plain GEMMs / reductions for the weight gradients.  w0/b0/w1/b1 are the weight-norm-folded
+    tensors; they are graph inputs only -- the kernels read the packed blob built from the same
+    parameters -- so torch back-propagates through the weight-norm fold itself."""
+
+    @staticmethod
+    def forward(ctx, x, embeddings, w0, b0, w1, b1, net, bound):
+        x = x.detach().reshape(-1, 3).float().contiguous()
+        out = torch.empty(x.shape[0], 16, device=x.device, dtype=torch.float32)
+        m = net._device_model()
+        _lib.check(_lib.lib().ac_nsr_forward_sdf(ctypes.byref(m), _lib.ptr(x), _lib.ptr(out), x.shape[0], float(bound),
+                                                 _lib.stream_ptr()), "ac_nsr_forward_sdf")
+        ctx.save_for_backward(x)
+        ctx.net, ctx.bound, ctx.emb_shape = net, float(bound), embeddings.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        net, B, dev = ctx.net, x.shape[0], x.device
+        gout = gout.contiguous().float()
+        f32 = dict(device=dev, dtype=torch.float32)
+        grad_table = torch.zeros(ctx.emb_shape, **f32)
+        delta = torch.empty(B, 64, **f32); hid = torch.empty(B, 64, **f32); feats = torch.empty(B, 32, **f32)
+        m = net._device_model()
+        _lib.check(_lib.lib().ac_nsr_sdf_backward(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound,
+                                                  _lib.ptr(grad_table), _lib.ptr(delta), _lib.ptr(hid), _lib.ptr(feats),
+                                                  _lib.stream_ptr()), "ac_nsr_sdf_backward")
+        gw0 = torch.cat([delta.t() @ x, delta.t() @ feats], dim=1)
+        return None, grad_table, gw0, delta.sum(0), gout.t() @ hid, gout.sum(0), None, None
+
+
 class SingleVarianceNetwork(nn.Module):
     """exp(10 * variance), one learnable scalar (models/instant_nsr.py:720-726)."""
 
@@ -67,8 +101,9 @@ class NeRFRenderer(nn.Module):
         `eikonal_segment=k` returns one eikonal mean per k consecutive rays (a [ceil(N/k)] tensor)."""
         if not render_can:
             raise NotImplementedError("warped (render_can=False) rendering is not wired yet")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self._needs_grad():
-            raise NotImplementedError("backward of the fused render core is not implemented yet")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._run_with_grad(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
+                                       normal_epsilon_ratio, perturb_overwrite, jitter)
         B, N = rays_o.shape[:2]
         rays_o = rays_o.reshape(-1, 3).float().contiguous()
         rays_d = rays_d.reshape(-1, 3).float().contiguous()
@@ -112,8 +147,71 @@ class NeRFRenderer(nn.Module):
                 eik.reshape(()) if n_seg == 1 else eik, 0.0,
                 color, alpha, z_vals)
 
-    def _needs_grad(self):
-        return getattr(self, "_grad_render", False)
+    def _run_with_grad(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
+                       normal_epsilon_ratio, perturb_overwrite, jitter):
+        """Training-mode `run` (autograd enabled).  As in the reference, sample placement carries no
+        gradient (`with torch.no_grad()`, models/instant_nsr.py:175-185): the depths come from the fused
+        kernel.  The differentiable part (:186-299) evaluates the 7 x N x T SDF points with the fused
+        `_SdfQuery` op (one launch forward, one fused backward + table scatter); the light per-sample
+        algebra (normals, alpha, compositing, eikonal) and the colour MLP are torch ops here -- a fused
+        backward kernel for them is the next step."""
+        B, N = rays_o.shape[:2]
+        o = rays_o.reshape(-1, 3).float().contiguous()
+        d = rays_d.reshape(-1, 3).float().contiguous()
+        n, dev = o.shape[0], o.device
+        if self.training and perturb_overwrite and jitter is None:
+            jitter = torch.rand(n, num_steps, device=dev)
+        with torch.no_grad():
+            z = NeRFRenderer.run(self, o[None], d[None], num_steps, bound, upsample_steps, None, cos_anneal_ratio,
+                                 normal_epsilon_ratio, perturb_overwrite=perturb_overwrite, jitter=jitter)[9]
+            T = z.shape[1]
+            near, far = near_far_from_bound(o, d, bound)
+            gaps = torch.cat([z[:, 1:] - z[:, :-1], ((far - near) / num_steps).expand(n, 1)], -1)
+            z_mid = torch.cat([z[:, :-1] + 0.5 * gaps[:, :-1], z[:, -1:]], -1)
+            P = (o[:, None, :] + d[:, None, :] * z_mid[..., None]).clamp(-bound, bound).reshape(-1, 3)
+            eps = 0.005 * (1.0 - normal_epsilon_ratio)
+            shifted = [P]
+            for axis in range(3):
+                for sign in (1.0, -1.0):
+                    q = P.clone()
+                    q[:, axis] = (q[:, axis] + sign * eps).clamp(-bound, bound)
+                    shifted.append(q)
+            pts = torch.cat(shifted, 0)
+        M = P.shape[0]
+        sdf_w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in self.sdf_net]
+        col_w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in self.color_net]
+        out = _SdfQuery.apply(pts, self.encoder.embeddings, sdf_w[0], self.sdf_net[0].bias, sdf_w[1], self.sdf_net[1].bias,
+                              self, bound)
+        sdf, feat = out[:M, :1], out[:M, 1:]
+        f = out[M:, 0].reshape(3, 2, M)
+        grad = (0.5 * (f[:, 0] - f[:, 1]) / eps).t()
+        gnorm = torch.linalg.norm(grad, ord=2, dim=-1, keepdim=True)
+        normal = grad / (1e-5 + gnorm)
+        h = torch.cat([P, normal, feat], dim=-1)
+        h = torch.relu(torch.nn.functional.linear(h, col_w[0]))
+        h = torch.relu(torch.nn.functional.linear(h, col_w[1]))
+        color = torch.sigmoid(torch.nn.functional.linear(h, col_w[2]))
+        inv_s = torch.exp(self.deviation_net.variance * 10.0).clip(1e-6, 1e6)
+        dirs = d[:, None, :].expand(n, T, 3).reshape(-1, 3)
+        cosv = (dirs * normal).sum(-1, keepdim=True)
+        sp = torch.nn.functional.softplus
+        it = -(sp(-cosv * 0.5 + 0.5, beta=100) * (1.0 - cos_anneal_ratio) + sp(-cosv, beta=100) * cos_anneal_ratio)
+        half = it * gaps.reshape(-1, 1) * 0.5
+        c0, c1 = torch.sigmoid((sdf - half) * inv_s), torch.sigmoid((sdf + half) * inv_s)
+        alpha = ((c0 - c1 + 1e-5) / (c0 + 1e-5)).reshape(n, T).clip(0.0, 1.0)
+        trans = torch.cumprod(torch.cat([torch.ones(n, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+        weights = alpha * trans
+        wsum = weights.sum(-1, keepdim=True)
+        color = color.reshape(n, T, 3)
+        image = (color * weights[..., None]).sum(1)
+        nmap = (normal.reshape(n, T, 3) * weights[..., None]).sum(1)
+        depth = (weights * ((z - near) / (far - near)).clamp(0, 1)).sum(-1)
+        relax = (torch.linalg.norm(P, ord=2, dim=-1).reshape(n, T) < 1.2).float()
+        gerr = (gnorm.reshape(n, T) - 1.0) ** 2
+        eik = (relax * gerr).sum() / (relax.sum() + 1e-5)
+        bg = 1 if bg_color is None else torch.as_tensor(bg_color, dtype=torch.float32, device=dev)
+        image = image + (1 - wsum) * bg
+        return depth.reshape(B, N), weights, wsum, image.reshape(B, N, 3), nmap, eik, 0.0, color, alpha, z
 
     def render(self, rays_o, rays_d, num_steps, bound, upsample_steps, staged=False, max_ray_batch=4096, bg_color=None,
                cos_anneal_ratio=1.0, normal_epsilon_ratio=1.0, render_can=True, verts=None, faces=None, Ts=None,

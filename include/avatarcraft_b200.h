@@ -94,6 +94,15 @@ typedef struct ac_nsr_model {
  * x [B,3] in [-bound,bound] -> out [B,16] (col 0 sdf, cols 1..15 geometry features). */
 int ac_nsr_forward_sdf(const ac_nsr_model *model, const float *x, float *out, uint32_t B, float bound,
                        void *stream);
+/* Training: backward of ac_nsr_forward_sdf.  grad_out [B,16] = dL/d(out).  Accumulates the
+ * hash-table gradient into grad_table [n_entries,2] (caller zeroes; fp32 reductions as in
+ * kernel_grid_backward, hashencoder.cu:223-308) and writes the per-point layer terms from which
+ * the host forms the weight gradients with plain GEMMs:
+ *   delta_a [B,64] = dL/d(hidden pre-activation), hidden [B,64] = softplus output, feats [B,32]
+ *   => dW0 = delta_a^T [x | feats], db0 = sum delta_a, dW1 = grad_out^T hidden, db1 = sum grad_out. */
+int ac_nsr_sdf_backward(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B,
+                        float bound, float *grad_table, float *delta_a, float *hidden, float *feats,
+                        void *stream);
 /* NeRFNetwork.forward_color (models/instant_nsr.py:644-663, use_viewdirs=False):
  * x [B,3], normal [B,3], geo_feat [B,15] -> rgb [B,3]. */
 int ac_nsr_forward_color(const ac_nsr_model *model, const float *x, const float *normal,

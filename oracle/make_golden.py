@@ -62,6 +62,14 @@ def pack(out):
                 pts_color=color.numpy(), pts_alpha=alpha.numpy(), z_vals=z.numpy())
 
 
+def training_loss(out, pixel_grad):
+    """The three terms stylize.py back-propagates per patch (:163-193): pixel gradient . rgb,
+    w_eikonal * eikonal, 1e5 * smooth_l1(clamp(opacity), target) -- target 0.5 stands in for net_gt."""
+    rgb, wsum, eik = out[3].reshape(-1, 3), out[2], out[5]
+    opacity = torch.nn.functional.smooth_l1_loss(wsum.clamp(0.0, 1.0), torch.full_like(wsum, 0.5)) * 1e5
+    return (rgb * pixel_grad).sum() + 0.01 * eik + opacity * 1e-3
+
+
 def compare(a, b, tag):
     worst = 0.0
     for k in a:
@@ -100,6 +108,41 @@ def main():
                             num_steps=ns, upsample_steps=us, bound=np.float32(1.6), kind=kind, seed=seed,
                             state_checksum=syn.state_checksum(sd), **out_ref)
         print(f"wrote {name}.npz  rays={ro.shape[0]} wsum mean={out_ref['weight_sum'].mean():.4f}")
+
+    # ---- gradient fixture: the reference's own autograd through its training-mode `run` ----
+    sd = syn.synthetic_state_dict("trained", 43)
+    o, d = syn.pinhole_rays(syn.orbit_pose(30.0), 256, 256)
+    sel = torch.arange(256 * 96 + 40, 256 * 160, 173)            # central rows: most rays hit the body
+    ro, rd = o[sel].contiguous(), d[sel].contiguous()
+    n = ro.shape[0]
+    G = torch.randn(n, 3, generator=torch.Generator().manual_seed(44))     # stands in for the SDS pixel gradient
+    torch.manual_seed(77)
+    jitter = torch.rand(n, 64)
+    net = ref_nsr.NeRFNetwork()
+    net.load_state_dict(sd)
+    net.train()
+    torch.manual_seed(77)
+    out = net.run(ro[None], rd[None], 64, 1.6, 64, None, cos_anneal_ratio=1.0, normal_epsilon_ratio=0.0,
+                  render_can=True, perturb_overwrite=True)
+    loss = training_loss(out, G)
+    loss.backward()
+    gref = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    orc = OracleNSR(sd)
+    params = orc.enable_grad(sd)
+    loss_o = training_loss(orc.run_grad(ro, rd, 64, 1.6, 64, jitter=jitter), G)
+    loss_o.backward()
+    for k, g in gref.items():
+        err = float((g - params[k].grad).abs().max())
+        assert err <= 2e-5 * max(1.0, float(g.abs().max())), (k, err)   # summation order of the broadcast variance
+    ge = gref["encoder.embeddings"]
+    nz = ge.abs().sum(1).nonzero().flatten()
+    pick = nz[torch.randperm(nz.numel(), generator=torch.Generator().manual_seed(3))[:20000]].sort()[0]
+    np.savez_compressed(os.path.join(GOLD, "grad_trained_jitter_64p64.npz"), rays_o=ro.numpy(), rays_d=rd.numpy(),
+                        jitter=jitter.numpy(), pixel_grad=G.numpy(), loss=np.float32(float(loss)),
+                        emb_rows=pick.numpy(), emb_grad=ge[pick].numpy(), emb_grad_abs_sum=np.float64(ge.abs().double().sum()),
+                        emb_grad_nnz=np.int64(nz.numel()), state_checksum=syn.state_checksum(sd),
+                        **{"g." + k: v.numpy() for k, v in gref.items() if k != "encoder.embeddings"})
+    print(f"wrote grad_trained_jitter_64p64.npz  rays={n} loss={float(loss):.4f} nnz table rows={nz.numel()}")
 
     # hash-encoder fixture through the reference's own HashEncoder.forward wrapper
     sd = syn.synthetic_state_dict("trained", 43)

@@ -20,6 +20,33 @@ import torch.nn.functional as F
 from . import hashgrid as _hg
 
 
+class _HashEncodeCPU(torch.autograd.Function):
+    """Autograd wrapper of the C restatement (forward + table backward), mirroring
+    encoder/hashencoder/hashgrid.py:11-73 so the oracle can produce parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, x01, table, offsets, per_level_scale, base_resolution, scales):
+        x01 = x01.detach().contiguous().float()
+        B, D = x01.shape
+        L, C = offsets.numel() - 1, table.shape[1]
+        S = float(np.log2(per_level_scale))
+        out = torch.empty(L, B, C)
+        _hg.hash_encode_forward(x01, table.detach().contiguous(), offsets, out, B, D, C, L, S, base_resolution, False, None,
+                                scales=scales)
+        ctx.save_for_backward(x01, offsets)
+        ctx.meta = (B, D, C, L, S, base_resolution, scales, table.shape)
+        return out.permute(1, 0, 2).reshape(B, L * C)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x01, offsets = ctx.saved_tensors
+        B, D, C, L, S, H, scales, shape = ctx.meta
+        g = grad.reshape(B, L, C).permute(1, 0, 2).contiguous()
+        gt = torch.zeros(shape)
+        _hg.hash_encode_backward(g, x01, None, offsets, gt, B, D, C, L, S, H, False, None, None, scales=scales)
+        return None, gt, None, None, None, None
+
+
 def fold_weight_norm(g, v):
     """Effective weight of nn.utils.weight_norm(dim=0): g * v / ||v||_row
     (models/instant_nsr.py:555-556,585-586).  torch._weight_norm is the very function the
@@ -50,6 +77,9 @@ class OracleNSR:
     # ---- encoder (encoder/hashencoder/hashgrid.py:126-142) -------------------------------
     def encode(self, x, bound, want_ids=False):
         x01 = (x + bound) / (2 * bound)
+        if self.table.requires_grad and not want_ids:
+            return _HashEncodeCPU.apply(x01, self.table, self.offsets, self.per_level_scale, self.base_resolution,
+                                        self.level_scales)
         return _hg.encode(x01, self.table, self.offsets, self.per_level_scale, self.base_resolution,
                           want_ids=want_ids, scales=self.level_scales)
 
@@ -136,9 +166,30 @@ class OracleNSR:
         return zz, sdf, order
 
     # ---- the render core (models/instant_nsr.py:133-299), render_can=True branch ----------
+    def enable_grad(self, state_dict):
+        """Make the parameters autograd leaves (keys of the reference state dict) so `run_grad` yields
+        d(loss)/d(parameter) exactly as the reference's autograd would (weight-norm fold included)."""
+        self.params = {k: v.detach().clone().float().requires_grad_(True) for k, v in state_dict.items()
+                       if v.is_floating_point()}
+        p = self.params
+        self.table = p["encoder.embeddings"]
+        self.sdf_w = [fold_weight_norm(p[f"sdf_net.{i}.weight_g"], p[f"sdf_net.{i}.weight_v"]) for i in range(2)]
+        self.sdf_b = [p[f"sdf_net.{i}.bias"] for i in range(2)]
+        self.col_w = [fold_weight_norm(p[f"color_net.{i}.weight_g"], p[f"color_net.{i}.weight_v"]) for i in range(3)]
+        self.variance = p["deviation_net.variance"]
+        return self.params
+
+    def run_grad(self, *args, **kwargs):
+        """`run` with autograd enabled for the render core; sample placement stays gradient-free
+        exactly as in the reference (`with torch.no_grad()`, models/instant_nsr.py:175-185)."""
+        return self._run(*args, grad=True, **kwargs)
+
     @torch.no_grad()
-    def run(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color=None, cos_anneal_ratio=1.0,
-            normal_epsilon_ratio=0.0, jitter=None, alpha_mask=None, trace=None):
+    def run(self, *args, **kwargs):
+        return self._run(*args, grad=False, **kwargs)
+
+    def _run(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color=None, cos_anneal_ratio=1.0,
+             normal_epsilon_ratio=0.0, jitter=None, alpha_mask=None, trace=None, grad=False):
         """rays_o/rays_d [N,3].  `jitter` [N,num_steps] in [0,1) replaces the reference's
         torch.rand draw (:162) so training-mode runs are reproducible.  Returns the same
         10-tuple as the reference.  `trace` (dict) receives intermediates for kernel tests."""
@@ -153,16 +204,17 @@ class OracleNSR:
         pts = (rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)).clamp(-bound, bound)
         T = num_steps
         if upsample_steps > 0:
-            sdf = self.forward_sdf(pts.reshape(-1, 3), bound)[:, :1].reshape(N, T)
-            if trace is not None:
-                trace["coarse_z"], trace["coarse_sdf"] = z.clone(), sdf.clone()
-            rounds = upsample_steps // 16
-            for i in range(rounds):
-                z_new, bins = self.up_sample(rays_o, rays_d, z, sdf, 16, 64 * 2 ** i)
-                z, sdf, order = self.cat_z_vals(rays_o, rays_d, z, z_new, sdf, bound, last=(i + 1 == rounds))
+            with torch.no_grad():           # sample placement carries no gradient (:175-185)
+                sdf = self.forward_sdf(pts.reshape(-1, 3), bound)[:, :1].reshape(N, T)
                 if trace is not None:
-                    trace[f"round{i}_znew"], trace[f"round{i}_bins"] = z_new.clone(), bins
-                    trace[f"round{i}_z"], trace[f"round{i}_sdf"] = z.clone(), sdf.clone()
+                    trace["coarse_z"], trace["coarse_sdf"] = z.clone(), sdf.clone()
+                rounds = upsample_steps // 16
+                for i in range(rounds):
+                    z_new, bins = self.up_sample(rays_o, rays_d, z, sdf, 16, 64 * 2 ** i)
+                    z, sdf, order = self.cat_z_vals(rays_o, rays_d, z, z_new, sdf, bound, last=(i + 1 == rounds))
+                    if trace is not None:
+                        trace[f"round{i}_znew"], trace[f"round{i}_bins"] = z_new.clone(), bins
+                        trace[f"round{i}_z"], trace[f"round{i}_sdf"] = z.clone(), sdf.clone()
             T += upsample_steps
         # section mid-points (:187-206); NB the tail delta keeps the COARSE step count (:160)
         deltas = torch.cat([z[:, 1:] - z[:, :-1], sample_dist * torch.ones_like(z[:, :1])], -1)

@@ -1,0 +1,80 @@
+"""GPU suite for the training path: parameter gradients of the product's
+autograd path (fused _SdfQuery forward/backward kernels + torch glue) against the reference's own
+autograd (fixture) and the live differentiable oracle.
+
+Tolerances: gradients are sums over ~12 000 samples x 7 points of terms that pass through
+sigmoid(403*sdf); the product and the reference agree on the sample depths only up to the
+chaotic-ray effect documented in DESIGN.md, so parameter gradients are compared in relative L2 norm
+(<= 2 %) and, on identical depths (z injected), elementwise to 1e-3 of the largest entry."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, state_dict, gpu_model
+from tests.test_oracle_cpu import training_loss
+from oracle.nsr_oracle import OracleNSR
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def product_grads(sd, ro, rd, jitter, G):
+    net = gpu_model(sd, train=True)
+    out = net.run(ro.cuda()[None], rd.cuda()[None], 64, 1.6, 64, None, 1.0, 0.0, perturb_overwrite=True, jitter=jitter.cuda())
+    loss = training_loss(out, G.cuda())
+    loss.backward()
+    return float(loss), {k: p.grad.detach().cpu() for k, p in net.named_parameters()}, out
+
+
+def test_parameter_gradients_against_reference_autograd_fixture():
+    g, sd = load_golden("grad_trained_jitter_64p64")
+    loss, grads, _ = product_grads(sd, torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]),
+                                   torch.from_numpy(g["jitter"]), torch.from_numpy(g["pixel_grad"]))
+    assert abs(loss - float(g["loss"])) < 2e-2 * max(1.0, abs(float(g["loss"])))
+    for k, v in grads.items():
+        if k == "encoder.embeddings":
+            rows = torch.from_numpy(g["emb_rows"])
+            assert rel_l2(v[rows].numpy(), g["emb_grad"]) < 0.05, (k, rel_l2(v[rows].numpy(), g["emb_grad"]))
+            assert abs(float(v.abs().double().sum()) / float(g["emb_grad_abs_sum"]) - 1.0) < 0.02
+        else:
+            assert rel_l2(v.numpy(), g["g." + k]) < 0.02, (k, rel_l2(v.numpy(), g["g." + k]))
+
+
+def test_sdf_query_backward_against_oracle_autograd():
+    """The fused backward kernel in isolation: d/d(table, W0, b0, W1, b1) of sum(out * R) on a flat
+    point list, against autograd through the oracle (C hash backward + torch linear layers)."""
+    from avatarcraft_b200.models.instant_nsr import _SdfQuery
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd, train=True)
+    gen = torch.Generator().manual_seed(8)
+    x = (torch.rand(30000, 3, generator=gen) * 2 - 1) * 1.6
+    R = torch.randn(30000, 16, generator=gen)
+    w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in net.sdf_net]
+    out = _SdfQuery.apply(x.cuda(), net.encoder.embeddings, w[0], net.sdf_net[0].bias, w[1], net.sdf_net[1].bias, net, 1.6)
+    (out * R.cuda()).sum().backward()
+    orc = OracleNSR(sd)
+    p = orc.enable_grad(sd)
+    (orc.forward_sdf(x, 1.6) * R).sum().backward()
+    for k in ("encoder.embeddings", "sdf_net.0.weight_v", "sdf_net.0.weight_g", "sdf_net.0.bias", "sdf_net.1.weight_v",
+              "sdf_net.1.weight_g", "sdf_net.1.bias"):
+        mine = dict(net.named_parameters())[k].grad.cpu().numpy()
+        ref = p[k].grad.numpy()
+        np.testing.assert_allclose(mine, ref, atol=2e-4 * float(np.abs(ref).max()), rtol=1e-3, err_msg=k)
+
+
+def test_training_forward_equals_fused_inference_render():
+    """Same rays, same jitter: the autograd path and the fused no-grad kernel produce the same image."""
+    g, sd = load_golden("grad_trained_jitter_64p64")
+    ro, rd, jit = (torch.from_numpy(g[k]).cuda() for k in ("rays_o", "rays_d", "jitter"))
+    net = gpu_model(sd, train=True)
+    out_g = net.run(ro[None], rd[None], 64, 1.6, 64, None, 1.0, 0.0, perturb_overwrite=True, jitter=jit)
+    with torch.no_grad():
+        out_n = net.run(ro[None], rd[None], 64, 1.6, 64, None, 1.0, 0.0, perturb_overwrite=True, jitter=jit)
+    assert torch.equal(out_g[9], out_n[9])
+    np.testing.assert_allclose(out_g[3].detach().cpu().numpy(), out_n[3].cpu().numpy(), atol=2e-4)
+    np.testing.assert_allclose(out_g[2].detach().cpu().numpy(), out_n[2].cpu().numpy(), atol=2e-4)
+    assert abs(float(out_g[5]) - float(out_n[5])) < 1e-4

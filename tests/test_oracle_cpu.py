@@ -133,3 +133,32 @@ def test_synthetic_rays_match_reference_camera():
     np.testing.assert_allclose(o[0].numpy(), [0, 0, 1.7], atol=1e-6)
     np.testing.assert_allclose(d[0].numpy(), [-0.4745, 0.4745, -0.7414], atol=1e-4)
     assert o.dtype == torch.float32 and abs(float(d.norm(dim=1).mean()) - 1) < 1e-6
+
+
+def training_loss(out, pixel_grad):
+    """Same three terms as oracle/make_golden.py::training_loss (stylize.py:163-193)."""
+    rgb, wsum, eik = out[3].reshape(-1, 3), out[2], out[5]
+    opacity = torch.nn.functional.smooth_l1_loss(wsum.clamp(0.0, 1.0), torch.full_like(wsum, 0.5)) * 1e5
+    return (rgb * pixel_grad).sum() + 0.01 * eik + opacity * 1e-3
+
+
+def test_oracle_gradients_match_reference_autograd_fixture():
+    """Parameter gradients of the differentiable oracle == the reference's own autograd
+    (fixture written from /root/reference by oracle/make_golden.py), training mode with jitter."""
+    g, sd = load_golden("grad_trained_jitter_64p64")
+    orc = OracleNSR(sd)
+    params = orc.enable_grad(sd)
+    out = orc.run_grad(torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]), 64, 1.6, 64,
+                       jitter=torch.from_numpy(g["jitter"]))
+    loss = training_loss(out, torch.from_numpy(g["pixel_grad"]))
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    loss.backward()
+    for k, p in params.items():
+        if k == "encoder.embeddings":
+            rows = torch.from_numpy(g["emb_rows"])
+            np.testing.assert_allclose(p.grad[rows].numpy(), g["emb_grad"], atol=1e-8, rtol=1e-4)
+            assert abs(float(p.grad.abs().double().sum()) - float(g["emb_grad_abs_sum"])) < 1e-5 * float(g["emb_grad_abs_sum"])
+            assert int((p.grad.abs().sum(1) > 0).sum()) == int(g["emb_grad_nnz"])
+        else:
+            ref = g["g." + k]
+            np.testing.assert_allclose(p.grad.numpy(), ref, atol=2e-5 * max(1.0, float(np.abs(ref).max())), rtol=1e-4)
