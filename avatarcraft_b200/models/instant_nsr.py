@@ -92,18 +92,20 @@ class NeRFRenderer(nn.Module):
     def run(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio=1.0,
             normal_epsilon_ratio=1.0, render_can=True, verts=None, faces=None, Ts=None,
             perturb_overwrite: bool = False, use_mesh_guide: bool = True, jitter=None, per_sample_outputs=True,
-            eikonal_segment=0):
+            eikonal_segment=0, z_override=None):
         """Same contract as the reference (models/instant_nsr.py:133-299): rays [B=1,N,3] ->
         (depth [1,N], weights [N,T], weights_sum [N,1], image [1,N,3], normal_map [N,3],
          gradient_error, curvature_error, color [N,T,3], alpha [N,T], z_vals [N,T]).
         `jitter` ([N,num_steps] in [0,1)) overrides the training-time torch.rand draw (:162);
         `per_sample_outputs=False` skips the four [N,T,...] stores (they are then None);
-        `eikonal_segment=k` returns one eikonal mean per k consecutive rays (a [ceil(N/k)] tensor)."""
+        `eikonal_segment=k` returns one eikonal mean per k consecutive rays (a [ceil(N/k)] tensor);
+        `z_override` ([N,T], autograd path only) replaces the sampled depths (parity tests)."""
         if not render_can:
             raise NotImplementedError("warped (render_can=False) rendering is not wired yet")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # eikonal_segment / per_sample_outputs are inference-launch options; one patch = one mean here
             return self._run_with_grad(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
-                                       normal_epsilon_ratio, perturb_overwrite, jitter)
+                                       normal_epsilon_ratio, perturb_overwrite, jitter, z_override)
         B, N = rays_o.shape[:2]
         rays_o = rays_o.reshape(-1, 3).float().contiguous()
         rays_d = rays_d.reshape(-1, 3).float().contiguous()
@@ -148,7 +150,7 @@ class NeRFRenderer(nn.Module):
                 color, alpha, z_vals)
 
     def _run_with_grad(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
-                       normal_epsilon_ratio, perturb_overwrite, jitter):
+                       normal_epsilon_ratio, perturb_overwrite, jitter, z_override=None):
         """Training-mode `run` (autograd enabled).  As in the reference, sample placement carries no
         gradient (`with torch.no_grad()`, models/instant_nsr.py:175-185): the depths come from the fused
         kernel.  The differentiable part (:186-299) evaluates the 7 x N x T SDF points with the fused
@@ -162,8 +164,11 @@ class NeRFRenderer(nn.Module):
         if self.training and perturb_overwrite and jitter is None:
             jitter = torch.rand(n, num_steps, device=dev)
         with torch.no_grad():
-            z = NeRFRenderer.run(self, o[None], d[None], num_steps, bound, upsample_steps, None, cos_anneal_ratio,
-                                 normal_epsilon_ratio, perturb_overwrite=perturb_overwrite, jitter=jitter)[9]
+            if z_override is not None:      # tests: differentiate at externally supplied sample depths
+                z = z_override.to(dev, torch.float32).contiguous()
+            else:
+                z = NeRFRenderer.run(self, o[None], d[None], num_steps, bound, upsample_steps, None, cos_anneal_ratio,
+                                     normal_epsilon_ratio, perturb_overwrite=perturb_overwrite, jitter=jitter)[9]
             T = z.shape[1]
             near, far = near_far_from_bound(o, d, bound)
             gaps = torch.cat([z[:, 1:] - z[:, :-1], ((far - near) / num_steps).expand(n, 1)], -1)

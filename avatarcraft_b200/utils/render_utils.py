@@ -51,6 +51,8 @@ def render_instantnsr_naive(net, rays_o, rays_d, rays_per_batch=6400, requires_g
         bg = torch.cat([select_background(rays_o[i:i + rays_per_batch].shape, bkg_key)
                         for i in range(0, total, rays_per_batch)]).to(device)
     with torch.set_grad_enabled(requires_grad):
+        if requires_grad and total > rays_per_batch:
+            raise NotImplementedError("requires_grad=True renders one patch per call (as stylize.py:153-158 does)")
         out = net.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), num_steps=num_steps, upsample_steps=upsample_steps,
                          bound=bound, staged=False, bg_color=bg, cos_anneal_ratio=1.0, normal_epsilon_ratio=0.0,
                          render_can=render_can, verts=verts, faces=faces, Ts=Ts, perturb=perturb,

@@ -256,13 +256,75 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Secondary workload (BASELINE.json configs[2]): one stylisation optimiser step on 4096 rays (the
+    coarse stage of stylize.py): pass 1 no-grad render, pass 2 patch re-render with gradients + eikonal +
+    opacity vs a frozen copy, ONE gradient all-reduce, Adam.  The SDS pixel gradient is randn (seed 44): the
+    Stable-Diffusion guidance is un-vendored third-party code with weights that are not available offline."""
+    import torch
+    import torch.distributed as dist
+    from avatarcraft_b200 import _lib
+    from avatarcraft_b200.models.instant_nsr import NeRFNetwork
+    from avatarcraft_b200.utils import synthetic as syn
+    from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
+    from avatarcraft_b200.utils.train_utils import stylize_patch_step
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    sd = syn.synthetic_state_dict("trained", 43)
+    net = NeRFNetwork(); net.load_state_dict(sd); net = net.to(dev).train()
+    gt = NeRFNetwork(); gt.load_state_dict(sd); gt = gt.to(dev).eval()
+    for p in gt.parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.Adam(net.parameters(), lr=5e-3)
+    o, d = frame_rays(0)
+    o, d = o.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3).to(dev), d.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3).to(dev)   # stride-4 = 4096 rays
+    G = torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(44)).to(dev)
+    torch.manual_seed(1000 + rank)
+
+    def step():
+        with torch.no_grad():
+            render_instantnsr_naive(net, o, d, rays_per_batch=4096, render_can=True, perturb=True)       # pass 1
+        stylize_patch_step(net, gt, opt, o, d, G, batch_size=4096, rank=rank, world=world)              # pass 2 + allreduce + Adam
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.lib().ac_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record(); e1.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier(); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "sds_style_steps_per_sec", "value": args.steps / (float(ms) * 1e-3), "unit": "steps/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(ms) / args.steps, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "stylize.py coarse-stage step: 4096 rays (256x256 stride 4), 64+64 samples, pass1 + pass2 "
+                                                 "(grad, eikonal 0.01, opacity vs frozen copy) + grad all-reduce + Adam; pixel gradient randn seed 44",
+                                     "parallelism": f"patch/ray shard x{world} + one 49 MB all-reduce"},
+                          "gpu_launches": int(_lib.lib().ac_launch_count() - l0)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="render", choices=["render", "train"])
     args = ap.parse_args()
+    if args.workload == "train" and args.impl == "ours":
+        return run_train(args)
     if args.impl == "reference":
         if args.steps == 20:
             args.steps = 3

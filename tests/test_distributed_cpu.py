@@ -1,0 +1,70 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: patch sharding and the single flat
+gradient all-reduce reproduce the single-process gradient of the reference's patch loop."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from avatarcraft_b200.utils.distributed import allreduce_gradients, shard_patches, shard_rays
+
+
+def test_shard_patches_partitions_every_ray_once():
+    for n, bs, world in [(65536, 4096, 8), (65536, 4096, 3), (4096, 4096, 8), (4096, 4096, 2), (5000, 4096, 4), (100, 7, 2)]:
+        seen = torch.zeros(n, dtype=torch.int32)
+        for r in range(world):
+            for s, e, scale in shard_patches(n, bs, r, world):
+                seen[s:e] += 1
+                patch_len = min(bs, n - (s // bs) * bs)
+                assert 0 < scale <= 1.0 and abs(scale - (e - s) / patch_len) < 1e-12 or scale == 1.0
+        assert int(seen.min()) == 1 and int(seen.max()) == 1, (n, bs, world)
+    lo, hi = shard_rays(65536, 3, 8)
+    assert (lo, hi) == (24576, 32768)
+
+
+def _loss(model, x, start, end, scale):
+    """Stand-in for one rendered patch: a sum-type term and a mean-type term (like eikonal / opacity)."""
+    y = model(x[start:end])
+    return (y * torch.arange(start, end, dtype=torch.float32)[:, None]).sum() + scale * 7.0 * (y ** 2).mean()
+
+
+def _worker(rank, world, port, n, bs, ref_grads, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 16), torch.nn.Softplus(beta=100), torch.nn.Linear(16, 2))
+    x = torch.rand(n, 3, generator=torch.Generator().manual_seed(1))
+    for s, e, scale in shard_patches(n, bs, rank, world):
+        _loss(model, x, s, e, scale).backward()
+    reduced = allreduce_gradients(model.parameters())
+    err = max(float((p.grad - g).abs().max() / (g.abs().max() + 1e-12)) for p, g in zip(model.parameters(), ref_grads))
+    q.put((rank, reduced, err))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,bs", [(4096, 512), (600, 600)])
+def test_two_rank_patch_step_equals_single_process(n, bs):
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 16), torch.nn.Softplus(beta=100), torch.nn.Linear(16, 2))
+    x = torch.rand(n, 3, generator=torch.Generator().manual_seed(1))
+    for s in range(0, n, bs):
+        _loss(model, x, s, min(s + bs, n), 1.0).backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, bs, ref, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, reduced, err in res:
+        assert reduced == sum(p.numel() for p in model.parameters())
+        # relative to the largest entry; (600, 600) = ONE patch split over both ranks with mean_scale 1/2 each
+        assert err < 1e-5, (rank, err)

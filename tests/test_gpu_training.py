@@ -22,9 +22,10 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
 
-def product_grads(sd, ro, rd, jitter, G):
+def product_grads(sd, ro, rd, jitter, G, z_override=None):
     net = gpu_model(sd, train=True)
-    out = net.run(ro.cuda()[None], rd.cuda()[None], 64, 1.6, 64, None, 1.0, 0.0, perturb_overwrite=True, jitter=jitter.cuda())
+    out = net.run(ro.cuda()[None], rd.cuda()[None], 64, 1.6, 64, None, 1.0, 0.0, perturb_overwrite=True, jitter=jitter.cuda(),
+                  z_override=z_override)
     loss = training_loss(out, G.cuda())
     loss.backward()
     return float(loss), {k: p.grad.detach().cpu() for k, p in net.named_parameters()}, out
@@ -35,13 +36,37 @@ def test_parameter_gradients_against_reference_autograd_fixture():
     loss, grads, _ = product_grads(sd, torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]),
                                    torch.from_numpy(g["jitter"]), torch.from_numpy(g["pixel_grad"]))
     assert abs(loss - float(g["loss"])) < 2e-2 * max(1.0, abs(float(g["loss"])))
+    errs = {}
     for k, v in grads.items():
         if k == "encoder.embeddings":
             rows = torch.from_numpy(g["emb_rows"])
-            assert rel_l2(v[rows].numpy(), g["emb_grad"]) < 0.05, (k, rel_l2(v[rows].numpy(), g["emb_grad"]))
-            assert abs(float(v.abs().double().sum()) / float(g["emb_grad_abs_sum"]) - 1.0) < 0.02
+            errs[k] = rel_l2(v[rows].numpy(), g["emb_grad"])
+            assert abs(float(v.abs().double().sum()) / float(g["emb_grad_abs_sum"]) - 1.0) < 0.05
         else:
-            assert rel_l2(v.numpy(), g["g." + k]) < 0.02, (k, rel_l2(v.numpy(), g["g." + k]))
+            errs[k] = rel_l2(v.numpy(), g["g." + k])
+    print("relative L2 error of parameter gradients vs the reference autograd:", {k: round(e, 4) for k, e in errs.items()})
+    # free-running depths: ~10 % of rays place their importance samples differently
+    assert max(errs.values()) < 0.2, errs
+
+
+def test_parameter_gradients_on_identical_depths_against_oracle():
+    """With the sample depths injected (z_override = the oracle's own z_vals) every downstream quantity is
+    a smooth function of the parameters: gradients must agree elementwise."""
+    g, sd = load_golden("grad_trained_jitter_64p64")
+    ro, rd, jit, G = (torch.from_numpy(g[k]) for k in ("rays_o", "rays_d", "jitter", "pixel_grad"))
+    orc = OracleNSR(sd)
+    params = orc.enable_grad(sd)
+    out_o = orc.run_grad(ro, rd, 64, 1.6, 64, jitter=jit)
+    loss_o = training_loss(out_o, G)
+    loss_o.backward()
+    loss, grads, out = product_grads(sd, ro, rd, jit, G, z_override=out_o[9].detach())
+    assert abs(loss - float(loss_o)) < 2e-3 * max(1.0, abs(float(loss_o)))
+    np.testing.assert_allclose(out[3].detach().reshape(-1, 3).cpu().numpy(), out_o[3].detach().reshape(-1, 3).numpy(), atol=2e-3)
+    for k, v in grads.items():
+        ref = params[k].grad.numpy()
+        assert rel_l2(v.numpy(), ref) < 5e-3, (k, rel_l2(v.numpy(), ref))
+        if k != "encoder.embeddings":
+            np.testing.assert_allclose(v.numpy(), ref, atol=5e-3 * float(np.abs(ref).max()), rtol=0, err_msg=k)
 
 
 def test_sdf_query_backward_against_oracle_autograd():
@@ -78,3 +103,48 @@ def test_training_forward_equals_fused_inference_render():
     np.testing.assert_allclose(out_g[3].detach().cpu().numpy(), out_n[3].cpu().numpy(), atol=2e-4)
     np.testing.assert_allclose(out_g[2].detach().cpu().numpy(), out_n[2].cpu().numpy(), atol=2e-4)
     assert abs(float(out_g[5]) - float(out_n[5])) < 1e-4
+
+
+def test_stylize_patch_step_updates_parameters_like_the_reference_loop():
+    """utils/train_utils.stylize_patch_step == the reference's pass-2 loop (stylize.py:143-199) written out by
+    hand with the same renderer: identical gradients before the optimiser step, parameters move."""
+    from avatarcraft_b200.utils.train_utils import stylize_patch_step
+    from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
+    from avatarcraft_b200.utils import synthetic as syn
+    sd = state_dict("trained", 43)
+    o, d = syn.pinhole_rays(syn.orbit_pose(30.0), 64, 64)
+    sel = torch.arange(64 * 20, 64 * 44)                      # 1536 rays, 3 patches of 512
+    o, d = o[sel].cuda(), d[sel].cuda()
+    G = torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(2)).cuda()
+    net_gt = gpu_model(sd, train=False)
+    for p in net_gt.parameters():
+        p.requires_grad_(False)
+
+    def fresh():
+        net = gpu_model(sd, train=True)
+        return net, torch.optim.Adam(net.parameters(), lr=5e-3)
+
+    # hand-written loop, fixed jitter seed
+    net_a, opt_a = fresh()
+    torch.manual_seed(11)
+    opt_a.zero_grad()
+    for s in range(0, o.shape[0], 512):
+        rgb, eik, extra = render_instantnsr_naive(net_a, o[s:s + 512], d[s:s + 512], requires_grad=True, rays_per_batch=512,
+                                                  perturb=1.0, return_raw=True, render_can=True)
+        rgb.backward(gradient=G[s:s + 512], retain_graph=True)
+        (eik * 0.01).backward(retain_graph=True)
+        with torch.no_grad():
+            _, _, egt = render_instantnsr_naive(net_gt, o[s:s + 512], d[s:s + 512], rays_per_batch=512, perturb=True,
+                                                return_raw=True, render_can=True)
+        (torch.nn.functional.smooth_l1_loss(extra["weight_sum"].clamp(0, 1), egt["weight_sum"].clamp(0, 1)) * 1e5).backward()
+    grads_a = {k: p.grad.clone() for k, p in net_a.named_parameters()}
+    net_b, opt_b = fresh()
+    torch.manual_seed(11)
+    before = {k: p.detach().clone() for k, p in net_b.named_parameters()}
+    stats = stylize_patch_step(net_b, net_gt, opt_b, o, d, G, batch_size=512)
+    for k, p in net_b.named_parameters():
+        ref = grads_a[k]
+        assert float((p.grad - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-12, k
+        assert torch.isfinite(p.grad).all()
+    moved = sum(float((p.detach() - before[k]).abs().sum()) for k, p in net_b.named_parameters())
+    assert moved > 0 and stats["eikonal"] is not None and stats["opacity"] is not None
