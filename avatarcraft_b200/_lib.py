@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libavatarcraft_b200.so")
-SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu"]
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -42,6 +42,7 @@ class NsrModel(ctypes.Structure):
 class NsrRenderArgs(ctypes.Structure):
     _fields_ = [("rays_o", ctypes.c_void_p), ("rays_d", ctypes.c_void_p),
                 ("bg_color", ctypes.c_void_p), ("jitter", ctypes.c_void_p), ("alpha_mask", ctypes.c_void_p),
+                ("z_in", ctypes.c_void_p), ("pts_in", ctypes.c_void_p), ("near_far_in", ctypes.c_void_p),
                 ("n_rays", ctypes.c_uint32), ("num_steps", ctypes.c_uint32), ("upsample_steps", ctypes.c_uint32),
                 ("eikonal_segment", ctypes.c_uint32),
                 ("bound", ctypes.c_float), ("cos_anneal_ratio", ctypes.c_float), ("normal_epsilon_ratio", ctypes.c_float),
@@ -67,6 +68,10 @@ _SIGNATURES = {
     "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
     "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),
     "ac_nsr_render": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrRenderArgs), _V]),
+    "ac_warp_mesh_bytes": (ctypes.c_uint64, [_U32]),
+    "ac_warp_prepare_mesh": (_I, [_V, _V, _U32, _U32, _V, _V]),
+    "ac_warp_samples_to_canonical": (_I, [_V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
+    "ac_mesh_guided_near_far": (_I, [_V, _V, _U32, _V, _U32, _F, _F, _V, _V]),
     "ac_nsr_debug_tc_layer": (_I, [_V, _V, _V, _V]),
     "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V, _V, _V]),
 }

@@ -538,6 +538,7 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
         eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(reinterpret_cast<float*>(a->workspace), a->n_rays, seg, a->eikonal);
         return acb::launched();
     }
+    if (a->z_in || a->pts_in || a->near_far_in) return AC_E_UNSUPPORTED;   // staged inputs: tensor-core kernel only
     RenderParams p;
     p.table = reinterpret_cast<const float2*>(m->embeddings);
     p.offsets = m->offsets; p.blob = m->mlp_blob; p.variance = m->variance;

@@ -218,12 +218,18 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
         r.ox = p.a.rays_o[3 * ray + 0]; r.oy = p.a.rays_o[3 * ray + 1]; r.oz = p.a.rays_o[3 * ray + 2];
         r.dx = p.a.rays_d[3 * ray + 0]; r.dy = p.a.rays_d[3 * ray + 1]; r.dz = p.a.rays_d[3 * ray + 2];
         float near, far;
-        ray_box(r, bound, near, far);
+        if (p.a.near_far_in) { near = p.a.near_far_in[2 * ray]; far = p.a.near_far_in[2 * ray + 1]; }
+        else ray_box(r, bound, near, far);
         const float span = far - near;
         const float sample_dist = span / (float)N0;
+        const bool staged = p.a.z_in != nullptr;       // sampling done by the host pipeline (warp path)
+        if (staged) {
+            for (int k = lane; k < Ttot; k += 32) zs[k] = p.a.z_in[(size_t)ray * Ttot + k];
+            __syncwarp();
+        }
 
         // ---- coarse samples (:155-174) and their SDF (:178) ----
-        for (int k0 = 0; k0 < N0; k0 += 32) {
+        for (int k0 = 0; k0 < N0 && !staged; k0 += 32) {
             const int k = min(k0 + lane, N0 - 1);
             float z = near + span * linspace01(k, N0);
             if (p.a.jitter) z = z + (p.a.jitter[(size_t)ray * N0 + k] - 0.5f) * sample_dist;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
 
         // ---- importance rounds (:182-184) ----
         int T = N0;
-        for (int i = 0; i < rounds; ++i) {
+        for (int i = 0; i < rounds && !staged; ++i) {
             float z_new; int below, above;
             importance_round(r, zs, sdfs, ta, tb, T, (float)(64 << i), lane, z_new, below, above);
             float s_new = 0.0f;
@@ -296,7 +302,10 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 const float zk = zs[k];
                 const float zmid = k < Ttot - 1 ? zk + 0.5f * (zs[k + 1] - zk) : zk;
                 float px, py, pz;
-                ray_point(r, zmid, px, py, pz);
+                if (p.a.pts_in) {
+                    const float* q3 = p.a.pts_in + 3 * ((size_t)ray * Ttot + k);
+                    px = q3[0]; py = q3[1]; pz = q3[2];
+                } else ray_point(r, zmid, px, py, pz);
                 px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
                 const float e = (dir & 1) ? -eps : eps;
                 const int ax = dir >> 1;
@@ -315,7 +324,10 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             const float delta = k < Ttot - 1 ? zs[k + 1] - zk : sample_dist;
             const float zmid = k < Ttot - 1 ? zk + 0.5f * delta : zk;
             float px, py, pz;
-            ray_point(r, zmid, px, py, pz);
+            if (p.a.pts_in) {
+                const float* q3 = p.a.pts_in + 3 * ((size_t)ray * Ttot + k);
+                px = q3[0]; py = q3[1]; pz = q3[2];
+            } else ray_point(r, zmid, px, py, pz);
             px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
             float o16[16];
             group_sdf_eval<true>(g, table, lv, sw, bound, px, py, pz, o16);

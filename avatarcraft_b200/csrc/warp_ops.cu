@@ -1,0 +1,228 @@
+// warp_ops.cu -- the SMPL-guided inverse warp of sample points, on the GPU.
+//
+// Reference: utils/ray_utils.py:62-90 warp_samples_to_canonical -- sample points go device->host,
+// libigl's AABB-tree closest-point query runs on the CPU, numpy inverts a blended 4x4 per point, and the
+// result goes back to the device, twice per ray batch (models/instant_nsr.py:166-172,198-203).
+// Here: one kernel per point set, no host round trip.  Closest point on the posed mesh is an exact
+// brute-force search over all triangles (Ericson's region test), pruned with per-triangle bounding
+// spheres; every lane walks the same triangle list, so triangle records are warp-uniform (broadcast)
+// loads from a 64-byte-per-triangle array staged through shared memory in tiles.
+// utils/ray_utils.py:277-294 geometry_guided_near_far becomes a warp-per-ray reduction over vertices.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/avatarcraft_b200.h"
+#include "launch_util.cuh"
+
+namespace {
+
+struct __align__(16) TriRec {     // 64 bytes
+    float ax, ay, az, r;          // vertex a, bounding-sphere radius
+    float abx, aby, abz, cx;      // edge b-a, sphere centre x
+    float acx, acy, acz, cy;      // edge c-a, sphere centre y
+    float cz; int32_t i0, i1, i2; // sphere centre z, vertex ids
+};
+
+__global__ void __launch_bounds__(256) mesh_prepare_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                                                           uint32_t face_stride, uint32_t n_faces, TriRec* __restrict__ out) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    const int32_t i0 = faces[(size_t)f * face_stride], i1 = faces[(size_t)f * face_stride + 1], i2 = faces[(size_t)f * face_stride + 2];
+    const float ax = verts[3 * i0], ay = verts[3 * i0 + 1], az = verts[3 * i0 + 2];
+    const float bx = verts[3 * i1], by = verts[3 * i1 + 1], bz = verts[3 * i1 + 2];
+    const float cx = verts[3 * i2], cy = verts[3 * i2 + 1], cz = verts[3 * i2 + 2];
+    TriRec t;
+    t.ax = ax; t.ay = ay; t.az = az;
+    t.abx = bx - ax; t.aby = by - ay; t.abz = bz - az;
+    t.acx = cx - ax; t.acy = cy - ay; t.acz = cz - az;
+    const float mx = (ax + bx + cx) / 3.0f, my = (ay + by + cy) / 3.0f, mz = (az + bz + cz) / 3.0f;
+    const float ra = (ax - mx) * (ax - mx) + (ay - my) * (ay - my) + (az - mz) * (az - mz);
+    const float rb = (bx - mx) * (bx - mx) + (by - my) * (by - my) + (bz - mz) * (bz - mz);
+    const float rc = (cx - mx) * (cx - mx) + (cy - my) * (cy - my) + (cz - mz) * (cz - mz);
+    t.cx = mx; t.cy = my; t.cz = mz;
+    t.r = sqrtf(fmaxf(ra, fmaxf(rb, rc))) * 1.0001f + 1e-7f;   // conservative
+    t.i0 = i0; t.i1 = i1; t.i2 = i2;
+    out[f] = t;
+}
+
+// Closest point on triangle (a, a+ab, a+ac) to p: returns squared distance and barycentrics (b0,b1,b2).
+__device__ __forceinline__ float closest_on_triangle(const TriRec& t, float px, float py, float pz, float& b1, float& b2) {
+    const float apx = px - t.ax, apy = py - t.ay, apz = pz - t.az;
+    const float d1 = t.abx * apx + t.aby * apy + t.abz * apz;
+    const float d2 = t.acx * apx + t.acy * apy + t.acz * apz;
+    float v, w;
+    do {
+        if (d1 <= 0.f && d2 <= 0.f) { v = 0.f; w = 0.f; break; }                          // vertex a
+        const float bpx = apx - t.abx, bpy = apy - t.aby, bpz = apz - t.abz;
+        const float d3 = t.abx * bpx + t.aby * bpy + t.abz * bpz;
+        const float d4 = t.acx * bpx + t.acy * bpy + t.acz * bpz;
+        if (d3 >= 0.f && d4 <= d3) { v = 1.f; w = 0.f; break; }                            // vertex b
+        const float vc = d1 * d4 - d3 * d2;
+        if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { v = d1 / (d1 - d3); w = 0.f; break; }   // edge ab
+        const float cpx = apx - t.acx, cpy = apy - t.acy, cpz = apz - t.acz;
+        const float d5 = t.abx * cpx + t.aby * cpy + t.abz * cpz;
+        const float d6 = t.acx * cpx + t.acy * cpy + t.acz * cpz;
+        if (d6 >= 0.f && d5 <= d6) { v = 0.f; w = 1.f; break; }                            // vertex c
+        const float vb = d5 * d2 - d1 * d6;
+        if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { v = 0.f; w = d2 / (d2 - d6); break; }   // edge ac
+        const float va = d3 * d6 - d5 * d4;
+        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {                            // edge bc
+            w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); v = 1.f - w; break;
+        }
+        const float den = 1.0f / (va + vb + vc);                                            // interior
+        v = vb * den; w = vc * den;
+    } while (false);
+    const float qx = apx - (t.abx * v + t.acx * w), qy = apy - (t.aby * v + t.acy * w), qz = apz - (t.abz * v + t.acz * w);
+    b1 = v; b2 = w;
+    return qx * qx + qy * qy + qz * qz;
+}
+
+constexpr int kTile = 512;       // triangles per shared-memory tile (32 KB)
+
+// pts [n,3] -> can_pts [n,3], mask [n] (dist^2 < threshold), optional closest [n,3], face_id [n], dist2 [n].
+// T [n_T,4,4] row-major per-vertex transforms whose last row is (0,0,0,c).
+__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, uint32_t n, const TriRec* __restrict__ tris,
+                                                                uint32_t n_faces, const float* __restrict__ T, float threshold,
+                                                                float* __restrict__ can_pts, float* __restrict__ mask,
+                                                                float* __restrict__ closest, int32_t* __restrict__ face_id,
+                                                                float* __restrict__ dist2_out) {
+    __shared__ TriRec tile[kTile];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    const uint32_t ii = live ? i : n - 1;
+    const float px = pts[3 * (size_t)ii], py = pts[3 * (size_t)ii + 1], pz = pts[3 * (size_t)ii + 2];
+    float best = INFINITY, best_sqrt = INFINITY, bb1 = 0.f, bb2 = 0.f;
+    uint32_t best_f = 0;
+    for (uint32_t base = 0; base < n_faces; base += kTile) {
+        const uint32_t cnt = min((uint32_t)kTile, n_faces - base);
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(tris + base);
+        float4* dst = reinterpret_cast<float4*>(tile);
+        for (uint32_t q = threadIdx.x; q < cnt * 4; q += blockDim.x) dst[q] = __ldg(src + q);
+        __syncthreads();
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const TriRec& t = tile[k];
+            const float dx = px - t.cx, dy = py - t.cy, dz = pz - t.cz;
+            const float dc = sqrtf(dx * dx + dy * dy + dz * dz);
+            if (dc - t.r >= best_sqrt) continue;                       // cannot beat the current best
+            float b1, b2;
+            const float d2 = closest_on_triangle(t, px, py, pz, b1, b2);
+            if (d2 < best) { best = d2; best_sqrt = sqrtf(d2); bb1 = b1; bb2 = b2; best_f = base + k; }
+        }
+    }
+    if (!live) return;
+    const TriRec t = tris[best_f];
+    const float b0 = 1.0f - bb1 - bb2;
+    // T_interp = sum_k b_k T[v_k]  (utils/ray_utils.py:80), then inverse applied to (p,1), xyz kept un-normalised (:84)
+    float M[12], c = 0.f;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) M[q] = 0.f;
+    const int32_t vid[3] = {t.i0, t.i1, t.i2};
+    const float bw[3] = {b0, bb1, bb2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* Tk = T + 16 * (size_t)vid[k];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) M[q] = fmaf(bw[k], Tk[q], M[q]);
+        c = fmaf(bw[k], Tk[15], c);
+    }
+    // rows of the 3x4: [m00 m01 m02 tx; m10 m11 m12 ty; m20 m21 m22 tz], last row (0,0,0,c)
+    const float m00 = M[0], m01 = M[1], m02 = M[2], tx = M[3];
+    const float m10 = M[4], m11 = M[5], m12 = M[6], ty = M[7];
+    const float m20 = M[8], m21 = M[9], m22 = M[10], tz = M[11];
+    const float c00 = m11 * m22 - m12 * m21, c01 = m12 * m20 - m10 * m22, c02 = m10 * m21 - m11 * m20;
+    const float det = m00 * c00 + m01 * c01 + m02 * c02;
+    const float id = 1.0f / det;
+    const float qx = px - tx / c, qy = py - ty / c, qz = pz - tz / c;     // inverse of [[M,t],[0,c]]: M^-1 (p - t/c)
+    const float ox = (c00 * qx + (m02 * m21 - m01 * m22) * qy + (m01 * m12 - m02 * m11) * qz) * id;
+    const float oy = (c01 * qx + (m00 * m22 - m02 * m20) * qy + (m02 * m10 - m00 * m12) * qz) * id;
+    const float oz = (c02 * qx + (m01 * m20 - m00 * m21) * qy + (m00 * m11 - m01 * m10) * qz) * id;
+    can_pts[3 * (size_t)i] = ox; can_pts[3 * (size_t)i + 1] = oy; can_pts[3 * (size_t)i + 2] = oz;
+    mask[i] = best < threshold ? 1.0f : 0.0f;
+    if (closest) {
+        closest[3 * (size_t)i] = t.ax + t.abx * bb1 + t.acx * bb2;
+        closest[3 * (size_t)i + 1] = t.ay + t.aby * bb1 + t.acy * bb2;
+        closest[3 * (size_t)i + 2] = t.az + t.abz * bb1 + t.acz * bb2;
+    }
+    if (face_id) face_id[i] = (int32_t)best_f;
+    if (dist2_out) dist2_out[i] = best;
+}
+
+// One warp per ray: near = min_v(z0 - dz), far = max_v(z0 + dz) over the vertex spheres the ray pierces
+// (utils/ray_utils.py:277-294); rays that miss every sphere fall back to the cube
+// (models/instant_nsr.py:147-153 + near_far_from_bound :58-77).
+__global__ void __launch_bounds__(256) mesh_near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t n_rays,
+                                                            const float* __restrict__ verts, uint32_t n_verts, float radius, float bound,
+                                                            float* __restrict__ near_far) {
+    const uint32_t ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ray >= n_rays) return;
+    const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
+    const float dx = rays_d[3 * ray], dy = rays_d[3 * ray + 1], dz = rays_d[3 * ray + 2];
+    float near = INFINITY, far = -INFINITY;
+    const float r2 = radius * radius;
+    for (uint32_t v = lane; v < n_verts; v += 32) {
+        const float ex = verts[3 * v] - ox, ey = verts[3 * v + 1] - oy, ez = verts[3 * v + 2] - oz;
+        const float z0 = ex * dx + ey * dy + ez * dz;
+        const float nn = sqrtf(ex * ex + ey * ey + ez * ez);
+        const float disc = r2 - (nn * nn - z0 * z0);
+        if (disc >= 0.f) {                      // sqrt of a negative -> NaN -> +-inf in the reference
+            const float h = sqrtf(disc);
+            near = fminf(near, z0 - h);
+            far = fmaxf(far, z0 + h);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        near = fminf(near, __shfl_xor_sync(0xffffffffu, near, o));
+        far = fmaxf(far, __shfl_xor_sync(0xffffffffu, far, o));
+    }
+    if (lane == 0) {
+        float cn = -INFINITY, cf = INFINITY;
+        const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float den = d3[k] + 1e-15f;
+            const float t0 = (-bound - o3[k]) / den, t1 = (bound - o3[k]) / den;
+            cn = fmaxf(cn, t0 < t1 ? t0 : t1);
+            cf = fminf(cf, t0 > t1 ? t0 : t1);
+        }
+        cn = fmaxf(cn, 0.05f);
+        near_far[2 * ray] = isinf(near) ? cn : near;
+        near_far[2 * ray + 1] = isinf(far) ? cf : far;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+uint64_t ac_warp_mesh_bytes(uint32_t n_faces) { return (uint64_t)n_faces * sizeof(TriRec); }
+
+int ac_warp_prepare_mesh(const float* verts, const int32_t* faces, uint32_t face_stride, uint32_t n_faces, void* mesh, void* stream) {
+    if (!verts || !faces || !mesh || face_stride < 3) return AC_E_INVALID_ARG;
+    if (n_faces == 0) return AC_OK;
+    mesh_prepare_kernel<<<(n_faces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts, faces, face_stride, n_faces,
+                                                                                 reinterpret_cast<TriRec*>(mesh));
+    return acb::launched();
+}
+
+int ac_warp_samples_to_canonical(const float* pts, uint32_t n_pts, const void* mesh, uint32_t n_faces, const float* T, float threshold,
+                                 float* can_pts, float* mask, float* closest, int32_t* face_id, float* dist2, void* stream) {
+    if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0) return AC_E_INVALID_ARG;
+    if (n_pts == 0) return AC_OK;
+    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, reinterpret_cast<const TriRec*>(mesh), n_faces,
+                                                                                   T, threshold, can_pts, mask, closest, face_id, dist2);
+    return acb::launched();
+}
+
+int ac_mesh_guided_near_far(const float* rays_o, const float* rays_d, uint32_t n_rays, const float* verts, uint32_t n_verts,
+                            float radius, float bound, float* near_far, void* stream) {
+    if (!rays_o || !rays_d || !verts || !near_far) return AC_E_INVALID_ARG;
+    if (n_rays == 0) return AC_OK;
+    mesh_near_far_kernel<<<(n_rays * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, verts, n_verts, radius, bound,
+                                                                                     near_far);
+    return acb::launched();
+}
+
+}  // extern "C"

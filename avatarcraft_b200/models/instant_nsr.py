@@ -101,7 +101,8 @@ class NeRFRenderer(nn.Module):
         `eikonal_segment=k` returns one eikonal mean per k consecutive rays (a [ceil(N/k)] tensor);
         `z_override` ([N,T], autograd path only) replaces the sampled depths (parity tests)."""
         if not render_can:
-            raise NotImplementedError("warped (render_can=False) rendering is not wired yet")
+            return self._run_warped(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
+                                    normal_epsilon_ratio, verts, faces, Ts, use_mesh_guide, per_sample_outputs, eikonal_segment)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # eikonal_segment / per_sample_outputs are inference-launch options; one patch = one mean here
             return self._run_with_grad(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
@@ -118,6 +119,15 @@ class NeRFRenderer(nn.Module):
             jitter = jitter.to(dev, torch.float32).contiguous()
         if bg_color is not None:
             bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
+        return self._launch_render(B, N, rays_o, rays_d, num_steps, upsample_steps, bound, bg_color, jitter, cos_anneal_ratio,
+                                   normal_epsilon_ratio, per_sample_outputs, eikonal_segment)
+
+    def _launch_render(self, B, N, rays_o, rays_d, num_steps, upsample_steps, bound, bg_color, jitter, cos_anneal_ratio,
+                       normal_epsilon_ratio, per_sample_outputs, eikonal_segment, alpha_mask=None, z_in=None, pts_in=None,
+                       near_far_in=None):
+        """One ac_nsr_render launch; returns the reference's 10-tuple."""
+        n, dev = rays_o.shape[0], rays_o.device
+        T = num_steps + upsample_steps
         model = self._device_model()
         f32 = dict(device=dev, dtype=torch.float32)
         rgb = torch.empty(n, 3, **f32); depth = torch.empty(n, **f32)
@@ -134,7 +144,10 @@ class NeRFRenderer(nn.Module):
         a = _lib.NsrRenderArgs(
             rays_o=rays_o.data_ptr(), rays_d=rays_d.data_ptr(),
             bg_color=None if bg_color is None else bg_color.data_ptr(),
-            jitter=None if jitter is None else jitter.data_ptr(), alpha_mask=None,
+            jitter=None if jitter is None else jitter.data_ptr(),
+            alpha_mask=None if alpha_mask is None else alpha_mask.data_ptr(),
+            z_in=None if z_in is None else z_in.data_ptr(), pts_in=None if pts_in is None else pts_in.data_ptr(),
+            near_far_in=None if near_far_in is None else near_far_in.data_ptr(),
             n_rays=n, num_steps=num_steps, upsample_steps=upsample_steps, eikonal_segment=int(eikonal_segment),
             bound=float(bound),
             cos_anneal_ratio=float(cos_anneal_ratio), normal_epsilon_ratio=float(normal_epsilon_ratio),
@@ -148,6 +161,58 @@ class NeRFRenderer(nn.Module):
         return (depth.reshape(B, N), weights, wsum.reshape(n, 1), rgb.reshape(B, N, 3), normal,
                 eik.reshape(()) if n_seg == 1 else eik, 0.0,
                 color, alpha, z_vals)
+
+    @torch.no_grad()
+    def _run_warped(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio, normal_epsilon_ratio,
+                    verts, faces, Ts, use_mesh_guide, per_sample_outputs, eikonal_segment):
+        """render_can=False (models/instant_nsr.py:147-153,166-172,198-203,245-248): mesh-guided near/far, coarse
+        points warped to canonical space before the SDF query, importance rounds on UN-warped points (the
+        reference's cat_z_vals, :464-469), section points warped again, alpha masked by dist^2 < 0.05.
+        Every stage is a kernel of libavatarcraft_b200.so; no host round trip."""
+        from ..utils.ray_utils import PosedMesh, warp_samples_to_canonical
+        B, N = rays_o.shape[:2]
+        o = rays_o.reshape(-1, 3).float().contiguous()
+        d = rays_d.reshape(-1, 3).float().contiguous()
+        n, dev = o.shape[0], o.device
+        L = _lib.lib()
+        mesh = PosedMesh(verts, faces, Ts, dev)
+        nf = torch.empty(n, 2, device=dev)
+        if use_mesh_guide:
+            _lib.check(L.ac_mesh_guided_near_far(_lib.ptr(o), _lib.ptr(d), n, _lib.ptr(mesh.verts), mesh.verts.shape[0],
+                                                 float(DEFAULT_GEO_THRESH), float(bound), _lib.ptr(nf), _lib.stream_ptr()),
+                       "ac_mesh_guided_near_far")
+        else:
+            near, far = near_far_from_bound(o, d, bound)
+            nf = torch.cat([near, far], -1).contiguous()
+        near, far = nf[:, :1], nf[:, 1:]
+        z = (near + (far - near) * torch.linspace(0.0, 1.0, num_steps, device=dev)[None]).contiguous()
+        T = num_steps
+        if upsample_steps > 0:
+            can, _, _, _ = warp_samples_to_canonical(o[:, None] + d[:, None] * z[..., None], None, None, None,
+                                                     DEFAULT_GEO_THRESH, mesh=mesh)
+            sdf = self.forward_sdf(can.clamp(-bound, bound).reshape(-1, 3), bound)[:, 0].reshape(n, T).contiguous()
+            rounds = upsample_steps // 16
+            for i in range(rounds):
+                z_new = torch.empty(n, 16, device=dev); bins = torch.empty(n, 16, 2, dtype=torch.int32, device=dev)
+                z_out = torch.empty(n, T + 16, device=dev); order = torch.empty(n, T + 16, dtype=torch.int32, device=dev)
+                _lib.check(L.ac_nsr_debug_upsample(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), _lib.ptr(sdf), n, T, float(64 * 2 ** i),
+                                                   None, None, _lib.ptr(z_new), _lib.ptr(bins), _lib.ptr(z_out), _lib.ptr(order),
+                                                   _lib.stream_ptr()), "ac_nsr_upsample_round")
+                if i + 1 < rounds:
+                    p_new = (o[:, None] + d[:, None] * z_new[..., None]).clamp(-bound, bound)        # un-warped (:464-465)
+                    s_new = self.forward_sdf(p_new.reshape(-1, 3), bound)[:, 0].reshape(n, 16)
+                    sdf = torch.gather(torch.cat([sdf, s_new], -1), 1, order.long()).contiguous()
+                z, T = z_out, T + 16
+        gaps = torch.cat([z[:, 1:] - z[:, :-1], (far - near) / num_steps], -1)
+        z_mid = torch.cat([z[:, :-1] + 0.5 * gaps[:, :-1], z[:, -1:]], -1)
+        P, _, _, mask = warp_samples_to_canonical(o[:, None] + d[:, None] * z_mid[..., None], None, None, None,
+                                                  DEFAULT_GEO_THRESH, mesh=mesh)
+        if bg_color is not None:
+            bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
+        return self._launch_render(B, N, o, d, num_steps, upsample_steps, bound, bg_color, None, cos_anneal_ratio,
+                                   normal_epsilon_ratio, per_sample_outputs, eikonal_segment,
+                                   alpha_mask=mask.float().contiguous(), z_in=z.contiguous(), pts_in=P.contiguous(),
+                                   near_far_in=nf.contiguous())
 
     def _run_with_grad(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
                        normal_epsilon_ratio, perturb_overwrite, jitter, z_override=None):

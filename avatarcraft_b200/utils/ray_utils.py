@@ -1,0 +1,72 @@
+"""Device-side counterparts of the reference's utils/ray_utils.py warp helpers.
+
+The reference moves every sample point to the host, queries libigl's AABB tree, inverts a blended 4x4 per
+point in numpy and moves the result back (utils/ray_utils.py:62-90; models/instant_nsr.py:166-172,198-203).
+These functions keep the same call shape but take and return CUDA tensors and run as single kernels."""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .constant import DEFAULT_GEO_THRESH
+
+
+class PosedMesh:
+    """Per-frame device copy of the posed SMPL surface: vertices, faces, per-vertex transforms and the
+    64-byte triangle records (vertex, two edges, bounding sphere, ids) the warp kernel walks."""
+
+    def __init__(self, verts, faces, Ts, device):
+        self.verts = torch.as_tensor(np.asarray(verts), dtype=torch.float32).to(device).contiguous()
+        f = torch.as_tensor(np.asarray(faces)).to(torch.int32).to(device).contiguous()
+        self.faces = f
+        T = torch.as_tensor(np.asarray(Ts), dtype=torch.float32)
+        if float(T[:, 3, :3].abs().max()) != 0.0:
+            raise RuntimeError("per-vertex transforms must be affine up to a homogeneous scale: last rows (0,0,0,c)")
+        self.Ts = T.to(device).contiguous()
+        self.n_faces = int(f.shape[0])
+        L = _lib.lib()
+        self.records = torch.empty(int(L.ac_warp_mesh_bytes(self.n_faces)), dtype=torch.uint8, device=device)
+        _lib.check(L.ac_warp_prepare_mesh(_lib.ptr(self.verts), _lib.ptr(f), int(f.shape[1]), self.n_faces,
+                                          _lib.ptr(self.records), _lib.stream_ptr()), "ac_warp_prepare_mesh")
+
+
+def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMesh = None, return_query=False):
+    """pts [num_rays, num_samples, 3] (CUDA) -> can_pts, can_dirs, closest, mask -- the reference's return tuple
+    (utils/ray_utils.py:62-90).  `can_dirs` is computed like the reference does although nothing downstream
+    reads it (models/instant_nsr.py:203,208)."""
+    assert pts.dim() == 3 and pts.shape[-1] == 3, 'pts should have shape [num_rays, num_samples, 3]'
+    if mesh is None:
+        mesh = PosedMesh(verts, faces, T, pts.device)
+    R, S, _ = pts.shape
+    flat = pts.reshape(-1, 3).float().contiguous()
+    n = flat.shape[0]
+    can = torch.empty_like(flat); mask = torch.empty(n, device=flat.device)
+    closest = torch.empty_like(flat)
+    face = torch.empty(n, dtype=torch.int32, device=flat.device) if return_query else None
+    dist2 = torch.empty(n, device=flat.device) if return_query else None
+    _lib.check(_lib.lib().ac_warp_samples_to_canonical(_lib.ptr(flat), n, _lib.ptr(mesh.records), mesh.n_faces, _lib.ptr(mesh.Ts),
+                                                       float(threshold), _lib.ptr(can), _lib.ptr(mask), _lib.ptr(closest),
+                                                       _lib.ptr(face), _lib.ptr(dist2), _lib.stream_ptr()),
+               "ac_warp_samples_to_canonical")
+    can = can.reshape(R, S, 3)
+    dirs = can[:, 1:] - can[:, :-1]
+    dirs = torch.cat([dirs, dirs[:, -1:]], dim=1)
+    dirs = dirs / torch.linalg.norm(dirs, dim=2, keepdim=True)
+    out = (can, dirs, closest.reshape(R, S, 3), mask.reshape(R, S) > 0.5)
+    return out + (face.reshape(R, S), dist2.reshape(R, S)) if return_query else out
+
+
+def geometry_guided_near_far(orig, dir, vert, geo_threshold=DEFAULT_GEO_THRESH, bound=None):
+    """near/far [n] from the radius-`geo_threshold` spheres around the posed vertices
+    (utils/ray_utils.py:277-294).  With `bound` given, rays that pierce no sphere fall back to the cube
+    intersection as models/instant_nsr.py:147-153 does; without it they get +-inf like the reference helper."""
+    vert = torch.as_tensor(np.asarray(vert) if not isinstance(vert, torch.Tensor) else vert, dtype=torch.float32).to(orig.device).contiguous()
+    o, d = orig.reshape(-1, 3).float().contiguous(), dir.reshape(-1, 3).float().contiguous()
+    nf = torch.empty(o.shape[0], 2, device=o.device)
+    _lib.check(_lib.lib().ac_mesh_guided_near_far(_lib.ptr(o), _lib.ptr(d), o.shape[0], _lib.ptr(vert), vert.shape[0],
+                                                  float(geo_threshold), float(bound if bound is not None else 1e30), _lib.ptr(nf),
+                                                  _lib.stream_ptr()), "ac_mesh_guided_near_far")
+    if bound is None:
+        raise NotImplementedError("pass bound: the cube fallback is fused into the kernel")
+    return nf[:, 0], nf[:, 1]

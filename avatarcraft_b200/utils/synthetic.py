@@ -109,3 +109,54 @@ def pinhole_rays(c2w, width, height):
     d = world - origin
     d = d / np.linalg.norm(d, axis=1, keepdims=True)
     return torch.from_numpy(origin), torch.from_numpy(d.astype(np.float32))
+
+
+def synthetic_body(pose_seed=46, amplitude=0.35):
+    """SMPL-shaped stand-in (the licensed SMPL model and smpl_uv.obj are not in the repo, readme.md:41-59):
+    a closed genus-0 mesh with SMPL's exact counts -- 6890 vertices, 13776 faces (82 rings x 84 segments + 2
+    poles) -- a 24-joint chain with smooth skinning weights, and per-vertex rest->pose 4x4 transforms built the
+    way render_warp.py:127-222 composes them (blend of rigid joint transforms, times diag(1/0.9) INCLUDING the
+    homogeneous entry).  Returns dict(rest_verts [6890,3], world_verts [6890,3] f32, faces [13776,6] int32 (first 3
+    columns = vertex ids, like utils.read_obj), Ts [6914,4,4] f32)."""
+    R, S = 82, 84
+    rng = np.random.default_rng(pose_seed)
+    ys = np.cos(np.linspace(0, np.pi, R + 2))[1:-1]                 # ring heights in (-1, 1), top to bottom
+    ang = np.linspace(0, 2 * np.pi, S, endpoint=False)
+    prof = np.sqrt(np.clip(1 - ys ** 2, 0, None)) * (1.0 + 0.25 * np.cos(3.0 * np.pi * ys))   # waist / shoulders
+    rings = np.stack([np.outer(prof, np.cos(ang)) * 0.28, np.repeat(ys[:, None], S, 1) * 0.85, np.outer(prof, np.sin(ang)) * 0.17], -1)
+    verts = np.concatenate([[[0, 0.85, 0]], rings.reshape(-1, 3), [[0, -0.85, 0]]]).astype(np.float64)
+    f = []
+    top, bot = 0, 1 + R * S
+    idx = lambda r, s: 1 + r * S + (s % S)
+    for s in range(S):
+        f.append((top, idx(0, s + 1), idx(0, s)))
+        f.append((bot, idx(R - 1, s), idx(R - 1, s + 1)))
+        for r in range(R - 1):
+            f.append((idx(r, s), idx(r, s + 1), idx(r + 1, s)))
+            f.append((idx(r, s + 1), idx(r + 1, s + 1), idx(r + 1, s)))
+    faces = np.array(f, dtype=np.int32)
+    assert verts.shape[0] == 6890 and faces.shape[0] == 13776
+    # 24-joint chain along y, smooth weights (4 neighbouring joints per vertex)
+    joints = np.stack([np.zeros(24), np.linspace(0.8, -0.8, 24), np.zeros(24)], -1)
+    dj = np.abs(verts[:, 1:2] - joints[None, :, 1])
+    w = np.exp(-(dj / 0.08) ** 2)
+    w[np.arange(6890)[:, None], np.argsort(-w, 1)[:, 4:]] = 0.0
+    w /= w.sum(1, keepdims=True)
+    # forward kinematics: small random axis-angle per joint, chained
+    A = np.zeros((24, 4, 4)); G = np.eye(4)
+    for j in range(24):
+        aa = rng.normal(size=3) * amplitude * (0.3 if j else 0.1)
+        th = np.linalg.norm(aa) + 1e-12
+        k = aa / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        Rm = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+        L = np.eye(4); L[:3, :3] = Rm; L[:3, 3] = joints[j] - Rm @ joints[j]      # rotate about the joint
+        G = G @ L
+        A[j] = G
+    T_v = np.einsum("vj,jab->vab", w, A)                                  # per-vertex blended transform
+    T_all = np.concatenate([T_v, A], 0)                                    # 6890 vertices + 24 joints ("concat_joints")
+    world = (T_v[:, :3, :3] @ verts[:, :, None])[:, :, 0] + T_v[:, :3, 3]
+    Ts = T_all @ (np.eye(4) / 0.9)
+    faces6 = np.concatenate([faces, faces], 1)
+    return dict(rest_verts=verts.astype(np.float32), world_verts=world.astype(np.float32), faces=faces6,
+                Ts=Ts.astype(np.float32))

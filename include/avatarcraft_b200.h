@@ -131,6 +131,11 @@ int ac_nsr_fd_gradient(const ac_nsr_model *model, const float *x, float *grad, u
 typedef struct ac_nsr_render_args {
     const float *rays_o, *rays_d;
     const float *bg_color, *jitter, *alpha_mask;
+    /* Optional stage inputs (all NULL for the plain canonical render).  When the SMPL warp is active
+     * (render_can=False) the host runs sampling and warping as separate launches and hands the fused
+     * kernel its results: z_in [n,T] sorted sample depths (skips sampling), pts_in [n,T,3] the
+     * (warped) section points at which the network is evaluated, near_far_in [n,2]. */
+    const float *z_in, *pts_in, *near_far_in;
     uint32_t n_rays, num_steps, upsample_steps, eikonal_segment;
     float bound, cos_anneal_ratio, normal_epsilon_ratio;
     float *rgb, *depth, *weight_sum, *normal;
@@ -153,6 +158,26 @@ int ac_nsr_render(const ac_nsr_model *model, const ac_nsr_render_args *args, voi
 int ac_nsr_debug_upsample(const float *rays_o, const float *rays_d, const float *z, const float *sdf,
                           uint32_t n_rays, uint32_t T, float inv_s, const float *alpha_in, float *alpha_out,
                           float *z_new, int32_t *bins, float *z_out, int32_t *order, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * SMPL-guided inverse warp (utils/ray_utils.py).
+ * ac_warp_prepare_mesh: verts [n_verts,3], faces [n_faces,face_stride] int32 (first 3 columns are
+ *   vertex ids, as read_obj returns 6 columns) -> opaque mesh records (ac_warp_mesh_bytes bytes).
+ * ac_warp_samples_to_canonical = warp_samples_to_canonical (utils/ray_utils.py:62-90):
+ *   pts [n,3] -> can_pts [n,3] = (sum_k b_k T[v_k])^-1 (p,1) (xyz, un-normalised), mask [n] =
+ *   (closest squared distance < threshold) as 0/1 floats; optional closest [n,3], face_id [n],
+ *   dist2 [n].  T [n_T,4,4] row-major fp32, last rows (0,0,0,c).
+ * ac_mesh_guided_near_far = geometry_guided_near_far_torch (utils/ray_utils.py:277-294) with the
+ *   cube fallback of models/instant_nsr.py:147-153: near_far [n_rays,2].
+ * ------------------------------------------------------------------------------------ */
+uint64_t ac_warp_mesh_bytes(uint32_t n_faces);
+int ac_warp_prepare_mesh(const float *verts, const int32_t *faces, uint32_t face_stride, uint32_t n_faces,
+                         void *mesh, void *stream);
+int ac_warp_samples_to_canonical(const float *pts, uint32_t n_pts, const void *mesh, uint32_t n_faces,
+                                 const float *T, float threshold, float *can_pts, float *mask,
+                                 float *closest, int32_t *face_id, float *dist2, void *stream);
+int ac_mesh_guided_near_far(const float *rays_o, const float *rays_d, uint32_t n_rays, const float *verts,
+                            uint32_t n_verts, float radius, float bound, float *near_far, void *stream);
 
 /* Unit test of the tensor-core layer in isolation: feats [128,32] fp32 x (sdf layer 0 feature
  * columns)^T -> out [128,64] pre-activations WITHOUT bias / xyz terms (3xTF32 tcgen05.mma). */

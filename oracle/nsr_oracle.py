@@ -189,7 +189,8 @@ class OracleNSR:
         return self._run(*args, grad=False, **kwargs)
 
     def _run(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color=None, cos_anneal_ratio=1.0,
-             normal_epsilon_ratio=0.0, jitter=None, alpha_mask=None, trace=None, grad=False):
+             normal_epsilon_ratio=0.0, jitter=None, alpha_mask=None, trace=None, grad=False,
+             verts=None, faces=None, Ts=None, use_mesh_guide=True):
         """rays_o/rays_d [N,3].  `jitter` [N,num_steps] in [0,1) replaces the reference's
         torch.rand draw (:162) so training-mode runs are reproducible.  Returns the same
         10-tuple as the reference.  `trace` (dict) receives intermediates for kernel tests."""
@@ -197,11 +198,25 @@ class OracleNSR:
         rays_d = rays_d.reshape(-1, 3).float()
         N = rays_o.shape[0]
         near, far = self.near_far(rays_o, rays_d, bound)
+        warp = None
+        if verts is not None:                      # render_can=False branch (:147-153, :166-172, :198-203)
+            from . import warp_oracle as _wo
+            if use_mesh_guide:
+                gn, gf = _wo.geometry_guided_near_far(rays_o, rays_d, verts, 0.05)
+                near = torch.where(torch.isinf(gn)[:, None], near, gn[:, None])
+                far = torch.where(torch.isinf(gf)[:, None], far, gf[:, None])
+
+            def warp(p):                           # float64 numpy round trip, then .float() like the reference
+                can, mask, *_ = _wo.warp_samples_to_canonical(p.numpy(), verts, faces, Ts, 0.05)
+                return torch.from_numpy(can), torch.from_numpy(mask)
         z = near + (far - near) * torch.linspace(0.0, 1.0, num_steps).unsqueeze(0).expand(N, num_steps)
         sample_dist = (far - near) / num_steps
         if jitter is not None:
             z = z + (jitter - 0.5) * sample_dist
-        pts = (rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)).clamp(-bound, bound)
+        pts = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)
+        if warp is not None:
+            pts, _ = warp(pts)
+        pts = pts.clamp(-bound, bound).float()
         T = num_steps
         if upsample_steps > 0:
             with torch.no_grad():           # sample placement carries no gradient (:175-185)
@@ -219,7 +234,11 @@ class OracleNSR:
         # section mid-points (:187-206); NB the tail delta keeps the COARSE step count (:160)
         deltas = torch.cat([z[:, 1:] - z[:, :-1], sample_dist * torch.ones_like(z[:, :1])], -1)
         z_mid = torch.cat([z[:, :-1] + 0.5 * deltas[:, :-1], z[:, -1:]], -1)
-        P = (rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_mid.unsqueeze(-1)).clamp(-bound, bound).reshape(-1, 3)
+        P = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_mid.unsqueeze(-1)
+        if warp is not None:                       # NB cat_z_vals evaluated the up-sample SDF at UN-warped points (:464-469)
+            P, wmask = warp(P)
+            alpha_mask = wmask.float()
+        P = P.clamp(-bound, bound).float().reshape(-1, 3)
         dirs = rays_d.unsqueeze(-2).expand(N, T, 3).reshape(-1, 3)
         out = self.forward_sdf(P, bound)
         sdf, feat = out[:, :1], out[:, 1:]

@@ -162,3 +162,26 @@ def test_oracle_gradients_match_reference_autograd_fixture():
         else:
             ref = g["g." + k]
             np.testing.assert_allclose(p.grad.numpy(), ref, atol=2e-5 * max(1.0, float(np.abs(ref).max())), rtol=1e-4)
+
+
+def test_warp_oracle_geometry():
+    """Closed-form checks of the restated closest-point / warp (igl is unavailable, so these pin the
+    restatement to geometry, not to igl): points on the surface have distance 0; a point above a face
+    centroid projects onto it with barycentrics (1/3,1/3,1/3); identity-like transforms scale by 0.9."""
+    from oracle import warp_oracle as wo
+    body = syn.synthetic_body()
+    assert body["world_verts"].shape == (6890, 3) and body["faces"].shape == (13776, 6) and body["Ts"].shape == (6914, 4, 4)
+    V, F = body["rest_verts"].astype(np.float64), body["faces"][:, :3]
+    tri = V[F[100:140]]
+    cen = tri.mean(1)
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    d2, face, closest, bary = wo.closest_point_on_mesh(cen + 0.01 * nrm, V, F)
+    np.testing.assert_allclose(d2, 1e-4, rtol=1e-6)
+    np.testing.assert_allclose(closest, cen, atol=1e-12)
+    assert (face == np.arange(100, 140)).all() and np.allclose(bary, 1 / 3)
+    d2v, *_ = wo.closest_point_on_mesh(V[:64], V, F)
+    assert d2v.max() < 1e-24
+    T = np.tile(np.eye(4) / 0.9, (6914, 1, 1))
+    can, mask, *_ = wo.warp_samples_to_canonical((cen + 0.01 * nrm)[None], V, body["faces"], T, 0.05)
+    np.testing.assert_allclose(can[0], 0.9 * (cen + 0.01 * nrm), atol=1e-12)       # inverse of diag(1/0.9): xyz * 0.9, w ignored
+    assert mask.all()
