@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libavatarcraft_b200.so")
-SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu"]
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -60,6 +60,8 @@ _SIGNATURES = {
     "ac_launch_count": (ctypes.c_uint64, []),
     "ac_hash_encode_forward": (_I, [_V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
     "ac_hash_encode_backward": (_I, [_V, _V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
+    "ac_sh_encode_forward": (_I, [_V, _V, _U32, _U32, _U32, _I, _V, _V]),
+    "ac_sh_encode_backward": (_I, [_V, _V, _U32, _U32, _U32, _V, _V, _V]),
     "ac_hash_level_scales": (_I, [_V, _U32, _F, _U32, _V]),
     "ac_nsr_pack_mlp": (_I, [_V] * 13 + [_V]),
     "ac_nsr_forward_sdf": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V]),

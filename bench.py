@@ -171,6 +171,8 @@ def run_ours(args):
     o, d = o_h.to(dev), d_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    torch.set_grad_enabled(False)          # inference: the fused kernel, no autograd graph (render_canonical.py is no-grad)
+
     def step_resident():
         return net.run(o[None], d[None], NUM_STEPS, BOUND, UPSAMPLE_STEPS, None, 1.0, 0.0, per_sample_outputs=False)
 

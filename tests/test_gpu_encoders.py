@@ -1,0 +1,75 @@
+"""GPU suite for the spherical-harmonics encoder op (dormant in the reference unless
+use_viewdirs=True, models/instant_nsr.py:564-569).  Oracle: oracle/sh_oracle.py (closed forms from the
+reference's own comments for degree <= 3, scipy's complex harmonics on unit vectors for all 64)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sh_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode(x, degree, jac=True):
+    from avatarcraft_b200.encoder.shencoder.backend import _backend
+    B = x.shape[0]
+    out = torch.empty(B, degree * degree, device="cuda")
+    dy_dx = torch.empty(B, 3 * degree * degree, device="cuda")
+    _backend.sh_encode_forward(x, out, B, 3, degree, jac, dy_dx)
+    torch.cuda.synchronize()
+    return out, dy_dx.reshape(B, 3, degree * degree)
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_sh_forward_against_scipy_on_unit_vectors(degree):
+    p = np.random.default_rng(degree).normal(size=(4000, 3))
+    p /= np.linalg.norm(p, axis=1, keepdims=True)
+    p[:3] = np.eye(3)                                                     # poles / axes
+    out, _ = _encode(torch.from_numpy(p).float().cuda(), degree)
+    ref = so.sh_scipy(p, degree)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=3e-5, rtol=2e-5)
+
+
+def test_sh_non_unit_inputs_and_jacobian_against_closed_forms():
+    """Arbitrary (non-normalised) xyz: the polynomials of shencoder.cu:48-58; Jacobian vs float64 central differences."""
+    p = np.random.default_rng(1).uniform(-1.5, 1.5, size=(3000, 3))
+    out, jac = _encode(torch.from_numpy(p).float().cuda(), 3)
+    np.testing.assert_allclose(out.cpu().numpy(), so.sh_closed_form(p), atol=5e-6, rtol=1e-5)
+    h = 1e-6
+    for d in range(3):
+        e = np.zeros(3); e[d] = h
+        fd = (so.sh_closed_form(p + e) - so.sh_closed_form(p - e)) / (2 * h)
+        np.testing.assert_allclose(jac[:, d].cpu().numpy(), fd, atol=2e-5, rtol=1e-5)
+
+
+def test_sh_jacobian_consistent_with_forward_degree8_and_backward():
+    """Degree 8: Jacobian vs central differences of the op's own forward (fp32, h=2e-3), and the backward op
+    grad_inputs[b,d] = sum_c grad[b,c] dy_dx[b,d,c] (shencoder.cu:360-384)."""
+    from avatarcraft_b200.encoder.shencoder.backend import _backend
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(2000, 3, generator=g) * 2 - 1).cuda()
+    out, jac = _encode(x, 8)
+    h = 2e-3
+    for d in range(3):
+        e = torch.zeros(3, device="cuda"); e[d] = h
+        fd = (_encode(x + e, 8, False)[0] - _encode(x - e, 8, False)[0]) / (2 * h)
+        scale = float(jac[:, d].abs().max())
+        assert float((jac[:, d] - fd).abs().max()) < 5e-3 * scale
+    grad = torch.randn(2000, 64, generator=g).cuda()
+    gi = torch.zeros(2000, 3, device="cuda")
+    _backend.sh_encode_backward(grad, x, 2000, 3, 8, jac.reshape(2000, -1).contiguous(), gi)
+    np.testing.assert_allclose(gi.cpu().numpy(), torch.einsum("bc,bdc->bd", grad, jac).cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+def test_sh_module_and_factory():
+    from avatarcraft_b200.encoder import get_encoder
+    enc, dim = get_encoder("sphere_harmonics", {"in_dim": 3})
+    assert dim == 16
+    d = torch.nn.functional.normalize(torch.randn(100, 3), dim=-1).cuda().requires_grad_(True)
+    y = enc(d)
+    y.sum().backward()
+    assert y.shape == (100, 16) and d.grad.shape == (100, 3) and torch.isfinite(d.grad).all()
+    np.testing.assert_allclose(y.detach().cpu().numpy(), so.sh_scipy(d.detach().cpu().numpy().astype(np.float64), 4), atol=2e-5)
+    with pytest.raises(RuntimeError):
+        from avatarcraft_b200.encoder.shencoder.backend import _backend
+        _backend.sh_encode_forward(d.detach(), y.detach(), 100, 3, 9, False, y.detach())     # degree 9 unsupported

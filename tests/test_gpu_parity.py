@@ -200,7 +200,7 @@ def _render(net, o, d, ns, us, jitter=None, **kw):
 def test_fused_render_against_reference_fixture(name):
     g, sd = load_golden(name)
     training = g["jitter"].size > 0
-    net = gpu_model(sd, train=training)
+    net = gpu_model(sd, train=training, grad=False)      # fused inference kernel, training-mode jitter injected
     jit = torch.from_numpy(g["jitter"]) if training else None
     depth, weights, wsum, image, nmap, eik, _, color, alpha, z = _render(
         net, torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"]), int(g["num_steps"]), int(g["upsample_steps"]), jit)

@@ -33,10 +33,14 @@ def psnr(a, b):
     return 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
 
 
-def gpu_model(sd, train=False):
+def gpu_model(sd, train=False, grad=None):
+    """Product model on cuda:0.  `grad` (default = `train`) decides whether parameters require grad: with
+    autograd on, `run` takes the differentiable path exactly like the reference would build a graph."""
     from avatarcraft_b200.models.instant_nsr import NeRFNetwork
     net = NeRFNetwork()
     net.load_state_dict(sd)
     net = net.cuda()
     net.train(train)
+    for p in net.parameters():
+        p.requires_grad_(train if grad is None else grad)
     return net
