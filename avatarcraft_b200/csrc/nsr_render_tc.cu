@@ -1,22 +1,25 @@
 // nsr_render_tc.cu -- the fused Instant-NSR render core, tensor-core edition (sm_100a).
 //
-// Persistent kernel, one CTA of 16 warps per SM.  A warp still owns a ray from box intersection
-// to composited pixel (nsr_device.cuh), but the SDF network's first layer -- 32 hash features ->
-// 64 hidden units, 84 % of the network's multiply-adds -- runs on the 5th-generation tensor cores:
+// Persistent kernel: one CTA of 32 warps (1024 threads, <= 64 registers) per SM, all 512 TMEM columns.
+// A warp owns a ray from box intersection to composited pixel (nsr_device.cuh); four warps form a
+// GROUP whose 128 lanes are the 128 rows of one MMA tile.  Every dense layer that matters runs on the
+// 5th-generation tensor cores (tcgen05.mma, kind::f16, fp32 accumulate in TMEM):
 //
-//   * four warps form a GROUP; one lane = one sample point = one row of a 128 x 32 A tile.  Each
-//     lane hash-encodes its point, splits the 32 fp32 features into tf32 (hi, lo) pairs and stores
-//     them into the group's A tiles in the UMMA K-major no-swizzle layout (16-byte row chunks,
-//     conflict-free st.shared.v4).
-//   * one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N64 K8; 4 K-steps x {hi*hi, lo*hi,
-//     hi*lo} = "3xTF32", error ~2^-22) against the weight tiles resident in shared memory; the fp32
-//     accumulator lives in the group's 64 TMEM columns; tcgen05.commit -> mbarrier.
-//   * every lane pulls its accumulator row back with tcgen05.ld, adds the raw-xyz columns and the
-//     bias in exact fp32 (the xyz part dominates the SDF and feeds the +-0.005 finite differences),
-//     applies softplus(beta=100) and finishes the 64 -> {1,16} second layer in registers.
+//   SDF layer 0   32 hash features -> 64 hidden      fp16x3: A = (hi, lo), B = (hi, lo); hi*hi + lo*hi + hi*lo,
+//                                                    6 MMAs M128 N64 K16; relative error ~2^-21 (fp32-class)
+//   colour 0      21 (padded 32) -> 64               fp16x3, 6 MMAs
+//   colour 1      64 -> 64                           A = fp16(h1) single, B = (hi, lo): 8 MMAs (colour tolerates 2^-11)
 //
-// Groups are independent (own A tiles, TMEM columns, named barrier, mbarrier), so while one group
-// waits on its MMA the other three keep the LSU / FMA / MUFU pipes busy with gathers and epilogues.
+// A rows are written by the lane that owns the point (hash-encode -> split -> st.shared.v4 into the
+// UMMA K-major no-swizzle layout: 16-byte chunks, 2 KB chunk stride), one elected thread issues the MMAs
+// and commits to the group's mbarrier, every lane reads its accumulator row back with tcgen05.ld.
+// The raw-xyz columns of SDF layer 0 + bias are added in exact fp32 in the epilogue (they dominate the
+// SDF and feed the +-0.005 finite differences), softplus(beta=100) costs two MUFU ops, and the 64 -> {1,16}
+// second SDF layer and the 64 -> 3 colour head are short register dot products.
+//
+// fp16x3 instead of 3xTF32 halves the A-tile footprint (16 KB per group), which is what lets 8 groups =
+// 32 warps share one SM: the kernel is bound by gather latency (ncu: long_scoreboard), so resident warps
+// are the lever.  Groups are independent (own A tile, 64 TMEM columns, named barrier, mbarrier).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -30,19 +33,26 @@ using namespace acb;
 
 namespace {
 
-constexpr int kGroups = 4;                      // groups of 4 warps per CTA
-constexpr int kWarpsTC = 4 * kGroups;           // 16 warps, 512 threads
+constexpr int kGroups = 8;                      // groups of 4 warps per CTA
+constexpr int kWarpsTC = 4 * kGroups;           // 32 warps, 1024 threads
 constexpr int kMaxT = 128;
-constexpr int kFeat = 32;                       // hash features = K of the tensor-core layer
-constexpr uint32_t kTmemCols = 64 * kGroups;    // 256 columns: one 128x64 fp32 accumulator per group
+constexpr uint32_t kTmemCols = 64 * kGroups;    // 512: one 128x64 fp32 accumulator per group
+
+// fp32 essentials kept for the epilogues (floats)
+constexpr int W_XB = 0;                         // [64][4]  (wx, wy, wz, b0) of SDF layer 0
+constexpr int W_W1T = W_XB + 64 * 4;            // [64][16] SDF layer 1, transposed
+constexpr int W_B1 = W_W1T + 64 * 16;           // [16]
+constexpr int W_C2T = W_B1 + 16;                // [64][4]  colour head, transposed (col 3 = 0)
+constexpr int W_FLOATS = W_C2T + 64 * 4;        // 1552
 
 // dynamic shared memory map (bytes)
-constexpr size_t SM_BLOB = 0;                                             // packed fp32 weights (SIMT part)
-constexpr size_t SM_LEVELS = SM_BLOB + BLOB_FLOATS * 4;                   // 16 x LevelMeta
-constexpr size_t SM_B = (SM_LEVELS + kLevels * sizeof(LevelMeta) + 127) / 128 * 128;   // B_hi 8 KB, B_lo 8 KB
-constexpr size_t SM_A = SM_B + 2 * 64 * kFeat * 4;                        // per group: A_hi 16 KB, A_lo 16 KB
-constexpr size_t SM_ROWS = SM_A + (size_t)kGroups * 2 * 128 * kFeat * 4;  // per warp: 4 rows x 128 floats
-constexpr size_t SM_BARS = SM_ROWS + (size_t)kWarpsTC * 4 * kMaxT * 4;    // mbarriers + tmem slot
+constexpr size_t SM_W32 = 0;
+constexpr size_t SM_LEVELS = SM_W32 + W_FLOATS * 4;
+constexpr size_t SM_B = (SM_LEVELS + kLevels * sizeof(LevelMeta) + 127) / 128 * 128;
+constexpr uint32_t B_W0_HI = 0, B_W0_LO = 4096, B_C0_HI = 8192, B_C0_LO = 12288, B_C1_HI = 16384, B_C1_LO = 24576, B_BYTES = 32768;
+constexpr size_t SM_A = SM_B + B_BYTES;                                   // per group 16 KB: hi [4 chunks] | lo [4 chunks]
+constexpr size_t SM_ROWS = SM_A + (size_t)kGroups * 16384;                // per warp: depths, sdf, scratch (3 x 128 floats)
+constexpr size_t SM_BARS = SM_ROWS + (size_t)kWarpsTC * 3 * kMaxT * 4;
 constexpr size_t SM_TOTAL = SM_BARS + kGroups * 8 + 16;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -58,19 +68,50 @@ struct RenderParamsTC {
 };
 
 struct Group {
-    float* a_hi;          // this group's A tiles, [8 chunks][128 rows][4 floats]
-    float* a_lo;
-    uint32_t a_hi_s, a_lo_s, b_hi_s, b_lo_s;   // shared-space addresses for the descriptors
+    unsigned char* a;     // this group's A region (generic pointer)
+    uint32_t a_s;         // ... and its shared-space address
+    uint32_t b_s;         // shared-space address of the weight tiles
     uint64_t* bar;
     uint32_t phase;
-    uint32_t tmem;        // TMEM address of this thread's accumulator row (lane field set), column 0 of the group
-    uint32_t tmem_d;      // accumulator base for the MMA (lane 0)
+    uint32_t tmem;        // accumulator address of this thread's row (lane field set), column 0 of the group
     uint32_t bar_id;
     int row;              // 0..127 inside the group
 };
 
-// Hash-encode (features only) -> A tiles -> tcgen05.mma -> epilogue.  Must be called by all 128
-// threads of the group, the same number of times.
+// Make this thread's A-row stores visible to the tensor core, rendezvous the group, let one thread issue,
+// wait for the commit.  `issue` runs in exactly one thread.
+template <class Issue>
+__device__ __forceinline__ void group_mma_round(Group& g, Issue issue) {
+    tc05::fence_proxy_async_smem();
+    tc05::fence_before_sync();
+    tc05::named_bar_sync(g.bar_id, 128);
+    if (g.row == 0) {
+        tc05::fence_after_sync();
+        issue();
+        tc05::mma_commit(g.bar);
+    }
+    tc05::mbar_wait(g.bar, g.phase);
+    g.phase ^= 1u;
+    tc05::fence_after_sync();
+}
+
+// D[128x64] = A(hi,lo)[128x32] * B(hi,lo)[64x32]^T with the three fp16 partial products.
+__device__ __forceinline__ void issue_k32_x3(uint32_t tmem_d, uint32_t a_s, uint32_t bhi_s, uint32_t blo_s) {
+    constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
+#pragma unroll
+    for (uint32_t s = 0; s < 2; ++s) {               // K = 32 = 2 x (K=16): chunks 2s, 2s+1
+        const uint64_t ah = tc05::smem_desc(a_s + s * 4096u, 2048u, 128u);
+        const uint64_t al = tc05::smem_desc(a_s + 8192u + s * 4096u, 2048u, 128u);
+        const uint64_t bh = tc05::smem_desc(bhi_s + s * 2048u, 1024u, 128u);
+        const uint64_t bl = tc05::smem_desc(blo_s + s * 2048u, 1024u, 128u);
+        tc05::mma_f16(tmem_d, ah, bh, idesc, s);
+        tc05::mma_f16(tmem_d, al, bh, idesc, 1u);
+        tc05::mma_f16(tmem_d, ah, bl, idesc, 1u);
+    }
+}
+
+// Hash-encode (features only) -> A tile -> tcgen05.mma -> epilogue.  Must be called by all 128 threads of the
+// group, the same number of times.
 template <bool FULL>
 __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
                                                const float* __restrict__ sw, float bound, float x, float y, float z,
@@ -80,55 +121,39 @@ __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restric
         const float u = (x + bound) / two_b, v = (y + bound) / two_b, w = (z + bound) / two_b;
         const bool oob = (u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {               // 2 levels = 4 features = one 16-byte chunk of the row
-            float2 f0 = make_float2(0.f, 0.f), f1 = f0;
+        for (int c = 0; c < 4; ++c) {               // 4 levels = 8 features = one 16-byte fp16 chunk of the row
+            uint4 hi, lo;
+            float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
             if (!oob) {
-                f0 = grid_level_3d(table, lv[2 * c], u, v, w);
-                f1 = grid_level_3d(table, lv[2 * c + 1], u, v, w);
+                f0 = grid_level_3d(table, lv[4 * c + 0], u, v, w);
+                f1 = grid_level_3d(table, lv[4 * c + 1], u, v, w);
+                f2 = grid_level_3d(table, lv[4 * c + 2], u, v, w);
+                f3 = grid_level_3d(table, lv[4 * c + 3], u, v, w);
             }
-            float4 hi, lo;
-            tc05::split_tf32(f0.x, hi.x, lo.x); tc05::split_tf32(f0.y, hi.y, lo.y);
-            tc05::split_tf32(f1.x, hi.z, lo.z); tc05::split_tf32(f1.y, hi.w, lo.w);
-            *reinterpret_cast<float4*>(g.a_hi + c * 512 + g.row * 4) = hi;
-            *reinterpret_cast<float4*>(g.a_lo + c * 512 + g.row * 4) = lo;
+            tc05::split_f16x2(f0.x, f0.y, hi.x, lo.x);
+            tc05::split_f16x2(f1.x, f1.y, hi.y, lo.y);
+            tc05::split_f16x2(f2.x, f2.y, hi.z, lo.z);
+            tc05::split_f16x2(f3.x, f3.y, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(g.a + c * 2048 + g.row * 16) = hi;
+            *reinterpret_cast<uint4*>(g.a + 8192 + c * 2048 + g.row * 16) = lo;
         }
     }
-    tc05::fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-    tc05::fence_before_sync();           // orders this thread's earlier tcgen05.ld before the next MMA
-    tc05::named_bar_sync(g.bar_id, 128);
-    if (g.row == 0) {
-        tc05::fence_after_sync();
-        constexpr uint32_t idesc = tc05::idesc_tf32(128, 64);
-#pragma unroll
-        for (uint32_t s = 0; s < 4; ++s) {           // K = 32 = 4 x (K=8): chunks 2s, 2s+1
-            const uint64_t ah = tc05::smem_desc(g.a_hi_s + s * 4096u, 2048u, 128u);
-            const uint64_t al = tc05::smem_desc(g.a_lo_s + s * 4096u, 2048u, 128u);
-            const uint64_t bh = tc05::smem_desc(g.b_hi_s + s * 2048u, 1024u, 128u);
-            const uint64_t bl = tc05::smem_desc(g.b_lo_s + s * 2048u, 1024u, 128u);
-            tc05::mma_tf32(g.tmem_d, ah, bh, idesc, s > 0 ? 1u : 0u);
-            tc05::mma_tf32(g.tmem_d, al, bh, idesc, 1u);
-            tc05::mma_tf32(g.tmem_d, ah, bl, idesc, 1u);
-        }
-        tc05::mma_commit(g.bar);
-    }
-    tc05::mbar_wait(g.bar, g.phase);
-    g.phase ^= 1u;
-    tc05::fence_after_sync();
+    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_W0_HI, g.b_s + B_W0_LO); });
 
 #pragma unroll
-    for (int o = 0; o < (FULL ? 16 : 1); ++o) out[o] = sw[OFF_B1 + o];
+    for (int o = 0; o < (FULL ? 16 : 1); ++o) out[o] = sw[W_B1 + o];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float acc[32];
-        tc05::tmem_ld32(g.tmem + half * 32, acc);
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float acc[16];
+        tc05::tmem_ld16(g.tmem + qtr * 16, acc);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = half * 32 + jj;
-            const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W0 + j * kSdfInPad);   // (wx, wy, wz, .)
-            const float lin = fmaf(wx.x, x, fmaf(wx.y, y, fmaf(wx.z, z, sw[OFF_B0 + j])));
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = qtr * 16 + jj;
+            const float4 xb = *reinterpret_cast<const float4*>(sw + W_XB + 4 * j);
+            const float lin = fmaf(xb.x, x, fmaf(xb.y, y, fmaf(xb.z, z, xb.w)));
             const float h = softplus100_mufu(acc[jj] + lin);
             if (FULL) {
-                const float4* __restrict__ w1 = reinterpret_cast<const float4*>(sw + OFF_W1T + j * 16);
+                const float4* __restrict__ w1 = reinterpret_cast<const float4*>(sw + W_W1T + j * 16);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 w4 = w1[q];
@@ -138,38 +163,111 @@ __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restric
                     out[4 * q + 3] = fmaf(w4.w, h, out[4 * q + 3]);
                 }
             } else {
-                out[0] = fmaf(sw[OFF_W1T + j * 16], h, out[0]);
+                out[0] = fmaf(sw[W_W1T + j * 16], h, out[0]);
             }
         }
     }
 }
 
+// Colour MLP 21 -> 64 -> 64 -> 3 (models/instant_nsr.py:644-663) for the group's 128 samples.
+// cin = (x, y, z, nx, ny, nz, 15 geometry features); all 128 threads of the group call it together.
+__device__ __forceinline__ void group_color_eval(Group& g, const float* __restrict__ sw, const float (&cin)[24], float (&rgb)[3]) {
+    // layer 0: K = 32 (21 inputs + zero pad), fp16x3
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 hi, lo;
+        if (c < 3) {
+            tc05::split_f16x2(cin[8 * c + 0], cin[8 * c + 1], hi.x, lo.x);
+            tc05::split_f16x2(cin[8 * c + 2], cin[8 * c + 3], hi.y, lo.y);
+            tc05::split_f16x2(cin[8 * c + 4], cin[8 * c + 5], hi.z, lo.z);
+            tc05::split_f16x2(cin[8 * c + 6], cin[8 * c + 7], hi.w, lo.w);
+        } else {
+            hi = make_uint4(0u, 0u, 0u, 0u); lo = hi;
+        }
+        *reinterpret_cast<uint4*>(g.a + c * 2048 + g.row * 16) = hi;
+        *reinterpret_cast<uint4*>(g.a + 8192 + c * 2048 + g.row * 16) = lo;
+    }
+    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_C0_HI, g.b_s + B_C0_LO); });
+    // relu -> fp16 -> A tile of layer 1 (K = 64 = 8 chunks, fills the whole 16 KB region)
+#pragma unroll
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float acc[16];
+        tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint4 pk;
+            pk.x = tc05::pack_f16x2(fmaxf(acc[8 * half + 0], 0.f), fmaxf(acc[8 * half + 1], 0.f));
+            pk.y = tc05::pack_f16x2(fmaxf(acc[8 * half + 2], 0.f), fmaxf(acc[8 * half + 3], 0.f));
+            pk.z = tc05::pack_f16x2(fmaxf(acc[8 * half + 4], 0.f), fmaxf(acc[8 * half + 5], 0.f));
+            pk.w = tc05::pack_f16x2(fmaxf(acc[8 * half + 6], 0.f), fmaxf(acc[8 * half + 7], 0.f));
+            *reinterpret_cast<uint4*>(g.a + (2 * qtr + half) * 2048 + g.row * 16) = pk;
+        }
+    }
+    group_mma_round(g, [&] {
+        constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
+#pragma unroll
+        for (uint32_t s = 0; s < 4; ++s) {           // K = 64 = 4 x (K=16)
+            const uint64_t ad = tc05::smem_desc(g.a_s + s * 4096u, 2048u, 128u);
+            const uint64_t bh = tc05::smem_desc(g.b_s + B_C1_HI + s * 2048u, 1024u, 128u);
+            const uint64_t bl = tc05::smem_desc(g.b_s + B_C1_LO + s * 2048u, 1024u, 128u);
+            tc05::mma_f16(g.tmem & 0xFFFFu, ad, bh, idesc, s);
+            tc05::mma_f16(g.tmem & 0xFFFFu, ad, bl, idesc, 1u);
+        }
+    });
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float acc[16];
+        tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const float h2 = fmaxf(acc[jj], 0.f);
+            const float4 c2 = *reinterpret_cast<const float4*>(sw + W_C2T + 4 * (qtr * 16 + jj));
+            o0 = fmaf(c2.x, h2, o0); o1 = fmaf(c2.y, h2, o1); o2 = fmaf(c2.z, h2, o2);
+        }
+    }
+    rgb[0] = sigmoidf(o0); rgb[1] = sigmoidf(o1); rgb[2] = sigmoidf(o2);
+}
+
+// Weight W[n][k] (n < 64) -> fp16 (hi, lo) tiles in the UMMA K-major layout: chunk k/8, row n, element k%8.
+__device__ __forceinline__ void stage_b_tile(unsigned char* bhi, unsigned char* blo, int n, int k, float w) {
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    const int at = (k >> 3) * 1024 + n * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(bhi + at) = h;
+    *reinterpret_cast<__half*>(blo + at) = l;
+}
+
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const RenderParamsTC p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* sw = reinterpret_cast<float*>(smem + SM_BLOB);
+    float* sw = reinterpret_cast<float*>(smem + SM_W32);
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
-    float* b_hi = reinterpret_cast<float*>(smem + SM_B);
-    float* b_lo = b_hi + 64 * kFeat;
+    unsigned char* bt = smem + SM_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroups);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp >> 2;
 
-    // ---- one-time staging: fp32 blob, level table, tf32 weight tiles, barriers, TMEM ----
+    // ---- one-time staging: fp32 epilogue weights, level table, fp16 weight tiles, barriers, TMEM ----
     {
-        const float4* src = reinterpret_cast<const float4*>(p.blob);
-        float4* dst = reinterpret_cast<float4*>(sw);
-        for (int i = threadIdx.x; i < BLOB_FLOATS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        const float* blob = p.blob;
+        for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
+            const int j = i >> 2, q = i & 3;
+            sw[W_XB + i] = q < 3 ? __ldg(blob + OFF_W0 + j * kSdfInPad + q) : __ldg(blob + OFF_B0 + j);
+            sw[W_C2T + i] = __ldg(blob + OFF_C2T + i);
+        }
+        for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[W_W1T + i] = __ldg(blob + OFF_W1T + i);
+        if (threadIdx.x < 16) sw[W_B1 + threadIdx.x] = __ldg(blob + OFF_B1 + threadIdx.x);
         if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(p.offsets, threadIdx.x, p.S, p.H, 3);
-        // B tiles: W0[n][3 + k] for n < 64, k < 32 -> [chunk k/4][n][k%4], hi and lo parts
-        for (int i = threadIdx.x; i < 64 * kFeat; i += blockDim.x) {
-            const int n = i / kFeat, k = i % kFeat;
-            float hi, lo;
-            tc05::split_tf32(__ldg(p.blob + OFF_W0 + n * kSdfInPad + 3 + k), hi, lo);
-            const int at = (k >> 2) * 256 + n * 4 + (k & 3);
-            b_hi[at] = hi;
-            b_lo[at] = lo;
+        for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+            const int n = i >> 5, k = i & 31;
+            stage_b_tile(bt + B_W0_HI, bt + B_W0_LO, n, k, __ldg(blob + OFF_W0 + n * kSdfInPad + 3 + k));
+            stage_b_tile(bt + B_C0_HI, bt + B_C0_LO, n, k, k < kColInPad ? __ldg(blob + OFF_C0 + n * kColInPad + k) : 0.f);
+        }
+        for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+            const int n = i >> 6, k = i & 63;
+            stage_b_tile(bt + B_C1_HI, bt + B_C1_LO, n, k, __ldg(blob + OFF_C1 + n * kHidden + k));
         }
         if (threadIdx.x == 0) {
             for (int gI = 0; gI < kGroups; ++gI) tc05::mbar_init(bars + gI, 1);
@@ -184,21 +282,19 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     const uint32_t tmem_base = *tmem_slot;
 
     Group g;
-    g.a_hi = reinterpret_cast<float*>(smem + SM_A) + (size_t)group * 2 * 128 * kFeat;
-    g.a_lo = g.a_hi + 128 * kFeat;
-    g.a_hi_s = tc05::smem_u32(g.a_hi); g.a_lo_s = tc05::smem_u32(g.a_lo);
-    g.b_hi_s = tc05::smem_u32(b_hi); g.b_lo_s = tc05::smem_u32(b_lo);
+    g.a = smem + SM_A + (size_t)group * 16384;
+    g.a_s = tc05::smem_u32(g.a);
+    g.b_s = tc05::smem_u32(bt);
     g.bar = bars + group;
     g.phase = 0;
     g.row = (warp & 3) * 32 + lane;
-    g.tmem_d = tmem_base + (uint32_t)group * 64u;
-    g.tmem = g.tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    g.tmem = tmem_base + (uint32_t)group * 64u + ((uint32_t)((warp & 3) * 32) << 16);
     g.bar_id = 1 + group;
 
-    float* zs = reinterpret_cast<float*>(smem + SM_ROWS) + warp * 4 * kMaxT;
-    float* sdfs = zs + kMaxT;
-    float* ta = sdfs + kMaxT;
-    float* tb = ta + kMaxT;
+    float* zs = reinterpret_cast<float*>(smem + SM_ROWS) + warp * 3 * kMaxT;   // sorted depths
+    float* sdfs = zs + kMaxT;                                                  // their SDF
+    float* ta = sdfs + kMaxT;                                                  // scratch (alpha, then cdf)
+    float* fd = sdfs;                                                          // 192 finite-difference values (render core)
 
     const float bound = p.a.bound;
     const float2* __restrict__ table = p.table;
@@ -209,6 +305,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     const float eps = 0.005f * (1.0f - p.a.normal_epsilon_ratio);
     const float car = p.a.cos_anneal_ratio;
     const uint32_t n_quads = (p.a.n_rays + 3) / 4;
+    const bool staged = p.a.z_in != nullptr;       // sampling done by the host pipeline (warp path)
 
     for (uint32_t quad = blockIdx.x * kGroups + group; quad < n_quads; quad += gridDim.x * kGroups) {
         const uint32_t ray_raw = quad * 4 + (warp & 3);
@@ -222,7 +319,6 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
         else ray_box(r, bound, near, far);
         const float span = far - near;
         const float sample_dist = span / (float)N0;
-        const bool staged = p.a.z_in != nullptr;       // sampling done by the host pipeline (warp path)
         if (staged) {
             for (int k = lane; k < Ttot; k += 32) zs[k] = p.a.z_in[(size_t)ray * Ttot + k];
             __syncwarp();
@@ -245,11 +341,11 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
         }
         __syncwarp();
 
-        // ---- importance rounds (:182-184) ----
+        // ---- importance rounds (:182-184), merged in place ----
         int T = N0;
         for (int i = 0; i < rounds && !staged; ++i) {
             float z_new; int below, above;
-            importance_round(r, zs, sdfs, ta, tb, T, (float)(64 << i), lane, z_new, below, above);
+            importance_round(r, zs, sdfs, ta, ta, T, (float)(64 << i), lane, z_new, below, above);
             float s_new = 0.0f;
             if (i + 1 < rounds) {                       // uniform across the launch: all 128 threads take it
                 const float zq = __shfl_sync(0xffffffffu, z_new, lane & 15);     // lanes 16..31 mirror 0..15
@@ -262,50 +358,46 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             }
             int pos_old[4], pos_new;
             merge_positions(zs, T, z_new, lane, pos_old, pos_new);
+            float zo[4], so[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = lane + 32 * q;
-                if (k < T) { ta[pos_old[q]] = zs[k]; tb[pos_old[q]] = sdfs[k]; }
+                zo[q] = k < T ? zs[k] : 0.f;
+                so[q] = k < T ? sdfs[k] : 0.f;
             }
-            if (lane < 16) { ta[pos_new] = z_new; tb[pos_new] = s_new; }
+            __syncwarp();                               // every lane holds its elements: safe to scatter in place
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (lane + 32 * q < T) { zs[pos_old[q]] = zo[q]; sdfs[pos_old[q]] = so[q]; }
+            if (lane < 16) { zs[pos_new] = z_new; sdfs[pos_new] = s_new; }
             __syncwarp();
-            float* t0 = zs; zs = ta; ta = t0;
-            float* t1 = sdfs; sdfs = tb; tb = t1;
             T += 16;
         }
 
-        // ---- render core (:186-299) ----
-        // Section samples are processed in halves of 64.  For each half, first the 6 x 64 finite-
-        // difference points (:687-704) are evaluated with lanes packed as (sample, direction): the
-        // six +-eps neighbours of a sample sit within 0.003 of each other, so on every level coarser
-        // than ~10 they fall in the same grid cell and the warp's gather collapses to a handful of
-        // cache lines (the L1 tag stage, one line per cycle, is what bounds this kernel).  Their SDF
-        // values are parked in three scratch rows; then the half's two 32-sample blocks are shaded
-        // in depth order (lane = sample), carrying the transmittance across blocks.
-        if (zs != reinterpret_cast<float*>(smem + SM_ROWS) + warp * 4 * kMaxT) {   // park the depths in row 0
-            float* row0 = reinterpret_cast<float*>(smem + SM_ROWS) + warp * 4 * kMaxT;
-            for (int k = lane; k < Ttot; k += 32) row0[k] = zs[k];
-            __syncwarp();
-            zs = row0;
-        }
-        float* fd = zs + kMaxT;            // rows 1..3: 384 floats = 64 samples x 6 directions
-        sdfs = zs + kMaxT; ta = zs + 2 * kMaxT; tb = zs + 3 * kMaxT;
+        // ---- render core (:186-299), 32 section samples at a time in depth order ----
+        // Per block: the 6 x 32 finite-difference points (:687-704) first, lanes packed as (sample, direction):
+        // the six +-eps neighbours of a sample sit within 0.003 of each other, so on every level coarser than
+        // ~10 they share a grid cell and the warp's gather collapses to a few cache lines.  Their SDF values
+        // are parked in the scratch rows (sdfs/ta are free now); then the block is shaded (lane = sample) and
+        // the transmittance is carried across blocks with a shuffle scan.
         float carry = 1.0f;
         float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_nx = 0.f, acc_ny = 0.f, acc_nz = 0.f;
         float acc_w = 0.f, acc_d = 0.f, eik_num = 0.f, eik_den = 0.f;
-        for (int h0 = 0; h0 < Ttot; h0 += 64) {
-            const int nS = min(64, Ttot - h0);
+        for (int k0 = 0; k0 < Ttot; k0 += 32) {
+            const int nS = min(32, Ttot - k0);
             for (int q0 = 0; q0 < 6 * nS; q0 += 32) {
                 const int q = min(q0 + lane, 6 * nS - 1);
                 const int sI = q / 6, dir = q - 6 * sI;
-                const int k = h0 + sI;
-                const float zk = zs[k];
-                const float zmid = k < Ttot - 1 ? zk + 0.5f * (zs[k + 1] - zk) : zk;
+                const int k = k0 + sI;
                 float px, py, pz;
                 if (p.a.pts_in) {
                     const float* q3 = p.a.pts_in + 3 * ((size_t)ray * Ttot + k);
                     px = q3[0]; py = q3[1]; pz = q3[2];
-                } else ray_point(r, zmid, px, py, pz);
+                } else {
+                    const float zk = zs[k];
+                    const float zmid = k < Ttot - 1 ? zk + 0.5f * (zs[k + 1] - zk) : zk;
+                    ray_point(r, zmid, px, py, pz);
+                }
                 px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
                 const float e = (dir & 1) ? -eps : eps;
                 const int ax = dir >> 1;
@@ -317,40 +409,44 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 if (q0 + lane < 6 * nS) fd[q] = o[0];
             }
             __syncwarp();
-            for (int k0 = h0; k0 < h0 + nS; k0 += 32) {
+
             const bool live = k0 + lane < Ttot;
             const int k = min(k0 + lane, Ttot - 1);
             const float zk = zs[k];
             const float delta = k < Ttot - 1 ? zs[k + 1] - zk : sample_dist;
-            const float zmid = k < Ttot - 1 ? zk + 0.5f * delta : zk;
             float px, py, pz;
             if (p.a.pts_in) {
                 const float* q3 = p.a.pts_in + 3 * ((size_t)ray * Ttot + k);
                 px = q3[0]; py = q3[1]; pz = q3[2];
-            } else ray_point(r, zmid, px, py, pz);
-            px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
-            float o16[16];
-            group_sdf_eval<true>(g, table, lv, sw, bound, px, py, pz, o16);
-            float gr[3];
-            {
-                const float* f6 = fd + 6 * (k - h0);
-                gr[0] = 0.5f * (f6[0] - f6[1]) / eps;
-                gr[1] = 0.5f * (f6[2] - f6[3]) / eps;
-                gr[2] = 0.5f * (f6[4] - f6[5]) / eps;
+            } else {
+                ray_point(r, k < Ttot - 1 ? zk + 0.5f * delta : zk, px, py, pz);
             }
-            const float gn = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
-            const float inv = 1e-5f + gn;
-            float nrm[3] = {gr[0] / inv, gr[1] / inv, gr[2] / inv};
-            float cin[kColInPad], col[3];
-            cin[0] = px; cin[1] = py; cin[2] = pz; cin[3] = nrm[0]; cin[4] = nrm[1]; cin[5] = nrm[2];
+            px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
+            float cin[24], sdf0, gn;
+            {
+                float o16[16];
+                group_sdf_eval<true>(g, table, lv, sw, bound, px, py, pz, o16);
+                sdf0 = o16[0];
 #pragma unroll
-            for (int q = 0; q < 15; ++q) cin[6 + q] = o16[1 + q];
+                for (int q = 0; q < 15; ++q) cin[6 + q] = o16[1 + q];
+            }
+            {
+                const float* f6 = fd + 6 * (k - k0);
+                const float gx = 0.5f * (f6[0] - f6[1]) / eps, gy = 0.5f * (f6[2] - f6[3]) / eps, gz = 0.5f * (f6[4] - f6[5]) / eps;
+                gn = sqrtf(gx * gx + gy * gy + gz * gz);
+                const float inv = 1e-5f + gn;
+                cin[3] = gx / inv; cin[4] = gy / inv; cin[5] = gz / inv;
+            }
+            cin[0] = px; cin[1] = py; cin[2] = pz;
             cin[21] = cin[22] = cin[23] = 0.f;
-            color_mlp(sw, cin, col);
-            const float cosv = r.dx * nrm[0] + r.dy * nrm[1] + r.dz * nrm[2];
+            __syncwarp();                                // fd[] consumed before the next block overwrites it
+            float col[3];
+            group_color_eval(g, sw, cin, col);
+            const float nx = cin[3], ny = cin[4], nz = cin[5];
+            const float cosv = r.dx * nx + r.dy * ny + r.dz * nz;
             const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);
             const float hs = it * delta * 0.5f;
-            const float c0 = sigmoidf((o16[0] - hs) * inv_s), c1 = sigmoidf((o16[0] + hs) * inv_s);
+            const float c0 = sigmoidf((sdf0 - hs) * inv_s), c1 = sigmoidf((sdf0 + hs) * inv_s);
             float alpha = clampf((c0 - c1 + 1e-5f) / (c0 + 1e-5f), 0.0f, 1.0f);
             if (p.a.alpha_mask) alpha = alpha * p.a.alpha_mask[(size_t)ray * Ttot + k];
             if (!live) alpha = 0.0f;
@@ -363,7 +459,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             const float w = alpha * tr;
             if (live) {
                 acc_r += w * col[0]; acc_g += w * col[1]; acc_b += w * col[2];
-                acc_nx += w * nrm[0]; acc_ny += w * nrm[1]; acc_nz += w * nrm[2];
+                acc_nx += w * nx; acc_ny += w * ny; acc_nz += w * nz;
                 acc_w += w;
                 acc_d += w * clampf((zk - near) / span, 0.0f, 1.0f);
                 if (ray_ok) {
@@ -374,9 +470,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                     if (p.a.pts_color) { p.a.pts_color[3 * s] = col[0]; p.a.pts_color[3 * s + 1] = col[1]; p.a.pts_color[3 * s + 2] = col[2]; }
                 }
             }
-            }   // 32-sample block
-            __syncwarp();
-        }       // 64-sample half
+        }
         acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
         acc_nx = warp_sum(acc_nx); acc_ny = warp_sum(acc_ny); acc_nz = warp_sum(acc_nz);
         acc_w = warp_sum(acc_w); acc_d = warp_sum(acc_d);
@@ -403,31 +497,24 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     if (warp == 0) tc05::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// Unit-test kernel for the tensor-core layer alone: feats [128,32] (fp32) x W0[:,3:35]^T -> acc [128,64].
+// Unit-test kernel for the tensor-core layer alone: feats [128,32] (fp32) x W0[:,3:35]^T -> acc [128,64] (fp16x3).
 __global__ void __launch_bounds__(128, 1) debug_tc_layer_kernel(const float* __restrict__ feats, const float* __restrict__ blob,
                                                                 float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* a_hi = reinterpret_cast<float*>(smem);
-    float* a_lo = a_hi + 128 * kFeat;
-    float* b_hi = a_lo + 128 * kFeat;
-    float* b_lo = b_hi + 64 * kFeat;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + 64 * kFeat);
+    unsigned char* a = smem;                      // 16 KB
+    unsigned char* bhi = smem + 16384;            // 4 KB
+    unsigned char* blo = bhi + 4096;              // 4 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(blo + 4096);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = threadIdx.x;
-    for (int i = threadIdx.x; i < 64 * kFeat; i += blockDim.x) {
-        const int n = i / kFeat, k = i % kFeat;
-        float hi, lo;
-        tc05::split_tf32(blob[OFF_W0 + n * kSdfInPad + 3 + k], hi, lo);
-        b_hi[(k >> 2) * 256 + n * 4 + (k & 3)] = hi;
-        b_lo[(k >> 2) * 256 + n * 4 + (k & 3)] = lo;
-    }
-    for (int c = 0; c < 8; ++c) {
-        float4 hi, lo;
-        const float* f = feats + row * kFeat + 4 * c;
-        tc05::split_tf32(f[0], hi.x, lo.x); tc05::split_tf32(f[1], hi.y, lo.y);
-        tc05::split_tf32(f[2], hi.z, lo.z); tc05::split_tf32(f[3], hi.w, lo.w);
-        *reinterpret_cast<float4*>(a_hi + c * 512 + row * 4) = hi;
-        *reinterpret_cast<float4*>(a_lo + c * 512 + row * 4) = lo;
+    const int warp = threadIdx.x >> 5, row = threadIdx.x;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) stage_b_tile(bhi, blo, i >> 5, i & 31, blob[OFF_W0 + (i >> 5) * kSdfInPad + 3 + (i & 31)]);
+    for (int c = 0; c < 4; ++c) {
+        uint4 hi, lo;
+        const float* f = feats + row * 32 + 8 * c;
+        tc05::split_f16x2(f[0], f[1], hi.x, lo.x); tc05::split_f16x2(f[2], f[3], hi.y, lo.y);
+        tc05::split_f16x2(f[4], f[5], hi.z, lo.z); tc05::split_f16x2(f[6], f[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(a + c * 2048 + row * 16) = hi;
+        *reinterpret_cast<uint4*>(a + 8192 + c * 2048 + row * 16) = lo;
     }
     if (threadIdx.x == 0) { tc05::mbar_init(bar, 1); tc05::fence_mbar_init(); }
     if (warp == 0) tc05::tmem_alloc<64>(slot);
@@ -437,29 +524,19 @@ __global__ void __launch_bounds__(128, 1) debug_tc_layer_kernel(const float* __r
     tc05::fence_after_sync();
     const uint32_t tmem = *slot;
     if (threadIdx.x == 0) {
-        constexpr uint32_t idesc = tc05::idesc_tf32(128, 64);
-        for (uint32_t s = 0; s < 4; ++s) {
-            const uint64_t ah = tc05::smem_desc(tc05::smem_u32(a_hi) + s * 4096u, 2048u, 128u);
-            const uint64_t al = tc05::smem_desc(tc05::smem_u32(a_lo) + s * 4096u, 2048u, 128u);
-            const uint64_t bh = tc05::smem_desc(tc05::smem_u32(b_hi) + s * 2048u, 1024u, 128u);
-            const uint64_t bl = tc05::smem_desc(tc05::smem_u32(b_lo) + s * 2048u, 1024u, 128u);
-            tc05::mma_tf32(tmem, ah, bh, idesc, s > 0 ? 1u : 0u);
-            tc05::mma_tf32(tmem, al, bh, idesc, 1u);
-            tc05::mma_tf32(tmem, ah, bl, idesc, 1u);
-        }
+        issue_k32_x3(tmem, tc05::smem_u32(a), tc05::smem_u32(bhi), tc05::smem_u32(blo));
         tc05::mma_commit(bar);
     }
     tc05::mbar_wait(bar, 0);
     tc05::fence_after_sync();
-    for (int half = 0; half < 2; ++half) {
-        float acc[32];
-        tc05::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, acc);
-        for (int j = 0; j < 32; ++j) out[row * 64 + half * 32 + j] = acc[j];
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float acc[16];
+        tc05::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + qtr * 16, acc);
+        for (int j = 0; j < 16; ++j) out[row * 64 + qtr * 16 + j] = acc[j];
     }
     tc05::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc05::tmem_dealloc<64>(tmem);
-    (void)lane;
 }
 
 }  // namespace
@@ -484,9 +561,7 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
 
 extern "C" int ac_nsr_debug_tc_layer(const float* feats, const float* blob, float* out, void* stream) {
     if (!feats || !blob || !out) return AC_E_INVALID_ARG;
-    const size_t smem = (size_t)(2 * 128 * kFeat + 2 * 64 * kFeat) * 4 + 32;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(debug_tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const size_t smem = 16384 + 8192 + 32;
     debug_tc_layer_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(feats, blob, out);
     return acb::launched();
 }
