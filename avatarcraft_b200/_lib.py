@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 AC_OK, AC_E_INVALID_ARG, AC_E_UNSUPPORTED, AC_E_CUDA, AC_E_WORKSPACE = 0, -1, -2, -3, -4
-MLP_BLOB_FLOATS = 9296
+MLP_BLOB_FLOATS = 10848
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

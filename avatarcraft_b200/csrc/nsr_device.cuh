@@ -23,8 +23,12 @@ constexpr int OFF_B1 = OFF_W1T + 64 * 16;    // [16]
 constexpr int OFF_C0 = OFF_B1 + 16;          // [64][24]  colour layer 0
 constexpr int OFF_C1 = OFF_C0 + 64 * 24;     // [64][64]  colour layer 1
 constexpr int OFF_C2T = OFF_C1 + 64 * 64;    // [64][4]   colour layer 2, TRANSPOSED (col 3 = 0)
-constexpr int BLOB_FLOATS = OFF_C2T + 64 * 4;
-static_assert(BLOB_FLOATS == 9296, "blob size is part of the C ABI");
+// Epilogue block, laid out exactly as the render kernel's __constant__ bank (copied with one D2D memcpy):
+constexpr int OFF_EPI = OFF_C2T + 64 * 4;    // XB[64][4] = (wx, wy, wz, b0) | W1T[64][16] | B1[16] | C2T[64][4]
+constexpr int EPI_XB = 0, EPI_W1T = EPI_XB + 64 * 4, EPI_B1 = EPI_W1T + 64 * 16, EPI_C2T = EPI_B1 + 16;
+constexpr int EPI_FLOATS = EPI_C2T + 64 * 4;  // 1552
+constexpr int BLOB_FLOATS = OFF_EPI + EPI_FLOATS;
+static_assert(BLOB_FLOATS == 10848, "blob size is part of the C ABI");
 
 struct LevelMeta {
     uint32_t offset;   // first table entry of the level
@@ -82,6 +86,38 @@ __device__ __forceinline__ float2 grid_level_3d(const float2* __restrict__ table
     float2 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float w = (((k & 1) ? px : qx) * ((k & 2) ? py : qy)) * ((k & 4) ? pz : qz);
+        r.x = fmaf(w, v[k].x, r.x);
+        r.y = fmaf(w, v[k].y, r.y);
+    }
+    return r;
+}
+
+// Same arithmetic as grid_level_3d with ONE code path for dense and hashed levels (both slot formulas are
+// a handful of integer ops; selecting between them is cheaper than carrying two bodies per level through
+// the instruction cache of a 32-warp persistent kernel).  Results are bit-identical to grid_level_3d.
+__device__ __forceinline__ float2 grid_level_3d_u(const float2* __restrict__ table, const LevelMeta m, float x, float y, float z) {
+    float px = fmaf(x, m.scale, 0.5f), py = fmaf(y, m.scale, 0.5f), pz = fmaf(z, m.scale, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz;
+    px -= fx; py -= fy; pz -= fz;
+    const float qx = 1.0f - px, qy = 1.0f - py, qz = 1.0f - pz;
+    const bool hashed = m.hashed != 0u;
+    const uint32_t my = hashed ? 2654435761u : m.res1, mz = hashed ? 805459861u : m.res1 * m.res1;
+    const uint32_t y0 = iy * my, y1 = y0 + my, z0 = iz * mz, z1 = z0 + mz;
+    const float2* __restrict__ t = table + m.offset;
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t cx = ix + (k & 1), cy = (k & 2) ? y1 : y0, cz = (k & 4) ? z1 : z0;
+        uint32_t slot = hashed ? (cx ^ cy ^ cz) : (cx + cy + cz);
+        if (m.hashed == 1u) slot &= m.size - 1u;
+        else if (m.hashed == 2u) slot %= m.size;
+        v[k] = __ldg(t + slot);
+    }
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {

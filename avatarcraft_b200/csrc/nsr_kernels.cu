@@ -397,6 +397,17 @@ __global__ void __launch_bounds__(256) pack_mlp_kernel(const PackArgs a) {
         a.blob[idx] = w;
     }
     if (L.b && lane == 0) a.blob[L.b_off + row] = L.b[row];
+    // mirror the pieces the render kernel's epilogues read into the contiguous OFF_EPI block
+    float* epi = a.blob + OFF_EPI;
+    if (li == 0) {                                   // sdf layer 0: raw-xyz columns + bias
+        if (lane < 3) epi[EPI_XB + 4 * row + lane] = L.v[row * L.cols + lane] * sc;
+        if (lane == 3) epi[EPI_XB + 4 * row + 3] = L.b[row];
+    } else if (li == 1) {                            // sdf layer 1, transposed, + bias
+        for (int c = lane; c < L.cols; c += 32) epi[EPI_W1T + c * 16 + row] = L.v[row * L.cols + c] * sc;
+        if (lane == 0) epi[EPI_B1 + row] = L.b[row];
+    } else if (li == 4) {                            // colour head, transposed
+        for (int c = lane; c < L.cols; c += 32) epi[EPI_C2T + c * 4 + row] = L.v[row * L.cols + c] * sc;
+    }
 }
 
 __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,

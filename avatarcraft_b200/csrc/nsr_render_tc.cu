@@ -38,16 +38,15 @@ constexpr int kWarpsTC = 4 * kGroups;           // 32 warps, 1024 threads
 constexpr int kMaxT = 128;
 constexpr uint32_t kTmemCols = 64 * kGroups;    // 512: one 128x64 fp32 accumulator per group
 
-// fp32 essentials kept for the epilogues (floats)
-constexpr int W_XB = 0;                         // [64][4]  (wx, wy, wz, b0) of SDF layer 0
-constexpr int W_W1T = W_XB + 64 * 4;            // [64][16] SDF layer 1, transposed
-constexpr int W_B1 = W_W1T + 64 * 16;           // [16]
-constexpr int W_C2T = W_B1 + 16;                // [64][4]  colour head, transposed (col 3 = 0)
-constexpr int W_FLOATS = W_C2T + 64 * 4;        // 1552
+// fp32 weights of the register epilogues live in the constant bank: every lane reads the same element, the
+// index is a compile-time constant after unrolling, so they fold into FFMA operands (c[bank][offset]) and cost
+// neither a load instruction nor MIO-queue bandwidth.  Refreshed from the blob's OFF_EPI block by a 6 KB D2D
+// copy on the launch stream before every render launch.
+__constant__ float c_w[EPI_FLOATS];
+constexpr int W_XB = EPI_XB, W_W1T = EPI_W1T, W_B1 = EPI_B1, W_C2T = EPI_C2T;
 
 // dynamic shared memory map (bytes)
-constexpr size_t SM_W32 = 0;
-constexpr size_t SM_LEVELS = SM_W32 + W_FLOATS * 4;
+constexpr size_t SM_LEVELS = 0;
 constexpr size_t SM_B = (SM_LEVELS + kLevels * sizeof(LevelMeta) + 127) / 128 * 128;
 constexpr uint32_t B_W0_HI = 0, B_W0_LO = 4096, B_C0_HI = 8192, B_C0_LO = 12288, B_C1_HI = 16384, B_C1_LO = 24576, B_BYTES = 32768;
 constexpr size_t SM_A = SM_B + B_BYTES;                                   // per group 16 KB: hi [4 chunks] | lo [4 chunks]
@@ -110,68 +109,77 @@ __device__ __forceinline__ void issue_k32_x3(uint32_t tmem_d, uint32_t a_s, uint
     }
 }
 
-// Hash-encode (features only) -> A tile -> tcgen05.mma -> epilogue.  Must be called by all 128 threads of the
-// group, the same number of times.
-template <bool FULL>
-__device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
-                                               const float* __restrict__ sw, float bound, float x, float y, float z,
-                                               float (&out)[FULL ? 16 : 1]) {
-    {
-        const float two_b = 2.0f * bound;
-        const float u = (x + bound) / two_b, v = (y + bound) / two_b, w = (z + bound) / two_b;
-        const bool oob = (u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {               // 4 levels = 8 features = one 16-byte fp16 chunk of the row
-            uint4 hi, lo;
-            float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
-            if (!oob) {
-                f0 = grid_level_3d(table, lv[4 * c + 0], u, v, w);
-                f1 = grid_level_3d(table, lv[4 * c + 1], u, v, w);
-                f2 = grid_level_3d(table, lv[4 * c + 2], u, v, w);
-                f3 = grid_level_3d(table, lv[4 * c + 3], u, v, w);
-            }
-            tc05::split_f16x2(f0.x, f0.y, hi.x, lo.x);
-            tc05::split_f16x2(f1.x, f1.y, hi.y, lo.y);
-            tc05::split_f16x2(f2.x, f2.y, hi.z, lo.z);
-            tc05::split_f16x2(f3.x, f3.y, hi.w, lo.w);
-            *reinterpret_cast<uint4*>(g.a + c * 2048 + g.row * 16) = hi;
-            *reinterpret_cast<uint4*>(g.a + 8192 + c * 2048 + g.row * 16) = lo;
+// Hash-encode one point (features only) into this thread's A-tile row.  ONE copy of this code serves every
+// call site (__noinline__): with 32 warps in eight independent phases the instruction cache, not the
+// issue slots, was the first thing to saturate when it was inlined four times.
+__device__ __noinline__ void encode_to_tile(unsigned char* arow, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
+                                            float bound, float x, float y, float z) {
+    const float two_b = 2.0f * bound;
+    const float u = (x + bound) / two_b, v = (y + bound) / two_b, w = (z + bound) / two_b;
+    const bool oob = (u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {               // 4 levels = 8 features = one 16-byte fp16 chunk of the row
+        uint4 hi, lo;
+        float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
+        if (!oob) {
+            f0 = grid_level_3d_u(table, lv[4 * c + 0], u, v, w);
+            f1 = grid_level_3d_u(table, lv[4 * c + 1], u, v, w);
+            f2 = grid_level_3d_u(table, lv[4 * c + 2], u, v, w);
+            f3 = grid_level_3d_u(table, lv[4 * c + 3], u, v, w);
         }
+        tc05::split_f16x2(f0.x, f0.y, hi.x, lo.x);
+        tc05::split_f16x2(f1.x, f1.y, hi.y, lo.y);
+        tc05::split_f16x2(f2.x, f2.y, hi.z, lo.z);
+        tc05::split_f16x2(f3.x, f3.y, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(arow + c * 2048) = hi;
+        *reinterpret_cast<uint4*>(arow + 8192 + c * 2048) = lo;
     }
-    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_W0_HI, g.b_s + B_W0_LO); });
+}
 
+// Epilogue of the SDF network for this thread's accumulator row: + raw-xyz columns + bias (exact fp32),
+// softplus, second layer 64 -> {1, 16}.
+template <bool FULL>
+__device__ __forceinline__ void sdf_tail(uint32_t tmem_row, float x, float y, float z, float (&out)[FULL ? 16 : 1]) {
 #pragma unroll
-    for (int o = 0; o < (FULL ? 16 : 1); ++o) out[o] = sw[W_B1 + o];
+    for (int o = 0; o < (FULL ? 16 : 1); ++o) out[o] = c_w[W_B1 + o];
 #pragma unroll
     for (int qtr = 0; qtr < 4; ++qtr) {
         float acc[16];
-        tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+        tc05::tmem_ld16(tmem_row + qtr * 16, acc);
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
             const int j = qtr * 16 + jj;
-            const float4 xb = *reinterpret_cast<const float4*>(sw + W_XB + 4 * j);
-            const float lin = fmaf(xb.x, x, fmaf(xb.y, y, fmaf(xb.z, z, xb.w)));
+            const float lin = fmaf(c_w[W_XB + 4 * j], x, fmaf(c_w[W_XB + 4 * j + 1], y, fmaf(c_w[W_XB + 4 * j + 2], z, c_w[W_XB + 4 * j + 3])));
             const float h = softplus100_mufu(acc[jj] + lin);
             if (FULL) {
-                const float4* __restrict__ w1 = reinterpret_cast<const float4*>(sw + W_W1T + j * 16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 w4 = w1[q];
-                    out[4 * q + 0] = fmaf(w4.x, h, out[4 * q + 0]);
-                    out[4 * q + 1] = fmaf(w4.y, h, out[4 * q + 1]);
-                    out[4 * q + 2] = fmaf(w4.z, h, out[4 * q + 2]);
-                    out[4 * q + 3] = fmaf(w4.w, h, out[4 * q + 3]);
-                }
+                for (int o = 0; o < 16; ++o) out[o] = fmaf(c_w[W_W1T + j * 16 + o], h, out[o]);
             } else {
-                out[0] = fmaf(sw[W_W1T + j * 16], h, out[0]);
+                out[0] = fmaf(c_w[W_W1T + j * 16], h, out[0]);
             }
         }
     }
 }
+__device__ __noinline__ float sdf_tail_scalar(uint32_t tmem_row, float x, float y, float z) {
+    float o[1];
+    sdf_tail<false>(tmem_row, x, y, z, o);
+    return o[0];
+}
+
+// Encode -> A tile -> tcgen05.mma -> epilogue.  Must be called by all 128 threads of the group, the same
+// number of times.
+template <bool FULL>
+__device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
+                                               float bound, float x, float y, float z, float (&out)[FULL ? 16 : 1]) {
+    encode_to_tile(g.a + g.row * 16, table, lv, bound, x, y, z);
+    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_W0_HI, g.b_s + B_W0_LO); });
+    if constexpr (FULL) sdf_tail<true>(g.tmem, x, y, z, out);
+    else out[0] = sdf_tail_scalar(g.tmem, x, y, z);
+}
 
 // Colour MLP 21 -> 64 -> 64 -> 3 (models/instant_nsr.py:644-663) for the group's 128 samples.
 // cin = (x, y, z, nx, ny, nz, 15 geometry features); all 128 threads of the group call it together.
-__device__ __forceinline__ void group_color_eval(Group& g, const float* __restrict__ sw, const float (&cin)[24], float (&rgb)[3]) {
+__device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24], float (&rgb)[3]) {
     // layer 0: K = 32 (21 inputs + zero pad), fp16x3
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -222,8 +230,8 @@ __device__ __forceinline__ void group_color_eval(Group& g, const float* __restri
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
             const float h2 = fmaxf(acc[jj], 0.f);
-            const float4 c2 = *reinterpret_cast<const float4*>(sw + W_C2T + 4 * (qtr * 16 + jj));
-            o0 = fmaf(c2.x, h2, o0); o1 = fmaf(c2.y, h2, o1); o2 = fmaf(c2.z, h2, o2);
+            const int j = qtr * 16 + jj;
+            o0 = fmaf(c_w[W_C2T + 4 * j], h2, o0); o1 = fmaf(c_w[W_C2T + 4 * j + 1], h2, o1); o2 = fmaf(c_w[W_C2T + 4 * j + 2], h2, o2);
         }
     }
     rgb[0] = sigmoidf(o0); rgb[1] = sigmoidf(o1); rgb[2] = sigmoidf(o2);
@@ -240,7 +248,6 @@ __device__ __forceinline__ void stage_b_tile(unsigned char* bhi, unsigned char* 
 
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const RenderParamsTC p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* sw = reinterpret_cast<float*>(smem + SM_W32);
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
     unsigned char* bt = smem + SM_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
@@ -252,13 +259,6 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     // ---- one-time staging: fp32 epilogue weights, level table, fp16 weight tiles, barriers, TMEM ----
     {
         const float* blob = p.blob;
-        for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
-            const int j = i >> 2, q = i & 3;
-            sw[W_XB + i] = q < 3 ? __ldg(blob + OFF_W0 + j * kSdfInPad + q) : __ldg(blob + OFF_B0 + j);
-            sw[W_C2T + i] = __ldg(blob + OFF_C2T + i);
-        }
-        for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[W_W1T + i] = __ldg(blob + OFF_W1T + i);
-        if (threadIdx.x < 16) sw[W_B1 + threadIdx.x] = __ldg(blob + OFF_B1 + threadIdx.x);
         if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(p.offsets, threadIdx.x, p.S, p.H, 3);
         for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
             const int n = i >> 5, k = i & 31;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 float x, y, zz;
                 ray_point(r, z, x, y, zz);
                 float o[1];
-                group_sdf_eval<false>(g, table, lv, sw, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
+                group_sdf_eval<false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
                                       clampf(zz, -bound, bound), o);
                 sdfs[k] = o[0];
             }
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 float x, y, zz;
                 ray_point(r, zq, x, y, zz);
                 float o[1];
-                group_sdf_eval<false>(g, table, lv, sw, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
+                group_sdf_eval<false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
                                       clampf(zz, -bound, bound), o);
                 s_new = o[0];
             }
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 const float qy = ax == 1 ? clampf(py + e, -bound, bound) : py;
                 const float qz = ax == 2 ? clampf(pz + e, -bound, bound) : pz;
                 float o[1];
-                group_sdf_eval<false>(g, table, lv, sw, bound, qx, qy, qz, o);
+                group_sdf_eval<false>(g, table, lv, bound, qx, qy, qz, o);
                 if (q0 + lane < 6 * nS) fd[q] = o[0];
             }
             __syncwarp();
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             float cin[24], sdf0, gn;
             {
                 float o16[16];
-                group_sdf_eval<true>(g, table, lv, sw, bound, px, py, pz, o16);
+                group_sdf_eval<true>(g, table, lv, bound, px, py, pz, o16);
                 sdf0 = o16[0];
 #pragma unroll
                 for (int q = 0; q < 15; ++q) cin[6 + q] = o16[1 + q];
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             cin[21] = cin[22] = cin[23] = 0.f;
             __syncwarp();                                // fd[] consumed before the next block overwrites it
             float col[3];
-            group_color_eval(g, sw, cin, col);
+            group_color_eval(g, cin, col);
             const float nx = cin[3], ny = cin[4], nz = cin[5];
             const float cosv = r.dx * nx + r.dy * ny + r.dz * nz;
             const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);
@@ -551,6 +551,8 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
     p.eik_partial = reinterpret_cast<float*>(a->workspace);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(nsr_render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); attr = true; }
+    if (cudaMemcpyToSymbolAsync(c_w, m->mlp_blob + OFF_EPI, EPI_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return acb::cuda_fail();
     const uint32_t n_quads = (a->n_rays + 3) / 4;
     const uint32_t want = (n_quads + kGroups - 1) / kGroups;
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();

@@ -70,7 +70,7 @@ int ac_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, ui
  * SDF MLP 35->64->16 (softplus beta=100) + colour MLP 21->64->64->3 (relu, sigmoid)
  * + the single NeuS variance.
  * ------------------------------------------------------------------------------------ */
-#define AC_NSR_MLP_BLOB_FLOATS 9296
+#define AC_NSR_MLP_BLOB_FLOATS 10848
 
 /* Folds weight-norm (w = g*v/||v||_row, models/instant_nsr.py:555-556,585-586) and packs
  * the five layers into the blob the render kernels stage in shared memory.  Pointers are
