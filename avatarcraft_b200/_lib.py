@@ -11,7 +11,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libavatarcraft_b200.so")
+LIB_PATH = os.environ.get("AC_LIB_PATH") or os.path.join(_PKG, "libavatarcraft_b200.so")   # AC_LIB_PATH: tuning variants
 SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
@@ -20,8 +20,18 @@ AC_OK, AC_E_INVALID_ARG, AC_E_UNSUPPORTED, AC_E_CUDA, AC_E_WORKSPACE = 0, -1, -2
 MLP_BLOB_FLOATS = 10848
 
 
+def build_variant(path: str, defines) -> str:
+    """Compile a tuning variant of the library (extra -D switches) to `path`."""
+    srcs = [os.path.join(_PKG, "csrc", s) for s in SOURCES]
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", path] + srcs)
+    return path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if os.environ.get("AC_LIB_PATH"):
+        return LIB_PATH
     srcs = [os.path.join(_PKG, "csrc", s) for s in SOURCES]
     deps = srcs + [os.path.join(_PKG, "csrc", h) for h in os.listdir(os.path.join(_PKG, "csrc")) if h.endswith(".cuh")]
     deps.append(os.path.join(_ROOT, "include", "avatarcraft_b200.h"))

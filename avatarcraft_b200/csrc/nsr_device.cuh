@@ -84,8 +84,17 @@ __device__ __forceinline__ float2 grid_level_3d(const float2* __restrict__ table
         s[6] = wrap_slot(hx0 ^ hy1 ^ hz1, m); s[7] = wrap_slot(hx1 ^ hy1 ^ hz1, m);
     }
     float2 v[8];
+#if defined(AC_FINE_NO_ALLOCATE) && AC_FINE_NO_ALLOCATE
+    if (m.hashed != 0u && m.scale > 200.0f) {      // fine hashed levels: no reuse inside an SM, keep them out of L1
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+        for (int k = 0; k < 8; ++k)
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v[k].x), "=f"(v[k].y) : "l"(t + s[k]));
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+    }
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {

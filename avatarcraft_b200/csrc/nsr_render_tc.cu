@@ -1,6 +1,6 @@
 // nsr_render_tc.cu -- the fused Instant-NSR render core, tensor-core edition (sm_100a).
 //
-// Persistent kernel: one CTA of 32 warps (1024 threads, <= 64 registers) per SM, all 512 TMEM columns.
+// Persistent kernel: one CTA of 28 warps (7 groups x 4 warps, <= 73 registers) per SM, 512 TMEM columns.
 // A warp owns a ray from box intersection to composited pixel (nsr_device.cuh); four warps form a
 // GROUP whose 128 lanes are the 128 rows of one MMA tile.  Every dense layer that matters runs on the
 // 5th-generation tensor cores (tcgen05.mma, kind::f16, fp32 accumulate in TMEM):
@@ -17,9 +17,10 @@
 // SDF and feed the +-0.005 finite differences), softplus(beta=100) costs two MUFU ops, and the 64 -> {1,16}
 // second SDF layer and the 64 -> 3 colour head are short register dot products.
 //
-// fp16x3 instead of 3xTF32 halves the A-tile footprint (16 KB per group), which is what lets 8 groups =
-// 32 warps share one SM: the kernel is bound by gather latency (ncu: long_scoreboard), so resident warps
-// are the lever.  Groups are independent (own A tile, 64 TMEM columns, named barrier, mbarrier).
+// fp16x3 instead of 3xTF32 halves the A-tile footprint (16 KB per group), which is what lets 7-8 groups
+// share one SM: the kernel is bound by gather latency (ncu: long_scoreboard), so resident warps are a lever --
+// up to the point where the register budget forces spills (8 groups = 64 registers is slower than 7 = 73).
+// Groups are independent (own A tile, 64 TMEM columns, named barrier, mbarrier).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -31,12 +32,29 @@
 
 using namespace acb;
 
+// Tuning switches (scripts/bench_variants.sh builds and times the combinations on the GPU box).
+#ifndef AC_SPECIALIZED_LEVELS
+#define AC_SPECIALIZED_LEVELS 1     // 1: separate dense / hashed level bodies (fewer instructions, more code)
+#endif
+#ifndef AC_FULL_TAIL_LOOP
+#define AC_FULL_TAIL_LOOP 0         // 1: 16-output SDF tail as a rolled loop (4x less code; ~2 % slower at 6-7 groups)
+#endif
+
+#ifndef AC_ENCODE_UNROLL
+#define AC_ENCODE_UNROLL 1          // unroll factor of the 4-chunk encode loop
+#endif
+#ifndef AC_GROUPS
+#define AC_GROUPS 7                 // 4-warp groups per CTA.  Measured ms/frame (B200, 256x256, 64+64): 4: 16.0  5: 16.0  6: 15.0  7: 14.5  8: 18.5 (64 regs, spills)
+#endif
+#define AC_PRAGMA(x) _Pragma(#x)
+#define AC_UNROLL(n) AC_PRAGMA(unroll n)
+
 namespace {
 
-constexpr int kGroups = 8;                      // groups of 4 warps per CTA
+constexpr int kGroups = AC_GROUPS;                      // groups of 4 warps per CTA
 constexpr int kWarpsTC = 4 * kGroups;           // 32 warps, 1024 threads
 constexpr int kMaxT = 128;
-constexpr uint32_t kTmemCols = 64 * kGroups;    // 512: one 128x64 fp32 accumulator per group
+constexpr uint32_t kTmemCols = 512;             // one 128x64 fp32 accumulator per group (8 x 64 = all of TMEM)
 
 // fp32 weights of the register epilogues live in the constant bank: every lane reads the same element, the
 // index is a compile-time constant after unrolling, so they fold into FFMA operands (c[bank][offset]) and cost
@@ -117,15 +135,22 @@ __device__ __noinline__ void encode_to_tile(unsigned char* arow, const float2* _
     const float two_b = 2.0f * bound;
     const float u = (x + bound) / two_b, v = (y + bound) / two_b, w = (z + bound) / two_b;
     const bool oob = (u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f);
-#pragma unroll 1
+    AC_UNROLL(AC_ENCODE_UNROLL)
     for (int c = 0; c < 4; ++c) {               // 4 levels = 8 features = one 16-byte fp16 chunk of the row
         uint4 hi, lo;
         float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
         if (!oob) {
+#if AC_SPECIALIZED_LEVELS
+            f0 = grid_level_3d(table, lv[4 * c + 0], u, v, w);
+            f1 = grid_level_3d(table, lv[4 * c + 1], u, v, w);
+            f2 = grid_level_3d(table, lv[4 * c + 2], u, v, w);
+            f3 = grid_level_3d(table, lv[4 * c + 3], u, v, w);
+#else
             f0 = grid_level_3d_u(table, lv[4 * c + 0], u, v, w);
             f1 = grid_level_3d_u(table, lv[4 * c + 1], u, v, w);
             f2 = grid_level_3d_u(table, lv[4 * c + 2], u, v, w);
             f3 = grid_level_3d_u(table, lv[4 * c + 3], u, v, w);
+#endif
         }
         tc05::split_f16x2(f0.x, f0.y, hi.x, lo.x);
         tc05::split_f16x2(f1.x, f1.y, hi.y, lo.y);
@@ -173,8 +198,30 @@ __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restric
                                                float bound, float x, float y, float z, float (&out)[FULL ? 16 : 1]) {
     encode_to_tile(g.a + g.row * 16, table, lv, bound, x, y, z);
     group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_W0_HI, g.b_s + B_W0_LO); });
-    if constexpr (FULL) sdf_tail<true>(g.tmem, x, y, z, out);
-    else out[0] = sdf_tail_scalar(g.tmem, x, y, z);
+    if constexpr (FULL) {
+#if AC_FULL_TAIL_LOOP
+#pragma unroll
+        for (int o = 0; o < 16; ++o) out[o] = c_w[W_B1 + o];
+#pragma unroll 1
+        for (int qtr = 0; qtr < 4; ++qtr) {
+            float acc[16];
+            tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+            const float* __restrict__ xb = c_w + W_XB + 64 * qtr;
+            const float* __restrict__ w1 = c_w + W_W1T + 256 * qtr;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const float lin = fmaf(xb[4 * jj], x, fmaf(xb[4 * jj + 1], y, fmaf(xb[4 * jj + 2], z, xb[4 * jj + 3])));
+                const float h = softplus100_mufu(acc[jj] + lin);
+#pragma unroll
+                for (int o = 0; o < 16; ++o) out[o] = fmaf(w1[jj * 16 + o], h, out[o]);
+            }
+        }
+#else
+        sdf_tail<true>(g.tmem, x, y, z, out);
+#endif
+    } else {
+        out[0] = sdf_tail_scalar(g.tmem, x, y, z);
+    }
 }
 
 // Colour MLP 21 -> 64 -> 64 -> 3 (models/instant_nsr.py:644-663) for the group's 128 samples.
