@@ -65,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -201,13 +201,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                     # nvidia-smi takes ~0.5 s to start: begin before the warm-up
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.ac_launch_count()
     barrier()
     ms = timed(step_resident, args.steps)
@@ -241,7 +241,7 @@ def run_ours(args):
                        "upsample_steps": UPSAMPLE_STEPS, "sdf_evals_per_ray": 1008, "color_evals_per_ray": 128,
                        "checkpoint": "synthetic trained-like seed 43", "parallelism": f"ray-shard x{world} (one view per rank)",
                        "l2": "flushed before every timed step (256 MiB memset); per-step CUDA events summed"},
-            "roofline": {"bound": "hbm", "kernel": "nsr_render_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "nsr_render_tc_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                          "peak_source": pk["source"], "algorithmic_bytes_per_launch": algo_bytes,
                          "note": "algorithmic gather bytes (no reuse) per SURVEY.md 8(d); gathers are served from L1/L2, "
