@@ -160,3 +160,33 @@ def synthetic_body(pose_seed=46, amplitude=0.35):
     faces6 = np.concatenate([faces, faces], 1)
     return dict(rest_verts=verts.astype(np.float32), world_verts=world.astype(np.float32), faces=faces6,
                 Ts=Ts.astype(np.float32))
+
+
+def synthetic_smpl_model(seed=45):
+    """SMPL-shaped model dict (fields of SMPL_NEUTRAL.pkl used by models/smpl.py) on the synthetic body:
+    6890-vertex template, 10 smooth shape directions, a 24-joint regressor (mean of the ring nearest each
+    joint height), SMPL's kinematic tree, sparse skinning weights (4 non-zeros per vertex)."""
+    body = synthetic_body()
+    V = body["rest_verts"].astype(np.float64)
+    rng = np.random.default_rng(seed)
+    joints_y = np.linspace(0.8, -0.8, 24)
+    dj = np.abs(V[:, 1:2] - joints_y[None])
+    w = np.exp(-(dj / 0.08) ** 2)
+    w[np.arange(6890)[:, None], np.argsort(-w, 1)[:, 4:]] = 0.0
+    w /= w.sum(1, keepdims=True)
+    Jr = np.exp(-(dj.T / 0.03) ** 2)
+    Jr /= Jr.sum(1, keepdims=True)
+    dirs = np.stack([np.sin((k + 1) * V[:, 1:2] * 2.0 + rng.uniform(0, 6.28)) * V * 0.03 for k in range(10)], -1)   # [V,3,10]
+    return dict(v_template=V, shapedirs=dirs, J_regressor=Jr, weights=w, f=body["faces"][:, :3],
+                kintree_table=np.stack([np.array([2 ** 32 - 1] + [p for p in (0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21)]),
+                                        np.arange(24)]))
+
+
+def sinusoid_pose_sequence(n_frames=120, amplitude=0.5, seed=46):
+    """[F,72] smooth axis-angle sequence standing in for an AMASS-SFU clip (convert_amass.py:5-17 layout)."""
+    rng = np.random.default_rng(seed)
+    phase, freq = rng.uniform(0, 6.28, (24, 3)), rng.uniform(0.5, 2.0, (24, 3))
+    t = np.linspace(0, 2 * np.pi, n_frames)[:, None, None]
+    p = amplitude * 0.3 * np.sin(freq[None] * t + phase[None])
+    p[:, 0] *= 0.2
+    return p.reshape(n_frames, 72).astype(np.float32)

@@ -144,6 +144,24 @@ def main():
                         **{"g." + k: v.numpy() for k, v in gref.items() if k != "encoder.embeddings"})
     print(f"wrote grad_trained_jitter_64p64.npz  rays={n} loss={float(loss):.4f} nnz table rows={nz.numel()}")
 
+    # ---- SMPL linear-blend-skinning fixture: the reference's own models/smpl.py::lbs on the synthetic model ----
+    import models.smpl as ref_smpl
+    md = syn.synthetic_smpl_model()
+    t32 = lambda a: torch.as_tensor(np.asarray(a, np.float32))
+    poses = syn.sinusoid_pose_sequence(4)
+    pose, betas = torch.from_numpy(poses[2:3]), torch.zeros(1, 10)
+    betas[0, 1] = 0.7
+    parents = torch.as_tensor(np.asarray(md["kintree_table"][0]).astype(np.int64))
+    parents[0] = -1
+    posedirs = torch.zeros(207, 6890 * 3)                 # multiplied but unused by lbs (v_posed = v_shaped, smpl.py:420)
+    args = (betas, pose, t32(md["v_template"])[None], t32(md["shapedirs"]), posedirs, t32(md["J_regressor"]), parents, t32(md["weights"]))
+    T_ref, _, _ = ref_smpl.lbs(*args, return_T=True, concat_joints=True)
+    verts_ref, J_ref = ref_smpl.lbs(*args)
+    np.savez_compressed(os.path.join(GOLD, "smpl_lbs_synthetic.npz"), pose=poses[2:3], betas=betas.numpy(),
+                        T_rows=np.arange(0, 6914, 37), T=T_ref[0, ::37].numpy(), posed_rows=np.arange(0, 6890, 53),
+                        posed=verts_ref[0, ::53].numpy(), joints=J_ref[0].numpy())
+    print("wrote smpl_lbs_synthetic.npz")
+
     # hash-encoder fixture through the reference's own HashEncoder.forward wrapper
     sd = syn.synthetic_state_dict("trained", 43)
     net = ref_nsr.NeRFNetwork()

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Stylisation trainer -- the optimisation loop of the reference's stylize.py (Trainer.train :47-217) on
+avatarcraft_b200: per view, pass 1 renders the (sub-sampled) image without gradients, a guidance function turns it
+into a pixel gradient, pass 2 re-renders 4096-ray patches with gradients and back-propagates pixel gradient +
+eikonal + opacity-vs-frozen-copy, ONE gradient all-reduce (multi-GPU), Adam(lr 5e-3).
+
+The Stable-Diffusion SDS guidance (models/diffusion.py:92-149) is third-party code + weights that are not available
+offline; `--guidance` selects a stand-in with the same interface ([1,3,h,w] image -> d(loss)/d(image)):
+  target   pulls the render towards a fixed colour tint (deterministic, for smoke tests)
+  randn    unit Gaussian pixel gradient (the bench's stand-in)
+Launch with torchrun for multi-GPU: patches are sharded across ranks.
+
+    python stylize.py --synthetic --exp_name demo --n_views 4 --coarse_epochs 1 --fine_epochs 0
+"""
+import argparse
+import os
+
+import torch
+import torch.distributed as dist
+
+from avatarcraft_b200.models.instant_nsr import NeRFNetwork
+from avatarcraft_b200.utils import render_utils, synthetic
+from avatarcraft_b200.utils.camera_paths import default_360_path, rays_for_pose
+from avatarcraft_b200.utils.constant import CANONICAL_CAMERA_DIST_TRAIN, NSR_BOUND
+from avatarcraft_b200.utils.train_utils import stylize_patch_step
+
+
+def guidance(kind, rgb_chw, step):
+    if kind == "randn":
+        return torch.randn(rgb_chw.shape, device=rgb_chw.device, generator=torch.Generator(rgb_chw.device).manual_seed(step))
+    tint = torch.tensor([0.9, 0.6, 0.3], device=rgb_chw.device).view(1, 3, 1, 1)
+    return (rgb_chw - tint) / rgb_chw[0, 0].numel()                    # d/d(rgb) of 0.5 * mean squared error to the tint
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--weights_path", type=str, default=None)
+    ap.add_argument("--synthetic", action="store_true")
+    ap.add_argument("--exp_name", type=str, default="style")
+    ap.add_argument("--render_h", type=int, default=256)
+    ap.add_argument("--render_w", type=int, default=256)
+    ap.add_argument("--n_views", type=int, default=100)
+    ap.add_argument("--coarse_epochs", type=int, default=40)
+    ap.add_argument("--fine_epochs", type=int, default=20)
+    ap.add_argument("--subsample_scale", type=int, default=4)
+    ap.add_argument("--batch_size", type=int, default=4096)
+    ap.add_argument("--w_eikonal", type=float, default=0.01)
+    ap.add_argument("--use_opacity", type=int, default=1)
+    ap.add_argument("--guidance", type=str, default="target", choices=["target", "randn"])
+    ap.add_argument("--i_save", type=int, default=1000)
+    opt = ap.parse_args()
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sd = synthetic.synthetic_state_dict("trained", 43) if opt.synthetic else torch.load(opt.weights_path, map_location="cpu")
+    net_style, net_gt = NeRFNetwork(), NeRFNetwork()
+    net_style.load_state_dict(sd); net_gt.load_state_dict(sd)
+    net_style, net_gt = net_style.cuda().train(), net_gt.cuda().eval()        # net_style is never .eval()ed (stylize.py:336)
+    for p in net_gt.parameters():
+        p.requires_grad_(False)
+    optimizer = torch.optim.Adam(net_style.parameters(), lr=5e-3)             # stylize.py:355-363
+    out_dir = os.path.join("style", "canonical_360", opt.exp_name)
+    os.makedirs(out_dir, exist_ok=True)
+    H, W, step = opt.render_h, opt.render_w, 0
+    for epoch in range(opt.coarse_epochs + opt.fine_epochs):
+        stride = opt.subsample_scale if epoch < opt.coarse_epochs else min(1, opt.subsample_scale // 2) or 1
+        poses = default_360_path((0.0, 0.0, 0.0), CANONICAL_CAMERA_DIST_TRAIN, opt.n_views)
+        perm = torch.randperm(opt.n_views, generator=torch.Generator().manual_seed(epoch))      # same order on every rank
+        for vi in perm.tolist():
+            o, d = rays_for_pose(poses[vi], W, H, "cuda")
+            o, d = o.reshape(H, W, 3)[::stride, ::stride].reshape(-1, 3).contiguous(), d.reshape(H, W, 3)[::stride, ::stride].reshape(-1, 3).contiguous()
+            h, w = H // stride, W // stride
+            with torch.no_grad():                                                                # pass 1 (stylize.py:115)
+                rgb, _ = render_utils.render_instantnsr_naive(net_style, o, d, opt.batch_size, render_can=True, perturb=True)
+            g = guidance(opt.guidance, rgb.reshape(h, w, 3).permute(2, 0, 1)[None], step)        # [1,3,h,w]
+            pixel_grad = g[0].permute(1, 2, 0).reshape(-1, 3).contiguous()
+            stats = stylize_patch_step(net_style, net_gt, optimizer, o, d, pixel_grad, batch_size=opt.batch_size,
+                                       w_eikonal=opt.w_eikonal, use_opacity=bool(opt.use_opacity), rank=rank, world=world)
+            step += 1
+            if rank == 0 and step % 10 == 0:
+                print(f"epoch {epoch} step {step} eikonal {float(stats['eikonal'] or 0):.4f}")
+            if rank == 0 and step % opt.i_save == 0:
+                torch.save(net_style.state_dict(), os.path.join(out_dir, f"{opt.exp_name}_{step:06d}.pth.tar"))
+    if rank == 0:
+        torch.save(net_style.state_dict(), os.path.join(out_dir, f"{opt.exp_name}.pth.tar"))
+        print("saved", os.path.join(out_dir, f"{opt.exp_name}.pth.tar"))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

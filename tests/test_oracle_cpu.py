@@ -184,3 +184,40 @@ def test_warp_oracle_geometry():
     can, mask, *_ = wo.warp_samples_to_canonical((cen + 0.01 * nrm)[None], V, body["faces"], T, 0.05)
     np.testing.assert_allclose(can[0], 0.9 * (cen + 0.01 * nrm), atol=1e-12)       # inverse of diag(1/0.9): xyz * 0.9, w ignored
     assert mask.all()
+
+
+def test_smpl_lbs_matches_reference_fixture():
+    """avatarcraft_b200.models.smpl (host-side W3) == the reference's models/smpl.py::lbs on the synthetic
+    SMPL-shaped model (fixture from /root/reference): per-vertex + joint transforms, posed vertices, joints."""
+    from avatarcraft_b200.models.smpl import SMPL, calc_local_trans
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "smpl_lbs_synthetic.npz")))
+    m = SMPL(syn.synthetic_smpl_model())
+    _, T, _ = m.verts_transformations(g["pose"], g["betas"], concat_joints=True)
+    np.testing.assert_allclose(T[0, g["T_rows"]].numpy(), g["T"], atol=1e-6)
+    v, J = m.forward(g["pose"], g["betas"], return_joints=True)
+    np.testing.assert_allclose(v[0, g["posed_rows"]].numpy(), g["posed"], atol=1e-6)
+    np.testing.assert_allclose(J[0].numpy(), g["joints"], atol=1e-6)
+    wv, Ts, n = calc_local_trans(m, poses=syn.sinusoid_pose_sequence(3))
+    assert n == 3 and wv[0].shape == (6890, 3) and Ts[0].shape == (6914, 4, 4)
+    assert np.abs(Ts[1][:, 3, :3]).max() == 0 and np.allclose(Ts[1][:, 3, 3], 1 / 0.9)      # (0,0,0,1/0.9) rows (render_warp.py:200-204)
+    # the posed surface is the rest surface pushed through T_rest2pose: inverse warp of a posed vertex lands on the rest vertex * 0.9
+    rest, _ = m.forward(np.zeros((1, 72), np.float32) + _da_pose(), np.zeros((1, 10), np.float32), return_joints=True)
+    back = np.einsum("nij,nj->ni", np.linalg.inv(Ts[1][:6890]), np.concatenate([wv[1], np.ones((6890, 1))], 1))[:, :3]
+    np.testing.assert_allclose(back, 0.9 * rest[0].numpy(), atol=2e-5)
+
+
+def _da_pose():
+    da = np.zeros((24, 3), np.float32)
+    da[1], da[2] = [0, 0, 1.0], [0, 0, -1.0]
+    return da.reshape(1, 72)
+
+
+def test_gen_rays_pose_convention():
+    from avatarcraft_b200.utils.ray_gen import dataset_intrinsics, gen_rays_pose
+    K = dataset_intrinsics()
+    pose = np.eye(4, dtype=np.float32); pose[:3, 3] = [0.1, 0.2, 2.0]
+    o, v = gen_rays_pose(pose, K, 512, 512, resolution_level=2)
+    assert o.shape == (256, 256, 3) and v.shape == (256, 256, 3)
+    np.testing.assert_allclose(o[5, 7].numpy(), [0.1, 0.2, 2.0])
+    np.testing.assert_allclose(torch.linalg.norm(v, dim=-1).numpy(), 1.0, atol=1e-6)
+    assert float(v[128, 128, 2]) < -0.99 and float(v[0, 0, 0]) < 0 < float(v[0, 0, 1])      # looks down -z, +y is up, x grows right
