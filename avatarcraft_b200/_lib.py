@@ -72,6 +72,8 @@ _SIGNATURES = {
     "ac_hash_encode_backward": (_I, [_V, _V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
     "ac_sh_encode_forward": (_I, [_V, _V, _U32, _U32, _U32, _I, _V, _V]),
     "ac_sh_encode_backward": (_I, [_V, _V, _U32, _U32, _U32, _V, _V, _V]),
+    "ac_hash_encode_forward_pm": (_I, [_V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V]),
+    "ac_hash_encode_backward_pm": (_I, [_V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
     "ac_hash_level_scales": (_I, [_V, _U32, _F, _U32, _V]),
     "ac_nsr_pack_mlp": (_I, [_V] * 13 + [_V]),
     "ac_nsr_forward_sdf": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V]),

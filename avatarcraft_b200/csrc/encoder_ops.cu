@@ -37,7 +37,7 @@ template <uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256) hash_forward_kernel(const float* __restrict__ inputs, const float* __restrict__ table,
                                                            const int32_t* __restrict__ offsets, float* __restrict__ outputs,
                                                            uint32_t B, uint32_t L, float S, uint32_t H, bool want_jac,
-                                                           float* __restrict__ dy_dx, int32_t* __restrict__ corner_ids) {
+                                                           float* __restrict__ dy_dx, int32_t* __restrict__ corner_ids, bool point_major) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) hash_forward_kernel(const float* __restri
     bool inside = true;
 #pragma unroll
     for (uint32_t d = 0; d < D; ++d) { x[d] = inputs[(size_t)b * D + d]; inside = inside && !(x[d] < 0.f || x[d] > 1.f); }
-    float* out = outputs + ((size_t)level * B + b) * C;
+    // reference layout [L,B,C] (hashgrid.py:31) or point-major [B,L,C] = the [B, L*C] tensor the module returns
+    float* out = outputs + (point_major ? ((size_t)b * L + level) : ((size_t)level * B + b)) * C;
     float* jac = want_jac ? dy_dx + (((size_t)b * L + level) * D) * C : nullptr;
     int32_t* ids = corner_ids ? corner_ids + ((size_t)level * B + b) * (1u << D) : nullptr;
     if (!inside) {
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) hash_forward_kernel(const float* __restri
 template <uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256) hash_backward_kernel(const float* __restrict__ grad, const float* __restrict__ inputs,
                                                             const int32_t* __restrict__ offsets, float* __restrict__ grad_table,
-                                                            uint32_t B, uint32_t L, float S, uint32_t H) {
+                                                            uint32_t B, uint32_t L, float S, uint32_t H, bool point_major) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) hash_backward_kernel(const float* __restr
     }
     float g[C];
 #pragma unroll
-    for (uint32_t c = 0; c < C; ++c) g[c] = grad[((size_t)level * B + b) * C + c];
+    for (uint32_t c = 0; c < C; ++c) g[c] = grad[(point_major ? ((size_t)b * L + level) : ((size_t)level * B + b)) * C + c];
     float* __restrict__ dst = grad_table + (size_t)m.offset * C;
 #pragma unroll
     for (uint32_t k = 0; k < (1u << D); ++k) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) hash_backward_kernel(const float* __restr
 // grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]   (hashencoder.cu:311-337)
 template <uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256) hash_input_backward_kernel(const float* __restrict__ grad, const float* __restrict__ dy_dx,
-                                                                  float* __restrict__ grad_inputs, uint32_t B, uint32_t L) {
+                                                                  float* __restrict__ grad_inputs, uint32_t B, uint32_t L, bool point_major) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * D) return;
     const uint32_t b = t / D, d = t - b * D;
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(256) hash_input_backward_kernel(const float* _
     float r = 0.f;
     for (uint32_t l = 0; l < L; ++l)
 #pragma unroll
-        for (uint32_t c = 0; c < C; ++c) r = fmaf(grad[((size_t)l * B + b) * C + c], jac[((size_t)l * D + d) * C + c], r);
+        for (uint32_t c = 0; c < C; ++c)
+            r = fmaf(grad[(point_major ? ((size_t)b * L + l) : ((size_t)l * B + b)) * C + c], jac[((size_t)l * D + d) * C + c], r);
     grad_inputs[t] = r;
 }
 
@@ -183,12 +185,12 @@ __global__ void level_scales_kernel(float* scales, uint32_t L, float S, uint32_t
 
 template <uint32_t D>
 int launch_forward(uint32_t C, dim3 grid, cudaStream_t st, const float* in, const float* tab, const int32_t* off, float* out,
-                   uint32_t B, uint32_t L, float S, uint32_t H, bool jac, float* dy_dx, int32_t* ids) {
+                   uint32_t B, uint32_t L, float S, uint32_t H, bool jac, float* dy_dx, int32_t* ids, bool pm) {
     switch (C) {
-        case 1: hash_forward_kernel<D, 1><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids); break;
-        case 2: hash_forward_kernel<D, 2><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids); break;
-        case 4: hash_forward_kernel<D, 4><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids); break;
-        case 8: hash_forward_kernel<D, 8><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids); break;
+        case 1: hash_forward_kernel<D, 1><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids, pm); break;
+        case 2: hash_forward_kernel<D, 2><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids, pm); break;
+        case 4: hash_forward_kernel<D, 4><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids, pm); break;
+        case 8: hash_forward_kernel<D, 8><<<grid, 256, 0, st>>>(in, tab, off, out, B, L, S, H, jac, dy_dx, ids, pm); break;
         default: return AC_E_UNSUPPORTED;
     }
     return acb::launched();
@@ -196,17 +198,17 @@ int launch_forward(uint32_t C, dim3 grid, cudaStream_t st, const float* in, cons
 
 template <uint32_t D>
 int launch_backward(uint32_t C, dim3 grid, cudaStream_t st, const float* grad, const float* in, const int32_t* off, float* gt,
-                    uint32_t B, uint32_t L, float S, uint32_t H, bool jac, const float* dy_dx, float* gi) {
+                    uint32_t B, uint32_t L, float S, uint32_t H, bool jac, const float* dy_dx, float* gi, bool pm) {
     const uint32_t gin = (B * D + 255) / 256;
     switch (C) {
-        case 1: hash_backward_kernel<D, 1><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H);
-                if (jac) hash_input_backward_kernel<D, 1><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L); break;
-        case 2: hash_backward_kernel<D, 2><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H);
-                if (jac) hash_input_backward_kernel<D, 2><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L); break;
-        case 4: hash_backward_kernel<D, 4><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H);
-                if (jac) hash_input_backward_kernel<D, 4><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L); break;
-        case 8: hash_backward_kernel<D, 8><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H);
-                if (jac) hash_input_backward_kernel<D, 8><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L); break;
+        case 1: hash_backward_kernel<D, 1><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H, pm);
+                if (jac) hash_input_backward_kernel<D, 1><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L, pm); break;
+        case 2: hash_backward_kernel<D, 2><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H, pm);
+                if (jac) hash_input_backward_kernel<D, 2><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L, pm); break;
+        case 4: hash_backward_kernel<D, 4><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H, pm);
+                if (jac) hash_input_backward_kernel<D, 4><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L, pm); break;
+        case 8: hash_backward_kernel<D, 8><<<grid, 256, 0, st>>>(grad, in, off, gt, B, L, S, H, pm);
+                if (jac) hash_input_backward_kernel<D, 8><<<gin, 256, 0, st>>>(grad, dy_dx, gi, B, L, pm); break;
         default: return AC_E_UNSUPPORTED;
     }
     int rc = acb::launched();
@@ -218,30 +220,49 @@ int launch_backward(uint32_t C, dim3 grid, cudaStream_t st, const float* grad, c
 
 extern "C" {
 
-int ac_hash_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs, uint32_t B,
-                           uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, float* dy_dx,
-                           int32_t* corner_ids, void* stream) {
+static int hash_forward_any(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs, uint32_t B,
+                            uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, float* dy_dx,
+                            int32_t* corner_ids, void* stream, bool pm) {
     if (!inputs || !embeddings || !offsets || !outputs || (calc_grad_inputs && !dy_dx) || L == 0) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
     const dim3 grid((B + 255) / 256, L, 1);
     cudaStream_t st = (cudaStream_t)stream;
-    if (D == 2) return launch_forward<2>(C, grid, st, inputs, embeddings, offsets, outputs, B, L, S, H, calc_grad_inputs != 0, dy_dx, corner_ids);
-    if (D == 3) return launch_forward<3>(C, grid, st, inputs, embeddings, offsets, outputs, B, L, S, H, calc_grad_inputs != 0, dy_dx, corner_ids);
+    if (D == 2) return launch_forward<2>(C, grid, st, inputs, embeddings, offsets, outputs, B, L, S, H, calc_grad_inputs != 0, dy_dx, corner_ids, pm);
+    if (D == 3) return launch_forward<3>(C, grid, st, inputs, embeddings, offsets, outputs, B, L, S, H, calc_grad_inputs != 0, dy_dx, corner_ids, pm);
     return AC_E_UNSUPPORTED;
 }
+int ac_hash_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs, uint32_t B,
+                           uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, float* dy_dx,
+                           int32_t* corner_ids, void* stream) {
+    return hash_forward_any(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, corner_ids, stream, false);
+}
+int ac_hash_encode_forward_pm(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs, uint32_t B,
+                              uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, float* dy_dx, void* stream) {
+    return hash_forward_any(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, nullptr, stream, true);
+}
 
-int ac_hash_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int32_t* offsets,
-                            float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
-                            int calc_grad_inputs, const float* dy_dx, float* grad_inputs, void* stream) {
-    (void)embeddings;
+static int hash_backward_any(const float* grad, const float* inputs, const int32_t* offsets,
+                             float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             int calc_grad_inputs, const float* dy_dx, float* grad_inputs, void* stream, bool pm) {
     if (!grad || !inputs || !offsets || !grad_embeddings || (calc_grad_inputs && (!dy_dx || !grad_inputs)) || L == 0)
         return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
     const dim3 grid((B + 255) / 256, L, 1);
     cudaStream_t st = (cudaStream_t)stream;
-    if (D == 2) return launch_backward<2>(C, grid, st, grad, inputs, offsets, grad_embeddings, B, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs);
-    if (D == 3) return launch_backward<3>(C, grid, st, grad, inputs, offsets, grad_embeddings, B, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs);
+    if (D == 2) return launch_backward<2>(C, grid, st, grad, inputs, offsets, grad_embeddings, B, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs, pm);
+    if (D == 3) return launch_backward<3>(C, grid, st, grad, inputs, offsets, grad_embeddings, B, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs, pm);
     return AC_E_UNSUPPORTED;
+}
+int ac_hash_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int32_t* offsets,
+                            float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                            int calc_grad_inputs, const float* dy_dx, float* grad_inputs, void* stream) {
+    (void)embeddings;
+    return hash_backward_any(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs, dy_dx, grad_inputs, stream, false);
+}
+int ac_hash_encode_backward_pm(const float* grad, const float* inputs, const int32_t* offsets, float* grad_embeddings, uint32_t B,
+                               uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, const float* dy_dx,
+                               float* grad_inputs, void* stream) {
+    return hash_backward_any(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs, dy_dx, grad_inputs, stream, true);
 }
 
 int ac_hash_level_scales(float* scales, uint32_t L, float S, uint32_t H, void* stream) {

@@ -1,1 +1,1 @@
-from .hashgrid import HashEncoder
+from .grid import GridSpec, HashEncoder, hash_encode  # noqa: F401

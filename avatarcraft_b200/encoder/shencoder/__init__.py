@@ -1,1 +1,1 @@
-from .sphere_harmonics import SHEncoder
+from .sh import SHEncoder, sh_encode  # noqa: F401

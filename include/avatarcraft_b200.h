@@ -51,6 +51,16 @@ int ac_hash_encode_backward(const float *grad, const float *inputs, const float 
                             const int32_t *offsets, float *grad_embeddings, uint32_t B, uint32_t D,
                             uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
                             const float *dy_dx, float *grad_inputs, void *stream);
+/* Point-major variants: outputs / grad are [B, L*C] -- the tensor HashEncoder.forward hands to the MLP -- so the
+ * reference wrapper's [L,B,C] -> [B,L*C] permute copies (hashgrid.py:41,56; 134 MB read+write per 524 288-point
+ * call) disappear.  Same arithmetic as the reference-layout ops. */
+int ac_hash_encode_forward_pm(const float *inputs, const float *embeddings, const int32_t *offsets,
+                              float *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                              uint32_t H, int calc_grad_inputs, float *dy_dx, void *stream);
+int ac_hash_encode_backward_pm(const float *grad, const float *inputs, const int32_t *offsets,
+                               float *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                               uint32_t H, int calc_grad_inputs, const float *dy_dx, float *grad_inputs,
+                               void *stream);
 /* Per-level scale exp2f(l*S)*H-1 as evaluated ON THE DEVICE (hashencoder.cu:121); scales [L]. */
 int ac_hash_level_scales(float *scales, uint32_t L, float S, uint32_t H, void *stream);
 

@@ -73,3 +73,32 @@ def test_sh_module_and_factory():
     with pytest.raises(RuntimeError):
         from avatarcraft_b200.encoder.shencoder.backend import _backend
         _backend.sh_encode_forward(d.detach(), y.detach(), 100, 3, 9, False, y.detach())     # degree 9 unsupported
+
+
+def test_point_major_hash_ops_equal_reference_layout_ops():
+    """ac_hash_encode_forward_pm / _backward_pm ([B, L*C] in and out) == the reference-layout ops up to the permute;
+    HashEncoder (module) gradients flow to the table and, when asked, to the inputs."""
+    from avatarcraft_b200 import _lib
+    from avatarcraft_b200.encoder.hashencoder import GridSpec, HashEncoder, hash_encode
+    from avatarcraft_b200.encoder.hashencoder.backend import _backend
+    spec = GridSpec(3, 16, 2, 16, float(np.exp2(np.log2(2048 / 16) / 15)), 19)
+    offs = torch.from_numpy(spec.level_offsets()).cuda()
+    g = torch.Generator().manual_seed(2)
+    table = ((torch.rand(int(offs[-1]), 2, generator=g) * 2 - 1) * 0.1).cuda().requires_grad_(True)
+    x = torch.rand(20000, 3, generator=g).cuda().requires_grad_(True)
+    feats = hash_encode(x, table, offs, spec)
+    ref = torch.empty(16, 20000, 2, device="cuda"); jac = torch.empty(20000, 16 * 3 * 2, device="cuda")
+    _backend.hash_encode_forward(x.detach(), table.detach(), offs, ref, 20000, 3, 2, 16, spec.log2_scale, 16, True, jac)
+    assert torch.equal(feats.detach(), ref.permute(1, 0, 2).reshape(20000, 32))
+    R = torch.randn(20000, 32, generator=g).cuda()
+    (feats * R).sum().backward()
+    gt = torch.zeros_like(table); gi = torch.zeros(20000, 3, device="cuda")
+    _backend.hash_encode_backward(R.view(20000, 16, 2).permute(1, 0, 2).contiguous(), x.detach(), table.detach(), offs, gt, 20000, 3, 2, 16,
+                                  spec.log2_scale, 16, True, jac, gi)
+    np.testing.assert_allclose(table.grad.cpu().numpy(), gt.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), gi.cpu().numpy(), rtol=1e-4, atol=1e-2)
+    enc = HashEncoder(desired_resolution=2048, per_level_scale=1.3819).cuda()
+    assert enc.offsets.tolist() == spec.level_offsets().tolist() and enc.output_dim == 32
+    y = enc((torch.rand(100, 7, 3, device="cuda") * 2 - 1) * 1.6, 1.6)
+    y.square().sum().backward()
+    assert y.shape == (100, 7, 32) and enc.embeddings.grad is not None and float(enc.embeddings.grad.abs().sum()) > 0

@@ -88,3 +88,25 @@ def test_render_driver_passes_warp_arguments(body):
                                               return_raw=True, verts=body["world_verts"], faces=body["faces"], Ts=body["Ts"],
                                               num_steps=32, upsample_steps=32, bound=1.6)
     assert rgb.shape == (1024, 3) and torch.isfinite(rgb).all() and extra["weight_sum"].shape == (1024, 1)
+
+
+def test_entry_scripts_run_end_to_end(tmp_path):
+    """render_canonical.py / render_warp.py / stylize.py in --synthetic mode at tiny sizes (assets of the reference are
+    not redistributable): they must run, write their outputs, and stylize must change the parameters."""
+    import os, subprocess, sys
+    from tests.util import ROOT
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    run = lambda *a: subprocess.run([sys.executable, *a], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    r = run(os.path.join(ROOT, "render_canonical.py"), "--synthetic", "--exp_name", "t", "--render_h", "32", "--render_w", "32", "--n_views", "2")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(tmp_path / "demo" / "canonical_360" / "t" / "t_body.gif")
+    r = run(os.path.join(ROOT, "render_warp.py"), "--synthetic", "--exp_name", "w", "--resolution", "32", "--max_frames", "2")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(tmp_path / "demo" / "test_views" / "w" / "w_0001.png")
+    r = run(os.path.join(ROOT, "stylize.py"), "--synthetic", "--exp_name", "s", "--render_h", "64", "--render_w", "64", "--n_views", "2",
+            "--coarse_epochs", "1", "--fine_epochs", "0", "--subsample_scale", "2", "--batch_size", "512")
+    assert r.returncode == 0, r.stderr[-2000:]
+    sd = torch.load(tmp_path / "style" / "canonical_360" / "s" / "s.pth.tar", map_location="cpu")
+    ref = state_dict("trained", 43)
+    assert set(sd.keys()) == set(ref.keys())
+    assert float((sd["encoder.embeddings"] - ref["encoder.embeddings"]).abs().max()) > 0
