@@ -47,6 +47,21 @@ __device__ __forceinline__ void stage_model(const float* __restrict__ blob, cons
 
 constexpr size_t kStageBytes = BLOB_FLOATS * sizeof(float) + kLevels * sizeof(LevelMeta);
 
+// SDF network weights (W0 | b0 | W1T | b1 = the first OFF_C0 floats of the blob) in the constant bank for the
+// point-query kernels of the training path: with the hidden-unit loop fully unrolled every weight is an
+// immediate constant-bank operand of its FFMA -- no shared-memory loads (they were ~3000 LDS per point in the
+// backward kernel).  Refreshed by a 13.6 KB D2D copy on the launch stream.
+__constant__ float c_sdf[OFF_C0];
+constexpr size_t kLevelBytes = kLevels * sizeof(LevelMeta);
+
+__device__ __forceinline__ void stage_levels(const int32_t* __restrict__ offsets, float S, uint32_t H, LevelMeta* lv) {
+    if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(offsets, threadIdx.x, S, H, 3);
+    __syncthreads();
+}
+int refresh_c_sdf(const float* blob, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_sdf, blob, OFF_C0 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? AC_OK : acb::cuda_fail();
+}
+
 __global__ void __launch_bounds__(kWarps * 32) nsr_render_kernel(const RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sw = reinterpret_cast<float*>(smem_raw);
@@ -231,19 +246,28 @@ __global__ void __launch_bounds__(1024) eikonal_reduce_kernel(const float* __res
 
 // ---- flat-point queries (NeRFNetwork.forward_sdf / forward_color / gradient) ----
 __global__ void __launch_bounds__(256) forward_sdf_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
-                                                          const float* __restrict__ blob, float S, uint32_t H,
-                                                          const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sw = reinterpret_cast<float*>(smem_raw);
-    LevelMeta* lv = reinterpret_cast<LevelMeta*>(sw + BLOB_FLOATS);
-    stage_model(blob, offsets, S, H, sw, lv);
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-        float o16[16];
-        sdf_point<true>(table, lv, sw, bound, x[3 * b], x[3 * b + 1], x[3 * b + 2], o16);
-        float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)b);
+                                                          float S, uint32_t H, const float* __restrict__ x, float* __restrict__ out,
+                                                          uint32_t B, float bound) {
+    __shared__ LevelMeta lv[kLevels];
+    stage_levels(offsets, S, H, lv);
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float in[kSdfInPad], o16[16];
+    encode_point(table, lv, bound, x[3 * (size_t)b], x[3 * (size_t)b + 1], x[3 * (size_t)b + 2], in);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+    for (int o = 0; o < 16; ++o) o16[o] = c_sdf[OFF_B1 + o];
+#pragma unroll
+    for (int j = 0; j < kHidden; ++j) {
+        float a = c_sdf[OFF_B0 + j];
+#pragma unroll
+        for (int k = 0; k < 35; ++k) a = fmaf(c_sdf[OFF_W0 + j * kSdfInPad + k], in[k], a);
+        const float h = softplus100(a);
+#pragma unroll
+        for (int o = 0; o < 16; ++o) o16[o] = fmaf(c_sdf[OFF_W1T + j * 16 + o], h, o16[o]);
     }
+    float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)b);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
 }
 
 __global__ void __launch_bounds__(256) fd_gradient_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
@@ -300,15 +324,13 @@ __global__ void __launch_bounds__(256) forward_color_kernel(const float* __restr
 //       delta_a [B,64] = dL/d(pre-activation), hidden [B,64] = softplus output, feats [B,32].
 // softplus'(a) = sigmoid(100 a) (1 above torch's threshold 100a > 20).
 __global__ void __launch_bounds__(256) sdf_backward_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
-                                                           const float* __restrict__ blob, float S, uint32_t H,
+                                                           float S, uint32_t H,
                                                            const float* __restrict__ x, const float* __restrict__ gout,
                                                            uint32_t B, float bound, float* __restrict__ grad_table,
                                                            float* __restrict__ delta_a, float* __restrict__ hidden,
                                                            float* __restrict__ feats) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sw = reinterpret_cast<float*>(smem_raw);
-    LevelMeta* lv = reinterpret_cast<LevelMeta*>(sw + BLOB_FLOATS);
-    stage_model(blob, offsets, S, H, sw, lv);
+    __shared__ LevelMeta lv[kLevels];
+    stage_levels(offsets, S, H, lv);
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float px = x[3 * (size_t)b], py = x[3 * (size_t)b + 1], pz = x[3 * (size_t)b + 2];
@@ -323,31 +345,21 @@ __global__ void __launch_bounds__(256) sdf_backward_kernel(const float2* __restr
     float din[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) din[k] = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < kHidden; ++j) {
-        const float4* __restrict__ wr = reinterpret_cast<const float4*>(sw + OFF_W0 + j * kSdfInPad);
-        float a = sw[OFF_B0 + j];
 #pragma unroll
-        for (int q = 0; q < kSdfInPad / 4; ++q) {
-            const float4 w4 = wr[q];
-            a = fmaf(w4.x, in[4 * q + 0], a); a = fmaf(w4.y, in[4 * q + 1], a);
-            a = fmaf(w4.z, in[4 * q + 2], a); a = fmaf(w4.w, in[4 * q + 3], a);
-        }
+    for (int j = 0; j < kHidden; ++j) {
+        float a = c_sdf[OFF_B0 + j];
+#pragma unroll
+        for (int k = 0; k < 35; ++k) a = fmaf(c_sdf[OFF_W0 + j * kSdfInPad + k], in[k], a);
         const float h = softplus100(a);
-        const float4* __restrict__ w1 = reinterpret_cast<const float4*>(sw + OFF_W1T + j * 16);
         float dh = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 w4 = w1[q];
-            dh = fmaf(w4.x, g[4 * q], dh); dh = fmaf(w4.y, g[4 * q + 1], dh);
-            dh = fmaf(w4.z, g[4 * q + 2], dh); dh = fmaf(w4.w, g[4 * q + 3], dh);
-        }
+        for (int o = 0; o < 16; ++o) dh = fmaf(c_sdf[OFF_W1T + j * 16 + o], g[o], dh);
         const float da = a * 100.0f > 20.0f ? dh : dh * sigmoidf(a * 100.0f);
         delta_a[(size_t)b * kHidden + j] = da;
         hidden[(size_t)b * kHidden + j] = h;
         // d(features): columns 3..34 of row j (floats 3..34 of the padded row)
 #pragma unroll
-        for (int k = 0; k < 32; ++k) din[k] = fmaf(sw[OFF_W0 + j * kSdfInPad + 3 + k], da, din[k]);
+        for (int k = 0; k < 32; ++k) din[k] = fmaf(c_sdf[OFF_W0 + j * kSdfInPad + 3 + k], da, din[k]);
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q)
@@ -489,10 +501,9 @@ static int check_model(const ac_nsr_model* m) {
 int ac_nsr_forward_sdf(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, void* stream) {
     if (check_model(m) || !x || !out) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(forward_sdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes); attr = true; }
-    forward_sdf_kernel<<<grid_for(B, 256, 4), 256, kStageBytes, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
+    if (int rc = refresh_c_sdf(m->mlp_blob, (cudaStream_t)stream)) return rc;
+    forward_sdf_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->log2_per_level_scale,
         m->base_resolution, x, out, B, bound);
     return acb::launched();
 }
@@ -501,10 +512,9 @@ int ac_nsr_sdf_backward(const ac_nsr_model* m, const float* x, const float* grad
                         float* grad_table, float* delta_a, float* hidden, float* feats, void* stream) {
     if (check_model(m) || !x || !grad_out || !grad_table || !delta_a || !hidden || !feats) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sdf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes); attr = true; }
-    sdf_backward_kernel<<<(B + 255) / 256, 256, kStageBytes, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
+    if (int rc = refresh_c_sdf(m->mlp_blob, (cudaStream_t)stream)) return rc;
+    sdf_backward_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->log2_per_level_scale,
         m->base_resolution, x, grad_out, B, bound, grad_table, delta_a, hidden, feats);
     return acb::launched();
 }
