@@ -324,67 +324,85 @@ __global__ void __launch_bounds__(256) forward_color_kernel(const float* __restr
 //       delta_a [B,64] = dL/d(pre-activation), hidden [B,64] = softplus output, feats [B,32].
 // softplus'(a) = sigmoid(100 a) (1 above torch's threshold 100a > 20).
 __global__ void __launch_bounds__(256) sdf_backward_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
-                                                           float S, uint32_t H,
+                                                           const float* __restrict__ blob, float S, uint32_t H,
                                                            const float* __restrict__ x, const float* __restrict__ gout,
                                                            uint32_t B, float bound, float* __restrict__ grad_table,
                                                            float* __restrict__ delta_a, float* __restrict__ hidden,
                                                            float* __restrict__ feats) {
-    __shared__ LevelMeta lv[kLevels];
-    stage_levels(offsets, S, H, lv);
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float px = x[3 * (size_t)b], py = x[3 * (size_t)b + 1], pz = x[3 * (size_t)b + 2];
-    float in[kSdfInPad];
-    encode_point(table, lv, bound, px, py, pz, in);
-    float g[16];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(sw + BLOB_FLOATS);
+    float* w0f = reinterpret_cast<float*>(lv + kLevels);          // [64][32] feature columns of W0, 16 B aligned rows
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) w0f[i] = __ldg(blob + OFF_W0 + (i >> 5) * kSdfInPad + 3 + (i & 31));
+    stage_model(blob, offsets, S, H, sw, lv);
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {     // persistent: weights staged once
+        const float px = x[3 * (size_t)b], py = x[3 * (size_t)b + 1], pz = x[3 * (size_t)b + 2];
+        float in[kSdfInPad];
+        encode_point(table, lv, bound, px, py, pz, in);
+        float g[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(gout + 16 * (size_t)b + 4 * q);
-        g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
-    }
-    float din[32];
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(gout + 16 * (size_t)b + 4 * q);
+            g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+        }
+        float din[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) din[k] = 0.f;
+        for (int k = 0; k < 32; ++k) din[k] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < kHidden; ++j) {
+            const float4* __restrict__ wr = reinterpret_cast<const float4*>(sw + OFF_W0 + j * kSdfInPad);
+            float a = sw[OFF_B0 + j];
 #pragma unroll
-    for (int j = 0; j < kHidden; ++j) {
-        float a = c_sdf[OFF_B0 + j];
+            for (int q = 0; q < kSdfInPad / 4; ++q) {
+                const float4 w4 = wr[q];
+                a = fmaf(w4.x, in[4 * q + 0], a); a = fmaf(w4.y, in[4 * q + 1], a);
+                a = fmaf(w4.z, in[4 * q + 2], a); a = fmaf(w4.w, in[4 * q + 3], a);
+            }
+            const float h = softplus100(a);
+            const float4* __restrict__ w1 = reinterpret_cast<const float4*>(sw + OFF_W1T + j * 16);
+            float dh = 0.f;
 #pragma unroll
-        for (int k = 0; k < 35; ++k) a = fmaf(c_sdf[OFF_W0 + j * kSdfInPad + k], in[k], a);
-        const float h = softplus100(a);
-        float dh = 0.f;
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = w1[q];
+                dh = fmaf(w4.x, g[4 * q], dh); dh = fmaf(w4.y, g[4 * q + 1], dh);
+                dh = fmaf(w4.z, g[4 * q + 2], dh); dh = fmaf(w4.w, g[4 * q + 3], dh);
+            }
+            const float da = a * 100.0f > 20.0f ? dh : dh * sigmoidf(a * 100.0f);
+            delta_a[(size_t)b * kHidden + j] = da;
+            hidden[(size_t)b * kHidden + j] = h;
+            const float4* __restrict__ wf = reinterpret_cast<const float4*>(w0f + j * 32);
 #pragma unroll
-        for (int o = 0; o < 16; ++o) dh = fmaf(c_sdf[OFF_W1T + j * 16 + o], g[o], dh);
-        const float da = a * 100.0f > 20.0f ? dh : dh * sigmoidf(a * 100.0f);
-        delta_a[(size_t)b * kHidden + j] = da;
-        hidden[(size_t)b * kHidden + j] = h;
-        // d(features): columns 3..34 of row j (floats 3..34 of the padded row)
+            for (int q = 0; q < 8; ++q) {
+                const float4 w4 = wf[q];
+                din[4 * q + 0] = fmaf(w4.x, da, din[4 * q + 0]); din[4 * q + 1] = fmaf(w4.y, da, din[4 * q + 1]);
+                din[4 * q + 2] = fmaf(w4.z, da, din[4 * q + 2]); din[4 * q + 3] = fmaf(w4.w, da, din[4 * q + 3]);
+            }
+        }
 #pragma unroll
-        for (int k = 0; k < 32; ++k) din[k] = fmaf(c_sdf[OFF_W0 + j * kSdfInPad + 3 + k], da, din[k]);
-    }
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(feats + 32 * (size_t)b + 4 * q) = make_float4(in[3 + 4 * q], in[4 + 4 * q], in[5 + 4 * q], in[6 + 4 * q]);
+        // scatter into the table
+        const float two_b = 2.0f * bound;
+        const float u = (px + bound) / two_b, v = (py + bound) / two_b, w = (pz + bound) / two_b;
+        if ((u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f)) continue;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(feats + 32 * (size_t)b + 4 * q) = make_float4(in[3 + 4 * q], in[4 + 4 * q], in[5 + 4 * q], in[6 + 4 * q]);
-    // scatter into the table
-    const float two_b = 2.0f * bound;
-    const float u = (px + bound) / two_b, v = (py + bound) / two_b, w = (pz + bound) / two_b;
-    if ((u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f)) return;
+        for (int l = 0; l < kLevels; ++l) {
+            const LevelMeta m = lv[l];
+            float fx = fmaf(u, m.scale, 0.5f), fy = fmaf(v, m.scale, 0.5f), fz = fmaf(w, m.scale, 0.5f);
+            const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+            const uint32_t ix = (uint32_t)flx, iy = (uint32_t)fly, iz = (uint32_t)flz;
+            fx -= flx; fy -= fly; fz -= flz;
+            float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
+            const float gx = din[2 * l], gy = din[2 * l + 1];
 #pragma unroll
-    for (int l = 0; l < kLevels; ++l) {
-        const LevelMeta m = lv[l];
-        float fx = fmaf(u, m.scale, 0.5f), fy = fmaf(v, m.scale, 0.5f), fz = fmaf(w, m.scale, 0.5f);
-        const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-        const uint32_t ix = (uint32_t)flx, iy = (uint32_t)fly, iz = (uint32_t)flz;
-        fx -= flx; fy -= fly; fz -= flz;
-        float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
-        const float gx = din[2 * l], gy = din[2 * l + 1];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t cx = ix + (k & 1), cy = iy + ((k >> 1) & 1), cz = iz + ((k >> 2) & 1);
-            uint32_t slot;
-            if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
-            else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
-            const float wgt = (((k & 1) ? fx : 1.0f - fx) * ((k & 2) ? fy : 1.0f - fy)) * ((k & 4) ? fz : 1.0f - fz);
-            atomicAdd(dst + slot, make_float2(wgt * gx, wgt * gy));
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t cx = ix + (k & 1), cy = iy + ((k >> 1) & 1), cz = iz + ((k >> 2) & 1);
+                uint32_t slot;
+                if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
+                else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
+                const float wgt = (((k & 1) ? fx : 1.0f - fx) * ((k & 2) ? fy : 1.0f - fy)) * ((k & 4) ? fz : 1.0f - fz);
+                atomicAdd(dst + slot, make_float2(wgt * gx, wgt * gy));
+            }
         }
     }
 }
@@ -512,9 +530,11 @@ int ac_nsr_sdf_backward(const ac_nsr_model* m, const float* x, const float* grad
                         float* grad_table, float* delta_a, float* hidden, float* feats, void* stream) {
     if (check_model(m) || !x || !grad_out || !grad_table || !delta_a || !hidden || !feats) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
-    if (int rc = refresh_c_sdf(m->mlp_blob, (cudaStream_t)stream)) return rc;
-    sdf_backward_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->log2_per_level_scale,
+    constexpr size_t smem = kStageBytes + 64 * 32 * sizeof(float);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sdf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    sdf_backward_kernel<<<grid_for(B, 256, 2), 256, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
         m->base_resolution, x, grad_out, B, bound, grad_table, delta_a, hidden, feats);
     return acb::launched();
 }
