@@ -54,8 +54,51 @@ __device__ __forceinline__ LevelMeta make_level_meta(const int32_t* __restrict__
     return m;
 }
 
+// Hashed levels whose size is not a power of two (never the case for the reference's configuration) take a real
+// function call, so the 20-instruction integer modulo is not if-converted into the common path.
+static __device__ __noinline__ uint32_t slot_modulo(uint32_t h, uint32_t size) { return h % size; }
 __device__ __forceinline__ uint32_t wrap_slot(uint32_t h, const LevelMeta& m) {
-    return m.hashed == 1u ? (h & (m.size - 1u)) : (h % m.size);
+    if (m.hashed == 1u) return h & (m.size - 1u);
+    return slot_modulo(h, m.size);
+}
+
+// Level bodies with the level kind known at compile time (used when the offsets table has the reference layout:
+// leading dense levels, then power-of-two hashed levels).  Bit-identical to grid_level_3d.
+template <bool HASHED>
+__device__ __forceinline__ float2 grid_level_3d_k(const float2* __restrict__ table, const LevelMeta m, float x, float y, float z) {
+    float px = fmaf(x, m.scale, 0.5f), py = fmaf(y, m.scale, 0.5f), pz = fmaf(z, m.scale, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz;
+    px -= fx; py -= fy; pz -= fz;
+    const float qx = 1.0f - px, qy = 1.0f - py, qz = 1.0f - pz;
+    const float2* __restrict__ t = table + m.offset;
+    uint32_t s[8];
+    if (!HASHED) {
+        const uint32_t s1 = m.res1, s2 = m.res1 * m.res1;
+        const uint32_t b = ix + iy * s1 + iz * s2;
+        s[0] = b;          s[1] = b + 1u;          s[2] = b + s1;          s[3] = b + s1 + 1u;
+        s[4] = b + s2;     s[5] = b + s2 + 1u;     s[6] = b + s2 + s1;     s[7] = b + s2 + s1 + 1u;
+    } else {
+        const uint32_t mask = m.size - 1u;
+        const uint32_t hx0 = ix, hx1 = ix + 1u;
+        const uint32_t hy0 = iy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = iz * 805459861u, hz1 = hz0 + 805459861u;
+        s[0] = (hx0 ^ hy0 ^ hz0) & mask; s[1] = (hx1 ^ hy0 ^ hz0) & mask;
+        s[2] = (hx0 ^ hy1 ^ hz0) & mask; s[3] = (hx1 ^ hy1 ^ hz0) & mask;
+        s[4] = (hx0 ^ hy0 ^ hz1) & mask; s[5] = (hx1 ^ hy0 ^ hz1) & mask;
+        s[6] = (hx0 ^ hy1 ^ hz1) & mask; s[7] = (hx1 ^ hy1 ^ hz1) & mask;
+    }
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float w = (((k & 1) ? px : qx) * ((k & 2) ? py : qy)) * ((k & 4) ? pz : qz);
+        r.x = fmaf(w, v[k].x, r.x);
+        r.y = fmaf(w, v[k].y, r.y);
+    }
+    return r;
 }
 
 // One level of the D=3, C=2 grid for a point already mapped to [0,1]^3

@@ -52,7 +52,6 @@ constexpr size_t kStageBytes = BLOB_FLOATS * sizeof(float) + kLevels * sizeof(Le
 // immediate constant-bank operand of its FFMA -- no shared-memory loads (they were ~3000 LDS per point in the
 // backward kernel).  Refreshed by a 13.6 KB D2D copy on the launch stream.
 __constant__ float c_sdf[OFF_C0];
-constexpr size_t kLevelBytes = kLevels * sizeof(LevelMeta);
 
 __device__ __forceinline__ void stage_levels(const int32_t* __restrict__ offsets, float S, uint32_t H, LevelMeta* lv) {
     if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(offsets, threadIdx.x, S, H, 3);

@@ -93,6 +93,7 @@ struct Group {
     uint32_t tmem;        // accumulator address of this thread's row (lane field set), column 0 of the group
     uint32_t bar_id;
     int row;              // 0..127 inside the group
+    bool std_layout;      // offsets table has the reference layout (5 dense + 11 power-of-two hashed levels)
 };
 
 // Make this thread's A-row stores visible to the tensor core, rendezvous the group, let one thread issue,
@@ -128,37 +129,48 @@ __device__ __forceinline__ void issue_k32_x3(uint32_t tmem_d, uint32_t a_s, uint
 }
 
 // Hash-encode one point (features only) into this thread's A-tile row.  ONE copy of this code serves every
-// call site (__noinline__): with 32 warps in eight independent phases the instruction cache, not the
+// call site (__noinline__): with 28 warps in seven independent phases the instruction cache, not the
 // issue slots, was the first thing to saturate when it was inlined four times.
+__device__ __forceinline__ void store_chunk(unsigned char* arow, int c, float2 f0, float2 f1, float2 f2, float2 f3) {
+    uint4 hi, lo;
+    tc05::split_f16x2(f0.x, f0.y, hi.x, lo.x);
+    tc05::split_f16x2(f1.x, f1.y, hi.y, lo.y);
+    tc05::split_f16x2(f2.x, f2.y, hi.z, lo.z);
+    tc05::split_f16x2(f3.x, f3.y, hi.w, lo.w);
+    *reinterpret_cast<uint4*>(arow + c * 2048) = hi;
+    *reinterpret_cast<uint4*>(arow + 8192 + c * 2048) = lo;
+}
+
+// Any offsets table (cold path): level kind decided per level at run time.
+__device__ __noinline__ void encode_to_tile_generic(unsigned char* arow, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
+                                                    float u, float v, float w) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c)
+        store_chunk(arow, c, grid_level_3d(table, lv[4 * c + 0], u, v, w), grid_level_3d(table, lv[4 * c + 1], u, v, w),
+                    grid_level_3d(table, lv[4 * c + 2], u, v, w), grid_level_3d(table, lv[4 * c + 3], u, v, w));
+}
+
+// `std_layout`: levels 0..4 dense, 5..15 hashed with power-of-two sizes -- the reference's only configuration
+// (models/instant_nsr.py:503-512); verified once per CTA from the offsets table.
 __device__ __noinline__ void encode_to_tile(unsigned char* arow, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
-                                            float bound, float x, float y, float z) {
+                                            float bound, float x, float y, float z, bool std_layout) {
     const float two_b = 2.0f * bound;
     const float u = (x + bound) / two_b, v = (y + bound) / two_b, w = (z + bound) / two_b;
-    const bool oob = (u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f);
-    AC_UNROLL(AC_ENCODE_UNROLL)
-    for (int c = 0; c < 4; ++c) {               // 4 levels = 8 features = one 16-byte fp16 chunk of the row
-        uint4 hi, lo;
-        float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
-        if (!oob) {
-#if AC_SPECIALIZED_LEVELS
-            f0 = grid_level_3d(table, lv[4 * c + 0], u, v, w);
-            f1 = grid_level_3d(table, lv[4 * c + 1], u, v, w);
-            f2 = grid_level_3d(table, lv[4 * c + 2], u, v, w);
-            f3 = grid_level_3d(table, lv[4 * c + 3], u, v, w);
-#else
-            f0 = grid_level_3d_u(table, lv[4 * c + 0], u, v, w);
-            f1 = grid_level_3d_u(table, lv[4 * c + 1], u, v, w);
-            f2 = grid_level_3d_u(table, lv[4 * c + 2], u, v, w);
-            f3 = grid_level_3d_u(table, lv[4 * c + 3], u, v, w);
-#endif
-        }
-        tc05::split_f16x2(f0.x, f0.y, hi.x, lo.x);
-        tc05::split_f16x2(f1.x, f1.y, hi.y, lo.y);
-        tc05::split_f16x2(f2.x, f2.y, hi.z, lo.z);
-        tc05::split_f16x2(f3.x, f3.y, hi.w, lo.w);
-        *reinterpret_cast<uint4*>(arow + c * 2048) = hi;
-        *reinterpret_cast<uint4*>(arow + 8192 + c * 2048) = lo;
+    if ((u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f)) {       // hashencoder.cu:94-119: zeros
+        const float2 z2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) store_chunk(arow, c, z2, z2, z2, z2);
+        return;
     }
+    if (!std_layout) { encode_to_tile_generic(arow, table, lv, u, v, w); return; }
+    store_chunk(arow, 0, grid_level_3d_k<false>(table, lv[0], u, v, w), grid_level_3d_k<false>(table, lv[1], u, v, w),
+                grid_level_3d_k<false>(table, lv[2], u, v, w), grid_level_3d_k<false>(table, lv[3], u, v, w));
+    store_chunk(arow, 1, grid_level_3d_k<false>(table, lv[4], u, v, w), grid_level_3d_k<true>(table, lv[5], u, v, w),
+                grid_level_3d_k<true>(table, lv[6], u, v, w), grid_level_3d_k<true>(table, lv[7], u, v, w));
+#pragma unroll 1
+    for (int c = 2; c < 4; ++c)
+        store_chunk(arow, c, grid_level_3d_k<true>(table, lv[4 * c + 0], u, v, w), grid_level_3d_k<true>(table, lv[4 * c + 1], u, v, w),
+                    grid_level_3d_k<true>(table, lv[4 * c + 2], u, v, w), grid_level_3d_k<true>(table, lv[4 * c + 3], u, v, w));
 }
 
 // Epilogue of the SDF network for this thread's accumulator row: + raw-xyz columns + bias (exact fp32),
@@ -196,7 +208,7 @@ __device__ __noinline__ float sdf_tail_scalar(uint32_t tmem_row, float x, float 
 template <bool FULL>
 __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
                                                float bound, float x, float y, float z, float (&out)[FULL ? 16 : 1]) {
-    encode_to_tile(g.a + g.row * 16, table, lv, bound, x, y, z);
+    encode_to_tile(g.a + g.row * 16, table, lv, bound, x, y, z, g.std_layout);
     group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_W0_HI, g.b_s + B_W0_LO); });
     if constexpr (FULL) {
 #if AC_FULL_TAIL_LOOP
@@ -337,6 +349,11 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     g.row = (warp & 3) * 32 + lane;
     g.tmem = tmem_base + (uint32_t)group * 64u + ((uint32_t)((warp & 3) * 32) << 16);
     g.bar_id = 1 + group;
+    {
+        bool ok = true;
+        for (int l = 0; l < kLevels; ++l) ok = ok && (lv[l].hashed == (l < 5 ? 0u : 1u));
+        g.std_layout = ok;
+    }
 
     float* zs = reinterpret_cast<float*>(smem + SM_ROWS) + warp * 3 * kMaxT;   // sorted depths
     float* sdfs = zs + kMaxT;                                                  // their SDF
