@@ -3,10 +3,11 @@
 // Reference: utils/ray_utils.py:62-90 warp_samples_to_canonical -- sample points go device->host,
 // libigl's AABB-tree closest-point query runs on the CPU, numpy inverts a blended 4x4 per point, and the
 // result goes back to the device, twice per ray batch (models/instant_nsr.py:166-172,198-203).
-// Here: one kernel per point set, no host round trip.  Closest point on the posed mesh is an exact
-// brute-force search over all triangles (Ericson's region test), pruned with per-triangle bounding
-// spheres; every lane walks the same triangle list, so triangle records are warp-uniform (broadcast)
-// loads from a 64-byte-per-triangle array staged through shared memory in tiles.
+// Here: one kernel per point set, no host round trip.  Closest point on the posed mesh is an EXACT
+// branch-and-bound search (Ericson's region test per triangle): triangles arrive sorted along a Morton curve
+// (host side, utils/ray_utils.PosedMesh), every 64 consecutive records form a cluster with a bounding sphere;
+// a query first scans the cluster whose sphere is nearest, then only the clusters (and, inside them, only the
+// triangles) whose bounding spheres can still beat the current best -- ~5 % of the 13 776 triangles on average.
 // utils/ray_utils.py:277-294 geometry_guided_near_far becomes a warp-per-ray reduction over vertices.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -78,40 +79,78 @@ __device__ __forceinline__ float closest_on_triangle(const TriRec& t, float px, 
     return qx * qx + qy * qy + qz * qz;
 }
 
-constexpr int kTile = 512;       // triangles per shared-memory tile (32 KB)
+constexpr uint32_t kCluster = 64;     // triangles per cluster
+
+// One thread per cluster: bounding sphere of the member triangles' bounding spheres.
+__global__ void __launch_bounds__(128) mesh_cluster_kernel(const TriRec* __restrict__ tris, uint32_t n_faces, float4* __restrict__ clusters) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = c * kCluster;
+    if (lo >= n_faces) return;
+    const uint32_t hi = min(n_faces, lo + kCluster);
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    for (uint32_t t = lo; t < hi; ++t) { mx += tris[t].cx; my += tris[t].cy; mz += tris[t].cz; }
+    const float inv = 1.0f / (float)(hi - lo);
+    mx *= inv; my *= inv; mz *= inv;
+    float R = 0.f;
+    for (uint32_t t = lo; t < hi; ++t) {
+        const float dx = tris[t].cx - mx, dy = tris[t].cy - my, dz = tris[t].cz - mz;
+        R = fmaxf(R, sqrtf(dx * dx + dy * dy + dz * dz) + tris[t].r);
+    }
+    clusters[c] = make_float4(mx, my, mz, R * 1.0001f + 1e-7f);
+}
+
+struct Best { float d2, d, b1, b2; uint32_t f; };
+
+__device__ __forceinline__ void scan_cluster(const TriRec* __restrict__ tris, uint32_t lo, uint32_t hi, float px, float py, float pz, Best& best) {
+    for (uint32_t k = lo; k < hi; ++k) {
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(tris + k) + 1);      // (abx, aby, abz, cx)
+        const float4 q2 = __ldg(reinterpret_cast<const float4*>(tris + k) + 2);      // (acx, acy, acz, cy)
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(tris + k));          // (ax, ay, az, r)
+        const float4 q3 = __ldg(reinterpret_cast<const float4*>(tris + k) + 3);      // (cz, ids)
+        const float dx = px - q1.w, dy = py - q2.w, dz = pz - q3.x;
+        if (sqrtf(dx * dx + dy * dy + dz * dz) - q0.w >= best.d) continue;           // its sphere cannot beat the best
+        TriRec t;
+        t.ax = q0.x; t.ay = q0.y; t.az = q0.z; t.abx = q1.x; t.aby = q1.y; t.abz = q1.z; t.acx = q2.x; t.acy = q2.y; t.acz = q2.z;
+        float b1, b2;
+        const float d2 = closest_on_triangle(t, px, py, pz, b1, b2);
+        if (d2 < best.d2 || (d2 == best.d2 && k < best.f)) { best.d2 = d2; best.d = sqrtf(d2); best.b1 = b1; best.b2 = b2; best.f = k; }
+    }
+}
 
 // pts [n,3] -> can_pts [n,3], mask [n] (dist^2 < threshold), optional closest [n,3], face_id [n], dist2 [n].
 // T [n_T,4,4] row-major per-vertex transforms whose last row is (0,0,0,c).
 __global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, uint32_t n, const TriRec* __restrict__ tris,
-                                                                uint32_t n_faces, const float* __restrict__ T, float threshold,
+                                                                uint32_t n_faces, const float4* __restrict__ clusters,
+                                                                const float* __restrict__ T, float threshold,
                                                                 float* __restrict__ can_pts, float* __restrict__ mask,
                                                                 float* __restrict__ closest, int32_t* __restrict__ face_id,
                                                                 float* __restrict__ dist2_out) {
-    __shared__ TriRec tile[kTile];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    const uint32_t ii = live ? i : n - 1;
-    const float px = pts[3 * (size_t)ii], py = pts[3 * (size_t)ii + 1], pz = pts[3 * (size_t)ii + 2];
-    float best = INFINITY, best_sqrt = INFINITY, bb1 = 0.f, bb2 = 0.f;
-    uint32_t best_f = 0;
-    for (uint32_t base = 0; base < n_faces; base += kTile) {
-        const uint32_t cnt = min((uint32_t)kTile, n_faces - base);
-        __syncthreads();
-        const float4* src = reinterpret_cast<const float4*>(tris + base);
-        float4* dst = reinterpret_cast<float4*>(tile);
-        for (uint32_t q = threadIdx.x; q < cnt * 4; q += blockDim.x) dst[q] = __ldg(src + q);
-        __syncthreads();
-        for (uint32_t k = 0; k < cnt; ++k) {
-            const TriRec& t = tile[k];
-            const float dx = px - t.cx, dy = py - t.cy, dz = pz - t.cz;
-            const float dc = sqrtf(dx * dx + dy * dy + dz * dz);
-            if (dc - t.r >= best_sqrt) continue;                       // cannot beat the current best
-            float b1, b2;
-            const float d2 = closest_on_triangle(t, px, py, pz, b1, b2);
-            if (d2 < best) { best = d2; best_sqrt = sqrtf(d2); bb1 = b1; bb2 = b2; best_f = base + k; }
-        }
+    if (i >= n) return;
+    const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
+    const uint32_t n_clusters = (n_faces + kCluster - 1) / kCluster;
+    // 1. nearest cluster sphere -> a tight first bound
+    uint32_t c0 = 0;
+    float lb0 = INFINITY;
+    for (uint32_t c = 0; c < n_clusters; ++c) {
+        const float4 s = __ldg(clusters + c);
+        const float dx = px - s.x, dy = py - s.y, dz = pz - s.z;
+        const float lb = sqrtf(dx * dx + dy * dy + dz * dz) - s.w;
+        if (lb < lb0) { lb0 = lb; c0 = c; }
     }
-    if (!live) return;
+    Best best; best.d2 = INFINITY; best.d = INFINITY; best.b1 = 0.f; best.b2 = 0.f; best.f = 0xFFFFFFFFu;
+    scan_cluster(tris, c0 * kCluster, min(n_faces, (c0 + 1) * kCluster), px, py, pz, best);
+    // 2. every other cluster whose sphere still reaches inside the best distance
+    for (uint32_t c = 0; c < n_clusters; ++c) {
+        if (c == c0) continue;
+        const float4 s = __ldg(clusters + c);
+        const float dx = px - s.x, dy = py - s.y, dz = pz - s.z;
+        if (sqrtf(dx * dx + dy * dy + dz * dz) - s.w > best.d) continue;
+        scan_cluster(tris, c * kCluster, min(n_faces, (c + 1) * kCluster), px, py, pz, best);
+    }
+    const uint32_t best_f = best.f;
+    const float bb1 = best.b1, bb2 = best.b2;
+    const float bestd2 = best.d2;
     const TriRec t = tris[best_f];
     const float b0 = 1.0f - bb1 - bb2;
     // T_interp = sum_k b_k T[v_k]  (utils/ray_utils.py:80), then inverse applied to (p,1), xyz kept un-normalised (:84)
@@ -139,14 +178,14 @@ __global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __r
     const float oy = (c01 * qx + (m00 * m22 - m02 * m20) * qy + (m02 * m10 - m00 * m12) * qz) * id;
     const float oz = (c02 * qx + (m01 * m20 - m00 * m21) * qy + (m00 * m11 - m01 * m10) * qz) * id;
     can_pts[3 * (size_t)i] = ox; can_pts[3 * (size_t)i + 1] = oy; can_pts[3 * (size_t)i + 2] = oz;
-    mask[i] = best < threshold ? 1.0f : 0.0f;
+    mask[i] = bestd2 < threshold ? 1.0f : 0.0f;
     if (closest) {
         closest[3 * (size_t)i] = t.ax + t.abx * bb1 + t.acx * bb2;
         closest[3 * (size_t)i + 1] = t.ay + t.aby * bb1 + t.acy * bb2;
         closest[3 * (size_t)i + 2] = t.az + t.abz * bb1 + t.acz * bb2;
     }
     if (face_id) face_id[i] = (int32_t)best_f;
-    if (dist2_out) dist2_out[i] = best;
+    if (dist2_out) dist2_out[i] = bestd2;
 }
 
 // One warp per ray: near = min_v(z0 - dz), far = max_v(z0 + dz) over the vertex spheres the ray pierces
@@ -197,13 +236,19 @@ __global__ void __launch_bounds__(256) mesh_near_far_kernel(const float* __restr
 
 extern "C" {
 
-uint64_t ac_warp_mesh_bytes(uint32_t n_faces) { return (uint64_t)n_faces * sizeof(TriRec); }
+uint64_t ac_warp_mesh_bytes(uint32_t n_faces) {
+    return (uint64_t)n_faces * sizeof(TriRec) + (uint64_t)((n_faces + kCluster - 1) / kCluster) * sizeof(float4);
+}
 
 int ac_warp_prepare_mesh(const float* verts, const int32_t* faces, uint32_t face_stride, uint32_t n_faces, void* mesh, void* stream) {
     if (!verts || !faces || !mesh || face_stride < 3) return AC_E_INVALID_ARG;
     if (n_faces == 0) return AC_OK;
-    mesh_prepare_kernel<<<(n_faces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts, faces, face_stride, n_faces,
-                                                                                 reinterpret_cast<TriRec*>(mesh));
+    TriRec* tris = reinterpret_cast<TriRec*>(mesh);
+    mesh_prepare_kernel<<<(n_faces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts, faces, face_stride, n_faces, tris);
+    int rc = acb::launched();
+    if (rc) return rc;
+    const uint32_t n_clusters = (n_faces + kCluster - 1) / kCluster;
+    mesh_cluster_kernel<<<(n_clusters + 127) / 128, 128, 0, (cudaStream_t)stream>>>(tris, n_faces, reinterpret_cast<float4*>(tris + n_faces));
     return acb::launched();
 }
 
@@ -211,8 +256,10 @@ int ac_warp_samples_to_canonical(const float* pts, uint32_t n_pts, const void* m
                                  float* can_pts, float* mask, float* closest, int32_t* face_id, float* dist2, void* stream) {
     if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0) return AC_E_INVALID_ARG;
     if (n_pts == 0) return AC_OK;
-    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, reinterpret_cast<const TriRec*>(mesh), n_faces,
-                                                                                   T, threshold, can_pts, mask, closest, face_id, dist2);
+    const TriRec* tris = reinterpret_cast<const TriRec*>(mesh);
+    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, tris, n_faces,
+                                                                                   reinterpret_cast<const float4*>(tris + n_faces), T, threshold,
+                                                                                   can_pts, mask, closest, face_id, dist2);
     return acb::launched();
 }
 

@@ -18,7 +18,19 @@ class PosedMesh:
 
     def __init__(self, verts, faces, Ts, device):
         self.verts = torch.as_tensor(np.asarray(verts), dtype=torch.float32).to(device).contiguous()
-        f = torch.as_tensor(np.asarray(faces)).to(torch.int32).to(device).contiguous()
+        f = torch.as_tensor(np.asarray(faces)).to(torch.int32).to(device)
+        # Sort the triangles along a Morton curve of their centroids so that every 64 consecutive records (one
+        # cluster of the kernel's branch-and-bound search) are spatially compact.  `order` maps sorted -> original ids.
+        cen = self.verts[f[:, :3].long()].mean(1)
+        q = ((cen - cen.min(0)[0]) / (cen.max(0)[0] - cen.min(0)[0] + 1e-12) * 1023.0).long().clamp_(0, 1023)
+
+        def spread(v):                       # 10 bits -> every third bit
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+        self.order = torch.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2))
+        f = f[self.order].contiguous()
         self.faces = f
         T = torch.as_tensor(np.asarray(Ts), dtype=torch.float32)
         if float(T[:, 3, :3].abs().max()) != 0.0:
@@ -54,7 +66,7 @@ def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMe
     dirs = torch.cat([dirs, dirs[:, -1:]], dim=1)
     dirs = dirs / torch.linalg.norm(dirs, dim=2, keepdim=True)
     out = (can, dirs, closest.reshape(R, S, 3), mask.reshape(R, S) > 0.5)
-    return out + (face.reshape(R, S), dist2.reshape(R, S)) if return_query else out
+    return out + (mesh.order[face.long()].to(torch.int32).reshape(R, S), dist2.reshape(R, S)) if return_query else out
 
 
 def geometry_guided_near_far(orig, dir, vert, geo_threshold=DEFAULT_GEO_THRESH, bound=None):
