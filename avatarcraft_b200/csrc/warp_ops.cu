@@ -18,11 +18,11 @@
 
 namespace {
 
-struct __align__(16) TriRec {     // 64 bytes
-    float ax, ay, az, r;          // vertex a, bounding-sphere radius
-    float abx, aby, abz, cx;      // edge b-a, sphere centre x
-    float acx, acy, acz, cy;      // edge c-a, sphere centre y
-    float cz; int32_t i0, i1, i2; // sphere centre z, vertex ids
+struct __align__(16) TriRec {       // 64 bytes = 4 x float4; the bounding sphere comes first so a rejected triangle costs one load
+    float cx, cy, cz, r;            // bounding sphere
+    float ax, ay, az; int32_t i0;   // vertex a, vertex ids
+    float abx, aby, abz; int32_t i1;// edge b-a
+    float acx, acy, acz; int32_t i2;// edge c-a
 };
 
 __global__ void __launch_bounds__(256) mesh_prepare_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces,
@@ -103,12 +103,12 @@ struct Best { float d2, d, b1, b2; uint32_t f; };
 
 __device__ __forceinline__ void scan_cluster(const TriRec* __restrict__ tris, uint32_t lo, uint32_t hi, float px, float py, float pz, Best& best) {
     for (uint32_t k = lo; k < hi; ++k) {
-        const float4 q1 = __ldg(reinterpret_cast<const float4*>(tris + k) + 1);      // (abx, aby, abz, cx)
-        const float4 q2 = __ldg(reinterpret_cast<const float4*>(tris + k) + 2);      // (acx, acy, acz, cy)
-        const float4 q0 = __ldg(reinterpret_cast<const float4*>(tris + k));          // (ax, ay, az, r)
-        const float4 q3 = __ldg(reinterpret_cast<const float4*>(tris + k) + 3);      // (cz, ids)
-        const float dx = px - q1.w, dy = py - q2.w, dz = pz - q3.x;
-        if (sqrtf(dx * dx + dy * dy + dz * dz) - q0.w >= best.d) continue;           // its sphere cannot beat the best
+        const float4 sp = __ldg(reinterpret_cast<const float4*>(tris + k));         // bounding sphere
+        const float dx = px - sp.x, dy = py - sp.y, dz = pz - sp.z;
+        if (sqrtf(dx * dx + dy * dy + dz * dz) - sp.w >= best.d) continue;           // its sphere cannot beat the best
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(tris + k) + 1);
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(tris + k) + 2);
+        const float4 q2 = __ldg(reinterpret_cast<const float4*>(tris + k) + 3);
         TriRec t;
         t.ax = q0.x; t.ay = q0.y; t.az = q0.z; t.abx = q1.x; t.aby = q1.y; t.abz = q1.z; t.acx = q2.x; t.acy = q2.y; t.acz = q2.z;
         float b1, b2;
