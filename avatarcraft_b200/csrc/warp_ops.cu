@@ -5,7 +5,7 @@
 // result goes back to the device, twice per ray batch (models/instant_nsr.py:166-172,198-203).
 // Here: one kernel per point set, no host round trip.  Closest point on the posed mesh is an EXACT
 // branch-and-bound search (Ericson's region test per triangle): triangles arrive sorted along a Morton curve
-// (host side, utils/ray_utils.PosedMesh), every 64 consecutive records form a cluster with a bounding sphere;
+// (host side, utils/ray_utils.PosedMesh), every 16 consecutive records form a cluster with a bounding sphere;
 // a query first scans the cluster whose sphere is nearest, then only the clusters (and, inside them, only the
 // triangles) whose bounding spheres can still beat the current best -- ~5 % of the 13 776 triangles on average.
 // utils/ray_utils.py:277-294 geometry_guided_near_far becomes a warp-per-ray reduction over vertices.
@@ -79,7 +79,7 @@ __device__ __forceinline__ float closest_on_triangle(const TriRec& t, float px, 
     return qx * qx + qy * qy + qz * qz;
 }
 
-constexpr uint32_t kCluster = 64;     // triangles per cluster
+constexpr uint32_t kCluster = 16;     // triangles per cluster (64: 69 ms per 256x256 animate frame)
 
 // One thread per cluster: bounding sphere of the member triangles' bounding spheres.
 __global__ void __launch_bounds__(128) mesh_cluster_kernel(const TriRec* __restrict__ tris, uint32_t n_faces, float4* __restrict__ clusters) {

@@ -102,12 +102,20 @@ def frame_rays(view_index):
     return syn.pinhole_rays(syn.orbit_pose(30.0 + 6.0 * view_index), W_IMG, H_IMG)
 
 
+def cpu_threads():
+    """Threads for the CPU baseline: every core up to 32 -- beyond that the small per-batch GEMMs and the C hash
+    restatement (OpenMP) get slower, not faster (measured on the 128-core GPU box: 128 threads 120 rays/s)."""
+    n = min(os.cpu_count() or 1, 32)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def cpu_oracle_rate(n_rays, repeats=1):
     """rays/s of the oracle port (torch CPU + C hash restatement, all host threads)."""
     import torch
     from avatarcraft_b200.utils import synthetic as syn
     from oracle.nsr_oracle import OracleNSR
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(cpu_threads())
     m = OracleNSR(syn.synthetic_state_dict("trained", 43))
     o, d = frame_rays(0)
     sel = slice(RAYS_PER_FRAME // 2 - n_rays // 2, RAYS_PER_FRAME // 2 + n_rays // 2)   # central rows: rays that hit
@@ -124,7 +132,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = cpu_threads()
     for _ in range(args.warmup):
         cpu_oracle_rate(256)
     t = 0.0
@@ -247,7 +255,7 @@ def run_ours(args):
                          "note": "algorithmic gather bytes (no reuse) per SURVEY.md 8(d); gathers are served from L1/L2, "
                                  "so frac may exceed 1 -- see traffic (ncu dram bytes) and profiles/",
                          "mlp_tflops": tflops, "mlp_frac_of_bf16_peak": tflops / pk["bf16_tflops"]},
-            "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+            "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": cpu_threads(), "kind": "port",
                              "sample": f"{CPU_SAMPLE_RAYS}-ray batch (central rows) of the same frame, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 2 * RAYS_PER_FRAME * 12,
                     "d2h_bytes_per_step": RAYS_PER_FRAME * 12, "ms_per_step": ms_e2e / args.steps,

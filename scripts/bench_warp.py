@@ -22,3 +22,8 @@ for _ in range(5): frame()
 e1.record(); e1.synchronize()
 ms = e0.elapsed_time(e1) / 5
 print(json.dumps({"workload": "render_warp animate frame 256x256, 32+32 samples, 13776-triangle posed mesh", "ms_per_frame": ms, "rays_per_sec": 65536 / ms * 1e3}))
+if "--profile" in sys.argv:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        frame(); torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
