@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("AC_LIB_PATH") or os.path.join(_PKG, "libavatarcraft_b200.so")   # AC_LIB_PATH: tuning variants
-SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu"]
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu", "raymarch_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -86,6 +86,12 @@ _SIGNATURES = {
     "ac_warp_prepare_mesh": (_I, [_V, _V, _U32, _U32, _V, _V]),
     "ac_warp_samples_to_canonical": (_I, [_V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
     "ac_mesh_guided_near_far": (_I, [_V, _V, _U32, _V, _U32, _F, _F, _V, _V]),
+    "ac_march_rays_train": (_I, [_V, _V, _V, _F, _I, _F, _U32, _U32, _U32, _V, _V, _V, _V, _V, _U32, _V]),
+    "ac_composite_rays_train_forward": (_I, [_V, _V, _V, _V, _F, _U32, _U32, _V, _V, _V]),
+    "ac_composite_rays_train_backward": (_I, [_V, _V, _V, _V, _V, _V, _V, _V, _F, _U32, _U32, _V, _V, _V]),
+    "ac_march_rays": (_I, [_U32, _U32, _V, _V, _V, _V, _F, _U32, _V, _F, _V, _V, _V, _V, _V, _U32, _V]),
+    "ac_composite_rays": (_I, [_U32, _U32, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "ac_compact_rays": (_I, [_U32, _V, _V, _V, _V, _V, _V]),
     "ac_nsr_debug_tc_layer": (_I, [_V, _V, _V, _V]),
     "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V, _V, _V]),
 }

@@ -189,6 +189,34 @@ int ac_warp_samples_to_canonical(const float *pts, uint32_t n_pts, const void *m
 int ac_mesh_guided_near_far(const float *rays_o, const float *rays_d, uint32_t n_rays, const float *verts,
                             uint32_t n_verts, float radius, float bound, float *near_far, void *stream);
 
+/* --------------------------------------------------------------------------------------
+ * Occupancy-grid ray marching + compositing: the six ops of the reference's `_raymarching` extension
+ * (raymarching/src/raymarching.h:8-16, bindings.cpp:5-11), same argument order and layouts, fp32:
+ *   march_rays_train              raymarching.cu:56-222   rays [N,3] = (ray id, first sample, #samples), counter [2]
+ *   composite_rays_train_forward  raymarching.cu:232-301  "sigmas" are alphas (NeuS variant)
+ *   composite_rays_train_backward raymarching.cu:315-391
+ *   march_rays / composite_rays / compact_rays            raymarching.cu:497-747 (inference, alive-ray compaction)
+ * Dead code in the reference (nothing imports the module); provided for API completeness.
+ * ------------------------------------------------------------------------------------ */
+int ac_march_rays_train(const float *rays_o, const float *rays_d, const float *grid, float mean_density,
+                        int iter_density, float bound, uint32_t N, uint32_t H, uint32_t M, float *xyzs, float *dirs,
+                        float *deltas, int32_t *rays, int32_t *counter, uint32_t perturb, void *stream);
+int ac_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                    float bound, uint32_t M, uint32_t N, float *weights_sum, float *image, void *stream);
+int ac_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                     const float *rgbs, const float *deltas, const int32_t *rays,
+                                     const float *weights_sum, const float *image, float bound, uint32_t M, uint32_t N,
+                                     float *grad_sigmas, float *grad_rgbs, void *stream);
+int ac_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t, const float *rays_o,
+                  const float *rays_d, float bound, uint32_t H, const float *grid, float mean_density,
+                  const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas, uint32_t perturb,
+                  void *stream);
+int ac_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, float *rays_t, const float *sigmas,
+                      const float *rgbs, const float *normals, const float *deltas, float *weights_sum, float *depth,
+                      float *image, float *normal_map, void *stream);
+int ac_compact_rays(uint32_t n_alive, int32_t *rays_alive, const int32_t *rays_alive_old, float *rays_t,
+                    const float *rays_t_old, int32_t *alive_counter, void *stream);
+
 /* Unit test of the tensor-core layer in isolation: feats [128,32] fp32 x (sdf layer 0 feature
  * columns)^T -> out [128,64] pre-activations WITHOUT bias / xyz terms (3xTF32 tcgen05.mma). */
 int ac_nsr_debug_tc_layer(const float *feats, const float *mlp_blob, float *out, void *stream);

@@ -14,6 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/encoder/hashencoder/src"
+SRC_RM = "/root/reference/raymarching/src"
 OUT = os.path.join(ROOT, "oracle", "_ref")
 
 
@@ -36,5 +37,23 @@ def main():
     print("build_ref: built", target)
 
 
+def build_raymarching():
+    """The reference's raymarching extension (dead code there, but its kernels are the oracle of ours)."""
+    target = os.path.join(OUT, "_ref_raymarching.so")
+    if not os.path.isdir(SRC_RM) or os.path.exists(target):
+        return
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+    load(name="_ref_raymarching", sources=[os.path.join(SRC_RM, "raymarching.cu"), os.path.join(SRC_RM, "bindings.cpp")],
+         extra_cflags=["-O3", "-std=c++17"], extra_cuda_cflags=["-O3", "-std=c++17"], build_directory=OUT, verbose=False,
+         is_python_module=False)
+    for f in os.listdir(OUT):
+        if f.endswith((".o", ".d")) or f in ("lock", "build.ninja", ".ninja_deps", ".ninja_log"):
+            os.remove(os.path.join(OUT, f))
+    print("build_ref: built", target)
+
+
 if __name__ == "__main__":
     main()
+    build_raymarching()
