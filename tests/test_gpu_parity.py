@@ -310,3 +310,21 @@ def test_tensor_core_layer_matches_fp64_matmul():
     err = (out.double().cpu() - ref).abs()
     assert float((err / (scale + 1e-12)).max()) < 2e-6, float((err / (scale + 1e-12)).max())
     assert float(out[0].abs().max()) == 0.0
+
+
+def test_full_frame_psnr_against_reference_gpu_path():
+    """BASELINE config 2 at FULL size against the reference's GPU path run on this box: the reference's own
+    hash-encoder kernel + eager torch for everything else (tests/reference_gpu.py).  north_star gate: PSNR >= 40 dB."""
+    import os
+    from tests.reference_gpu import REF_SO, RefGpuNSR
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    sd = state_dict("trained", 43)
+    o, d = syn.pinhole_rays(syn.orbit_pose(75.0), 256, 256)
+    rgb_r, dep_r, ws_r = RefGpuNSR(sd).render_frame(o.cuda(), d.cuda())
+    out = _render(gpu_model(sd), o, d, 64, 64)
+    rgb, dep, ws = out[3].reshape(-1, 3), out[0].reshape(-1), out[2].reshape(-1)
+    assert psnr(rgb.cpu().numpy(), rgb_r.cpu().numpy()) >= 40.0
+    assert psnr(ws.cpu().numpy(), ws_r.cpu().numpy()) >= 40.0
+    assert float(((rgb - rgb_r).abs().max(1)[0] <= 2e-3).float().mean()) >= 0.97
+    assert float(((dep - dep_r).abs() <= 2e-3).float().mean()) >= 0.97

@@ -104,7 +104,26 @@ def test_composite_rays_train_forward_backward_match_reference_kernel():
     assert torch.allclose(a.grad, ga_r, rtol=0, atol=2e-7 * float(ga_r.abs().max()))      # fma contraction choices
 
 
-@pytest.mark.parametrize("perturb", [0, 3])
+def test_march_rays_perturbed_single_call_matches_reference_kernel():
+    """The inference jitter is seeded by the ALIVE SLOT (raymarching.cu:543), so after the first atomic compaction it is
+    not reproducible even between two runs of the reference; pin it on one call with an identical alive list."""
+    from avatarcraft_b200 import raymarching as rm
+    ref = ref_module()
+    N, n_step = 16384, 8
+    o, d, grid = scene(N)
+    alive = torch.randperm(N, generator=torch.Generator().manual_seed(5)).int().cuda()[: N // 2].contiguous()
+    ts = (0.05 + torch.rand(N // 2, generator=torch.Generator().manual_seed(6))).cuda()
+    near, far = torch.full((N,), 0.05, device="cuda"), torch.full((N,), 4.0, device="cuda")
+    x_m, d_m, t_m = rm.march_rays(N // 2, n_step, alive, ts, o, d, BOUND, grid, 12.0, near, far, perturb=7)
+    M = N // 2 * n_step
+    x_r, d_r, t_r = torch.zeros(M, 3, device="cuda"), torch.zeros(M, 3, device="cuda"), torch.zeros(M, 2, device="cuda")
+    ref.march_rays(N // 2, n_step, alive, ts, o, d, BOUND, H, grid, 12.0, near, far, x_r, d_r, t_r, 7)
+    torch.cuda.synchronize()
+    assert float((t_r[:, 0] > 0).float().mean()) > 0.2
+    assert torch.equal(x_m, x_r) and torch.equal(d_m, d_r) and torch.equal(t_m, t_r)
+
+
+@pytest.mark.parametrize("perturb", [0])
 def test_inference_loop_matches_reference_kernels(perturb):
     """march_rays -> composite_rays -> compact_rays until every ray retires (the reference's run_cuda loop shape)."""
     from avatarcraft_b200 import raymarching as rm
