@@ -5,9 +5,10 @@
 // result goes back to the device, twice per ray batch (models/instant_nsr.py:166-172,198-203).
 // Here: one kernel per point set, no host round trip.  Closest point on the posed mesh is an EXACT
 // branch-and-bound search (Ericson's region test per triangle): triangles arrive sorted along a Morton curve
-// (host side, utils/ray_utils.PosedMesh), every 16 consecutive records form a cluster with a bounding sphere;
-// a query first scans the cluster whose sphere is nearest, then only the clusters (and, inside them, only the
-// triangles) whose bounding spheres can still beat the current best -- ~5 % of the 13 776 triangles on average.
+// (host side, utils/ray_utils.PosedMesh); 16 consecutive records form a leaf box, 8 leaves a 128-triangle box,
+// 8 of those a 1024-triangle box (an implicit 3-level AABB tree rebuilt per pose in 3 tiny launches).  A query
+// descends greedily to the nearest leaf for a first bound, then visits only the boxes (and, inside a leaf, only
+// the triangles, by their bounding spheres) that can still beat or tie the current best.
 // utils/ray_utils.py:277-294 geometry_guided_near_far becomes a warp-per-ray reduction over vertices.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -79,24 +80,67 @@ __device__ __forceinline__ float closest_on_triangle(const TriRec& t, float px, 
     return qx * qx + qy * qy + qz * qz;
 }
 
-constexpr uint32_t kCluster = 16;     // triangles per cluster (64: 69 ms per 256x256 animate frame)
+constexpr uint32_t kCluster = 16;     // triangles per leaf box (64: 69 ms per 256x256 animate frame with a flat list)
+constexpr uint32_t kFan = 8;          // children per inner box: leaves -> 128-triangle boxes -> 1024-triangle boxes
 
-// One thread per cluster: bounding sphere of the member triangles' bounding spheres.
-__global__ void __launch_bounds__(128) mesh_cluster_kernel(const TriRec* __restrict__ tris, uint32_t n_faces, float4* __restrict__ clusters) {
+struct __align__(16) Box { float lx, ly, lz, pad0, hx, hy, hz, pad1; };   // 32 bytes = 2 x float4
+
+struct MeshView {                     // layout of the caller's `mesh` buffer (ac_warp_mesh_bytes)
+    const TriRec* tris; const Box* l0; const Box* l1; const Box* l2;
+    uint32_t n_faces, n0, n1, n2;
+};
+__host__ __device__ inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+__host__ inline MeshView mesh_view(const void* mesh, uint32_t n_faces) {
+    MeshView m;
+    m.n_faces = n_faces; m.n0 = ceil_div(n_faces, kCluster); m.n1 = ceil_div(m.n0, kFan); m.n2 = ceil_div(m.n1, kFan);
+    m.tris = reinterpret_cast<const TriRec*>(mesh);
+    m.l0 = reinterpret_cast<const Box*>(m.tris + n_faces); m.l1 = m.l0 + m.n0; m.l2 = m.l1 + m.n1;
+    return m;
+}
+
+// Leaf boxes: one thread per 16 consecutive (Morton-ordered) triangles.  Padded so that the triangle as the
+// query evaluates it (a, a+ab, a+ac with rounded edges) is inside.
+__global__ void __launch_bounds__(128) mesh_leaf_box_kernel(const TriRec* __restrict__ tris, uint32_t n_faces, Box* __restrict__ out) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lo = c * kCluster;
     if (lo >= n_faces) return;
     const uint32_t hi = min(n_faces, lo + kCluster);
-    float mx = 0.f, my = 0.f, mz = 0.f;
-    for (uint32_t t = lo; t < hi; ++t) { mx += tris[t].cx; my += tris[t].cy; mz += tris[t].cz; }
-    const float inv = 1.0f / (float)(hi - lo);
-    mx *= inv; my *= inv; mz *= inv;
-    float R = 0.f;
-    for (uint32_t t = lo; t < hi; ++t) {
-        const float dx = tris[t].cx - mx, dy = tris[t].cy - my, dz = tris[t].cz - mz;
-        R = fmaxf(R, sqrtf(dx * dx + dy * dy + dz * dz) + tris[t].r);
+    float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t k = lo; k < hi; ++k) {
+        const TriRec t = tris[k];
+        const float v[3][3] = {{t.ax, t.ay, t.az}, {t.ax + t.abx, t.ay + t.aby, t.az + t.abz}, {t.ax + t.acx, t.ay + t.acy, t.az + t.acz}};
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { l[d] = fminf(l[d], v[q][d]); h[d] = fmaxf(h[d], v[q][d]); }
     }
-    clusters[c] = make_float4(mx, my, mz, R * 1.0001f + 1e-7f);
+    Box b;
+    const float pad = 1e-6f + 1e-5f * fmaxf(h[0] - l[0], fmaxf(h[1] - l[1], h[2] - l[2]));
+    b.lx = l[0] - pad; b.ly = l[1] - pad; b.lz = l[2] - pad; b.hx = h[0] + pad; b.hy = h[1] + pad; b.hz = h[2] + pad;
+    b.pad0 = b.pad1 = 0.f;
+    out[c] = b;
+}
+// Inner boxes: union of kFan children.
+__global__ void __launch_bounds__(128) mesh_inner_box_kernel(const Box* __restrict__ child, uint32_t n_child, Box* __restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = c * kFan;
+    if (lo >= n_child) return;
+    const uint32_t hi = min(n_child, lo + kFan);
+    Box b = child[lo];
+    for (uint32_t k = lo + 1; k < hi; ++k) {
+        const Box o = child[k];
+        b.lx = fminf(b.lx, o.lx); b.ly = fminf(b.ly, o.ly); b.lz = fminf(b.lz, o.lz);
+        b.hx = fmaxf(b.hx, o.hx); b.hy = fmaxf(b.hy, o.hy); b.hz = fmaxf(b.hz, o.hz);
+    }
+    out[c] = b;
+}
+
+// Squared distance from p to a box (0 inside): a lower bound of the squared distance to anything in it.
+__device__ __forceinline__ float box_dist2(const Box* __restrict__ b, float px, float py, float pz) {
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(b)), hi = __ldg(reinterpret_cast<const float4*>(b) + 1);
+    const float dx = fmaxf(fmaxf(lo.x - px, px - hi.x), 0.f), dy = fmaxf(fmaxf(lo.y - py, py - hi.y), 0.f),
+                dz = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
 }
 
 struct Best { float d2, d, b1, b2; uint32_t f; };
@@ -117,10 +161,20 @@ __device__ __forceinline__ void scan_cluster(const TriRec* __restrict__ tris, ui
     }
 }
 
+// index of the child box in [lo,hi) nearest to p
+__device__ __forceinline__ uint32_t nearest_box(const Box* __restrict__ b, uint32_t lo, uint32_t hi, float px, float py, float pz) {
+    uint32_t arg = lo;
+    float m = INFINITY;
+    for (uint32_t k = lo; k < hi; ++k) {
+        const float d = box_dist2(b + k, px, py, pz);
+        if (d < m) { m = d; arg = k; }
+    }
+    return arg;
+}
+
 // pts [n,3] -> can_pts [n,3], mask [n] (dist^2 < threshold), optional closest [n,3], face_id [n], dist2 [n].
 // T [n_T,4,4] row-major per-vertex transforms whose last row is (0,0,0,c).
-__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, uint32_t n, const TriRec* __restrict__ tris,
-                                                                uint32_t n_faces, const float4* __restrict__ clusters,
+__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, uint32_t n, const MeshView m,
                                                                 const float* __restrict__ T, float threshold,
                                                                 float* __restrict__ can_pts, float* __restrict__ mask,
                                                                 float* __restrict__ closest, int32_t* __restrict__ face_id,
@@ -128,25 +182,26 @@ __global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __r
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
-    const uint32_t n_clusters = (n_faces + kCluster - 1) / kCluster;
-    // 1. nearest cluster sphere -> a tight first bound
-    uint32_t c0 = 0;
-    float lb0 = INFINITY;
-    for (uint32_t c = 0; c < n_clusters; ++c) {
-        const float4 s = __ldg(clusters + c);
-        const float dx = px - s.x, dy = py - s.y, dz = pz - s.z;
-        const float lb = sqrtf(dx * dx + dy * dy + dz * dz) - s.w;
-        if (lb < lb0) { lb0 = lb; c0 = c; }
-    }
+    const TriRec* __restrict__ tris = m.tris;
+    const uint32_t n_faces = m.n_faces;
+    // 1. greedy descent to the nearest leaf box -> a tight first bound
+    const uint32_t s0 = nearest_box(m.l2, 0, m.n2, px, py, pz);
+    const uint32_t g0 = nearest_box(m.l1, s0 * kFan, min(m.n1, (s0 + 1) * kFan), px, py, pz);
+    const uint32_t c0 = nearest_box(m.l0, g0 * kFan, min(m.n0, (g0 + 1) * kFan), px, py, pz);
     Best best; best.d2 = INFINITY; best.d = INFINITY; best.b1 = 0.f; best.b2 = 0.f; best.f = 0xFFFFFFFFu;
     scan_cluster(tris, c0 * kCluster, min(n_faces, (c0 + 1) * kCluster), px, py, pz, best);
-    // 2. every other cluster whose sphere still reaches inside the best distance
-    for (uint32_t c = 0; c < n_clusters; ++c) {
-        if (c == c0) continue;
-        const float4 s = __ldg(clusters + c);
-        const float dx = px - s.x, dy = py - s.y, dz = pz - s.z;
-        if (sqrtf(dx * dx + dy * dy + dz * dz) - s.w > best.d) continue;
-        scan_cluster(tris, c * kCluster, min(n_faces, (c + 1) * kCluster), px, py, pz, best);
+    // 2. exact branch and bound: every box that can still hold a closer (or equally close) triangle
+    for (uint32_t s = 0; s < m.n2; ++s) {
+        if (box_dist2(m.l2 + s, px, py, pz) > best.d2) continue;
+        const uint32_t g_hi = min(m.n1, (s + 1) * kFan);
+        for (uint32_t g = s * kFan; g < g_hi; ++g) {
+            if (box_dist2(m.l1 + g, px, py, pz) > best.d2) continue;
+            const uint32_t c_hi = min(m.n0, (g + 1) * kFan);
+            for (uint32_t c = g * kFan; c < c_hi; ++c) {
+                if (c == c0 || box_dist2(m.l0 + c, px, py, pz) > best.d2) continue;
+                scan_cluster(tris, c * kCluster, min(n_faces, (c + 1) * kCluster), px, py, pz, best);
+            }
+        }
     }
     const uint32_t best_f = best.f;
     const float bb1 = best.b1, bb2 = best.b2;
@@ -237,7 +292,8 @@ __global__ void __launch_bounds__(256) mesh_near_far_kernel(const float* __restr
 extern "C" {
 
 uint64_t ac_warp_mesh_bytes(uint32_t n_faces) {
-    return (uint64_t)n_faces * sizeof(TriRec) + (uint64_t)((n_faces + kCluster - 1) / kCluster) * sizeof(float4);
+    const MeshView m = mesh_view(nullptr, n_faces);
+    return (uint64_t)n_faces * sizeof(TriRec) + (uint64_t)(m.n0 + m.n1 + m.n2) * sizeof(Box);
 }
 
 int ac_warp_prepare_mesh(const float* verts, const int32_t* faces, uint32_t face_stride, uint32_t n_faces, void* mesh, void* stream) {
@@ -247,8 +303,12 @@ int ac_warp_prepare_mesh(const float* verts, const int32_t* faces, uint32_t face
     mesh_prepare_kernel<<<(n_faces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts, faces, face_stride, n_faces, tris);
     int rc = acb::launched();
     if (rc) return rc;
-    const uint32_t n_clusters = (n_faces + kCluster - 1) / kCluster;
-    mesh_cluster_kernel<<<(n_clusters + 127) / 128, 128, 0, (cudaStream_t)stream>>>(tris, n_faces, reinterpret_cast<float4*>(tris + n_faces));
+    const MeshView m = mesh_view(mesh, n_faces);
+    mesh_leaf_box_kernel<<<(m.n0 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(tris, n_faces, const_cast<Box*>(m.l0));
+    if ((rc = acb::launched())) return rc;
+    mesh_inner_box_kernel<<<(m.n1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m.l0, m.n0, const_cast<Box*>(m.l1));
+    if ((rc = acb::launched())) return rc;
+    mesh_inner_box_kernel<<<(m.n2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m.l1, m.n1, const_cast<Box*>(m.l2));
     return acb::launched();
 }
 
@@ -256,10 +316,8 @@ int ac_warp_samples_to_canonical(const float* pts, uint32_t n_pts, const void* m
                                  float* can_pts, float* mask, float* closest, int32_t* face_id, float* dist2, void* stream) {
     if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0) return AC_E_INVALID_ARG;
     if (n_pts == 0) return AC_OK;
-    const TriRec* tris = reinterpret_cast<const TriRec*>(mesh);
-    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, tris, n_faces,
-                                                                                   reinterpret_cast<const float4*>(tris + n_faces), T, threshold,
-                                                                                   can_pts, mask, closest, face_id, dist2);
+    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, mesh_view(mesh, n_faces), T, threshold, can_pts,
+                                                                                   mask, closest, face_id, dist2);
     return acb::launched();
 }
 
