@@ -85,6 +85,8 @@ _SIGNATURES = {
     "ac_warp_mesh_bytes": (ctypes.c_uint64, [_U32]),
     "ac_warp_prepare_mesh": (_I, [_V, _V, _U32, _U32, _V, _V]),
     "ac_warp_samples_to_canonical": (_I, [_V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
+    "ac_warp_samples_to_canonical_ordered": (_I, [_V, _V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
+    "ac_warp_query_keys": (_I, [_V, _U32, _V, _U32, _F, _V, _V]),
     "ac_mesh_guided_near_far": (_I, [_V, _V, _U32, _V, _U32, _F, _F, _V, _V]),
     "ac_march_rays_train": (_I, [_V, _V, _V, _F, _I, _F, _U32, _U32, _U32, _V, _V, _V, _V, _V, _U32, _V]),
     "ac_composite_rays_train_forward": (_I, [_V, _V, _V, _V, _F, _U32, _U32, _V, _V, _V]),

@@ -143,13 +143,39 @@ __device__ __forceinline__ float box_dist2(const Box* __restrict__ b, float px, 
     return dx * dx + dy * dy + dz * dz;
 }
 
+// 30-bit Morton key of a query point inside the mesh's bounding box grown by `margin` (clamped outside): sorting
+// the queries by it puts 32 spatially adjacent points in a warp.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u;
+    return (v | (v << 2)) & 0x09249249u;
+}
+__global__ void __launch_bounds__(256) query_keys_kernel(const float* __restrict__ pts, uint32_t n, const MeshView m, float margin,
+                                                         int32_t* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t s = 0; s < m.n2; ++s) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(m.l2 + s)), hi = __ldg(reinterpret_cast<const float4*>(m.l2 + s) + 1);
+        l[0] = fminf(l[0], lo.x); l[1] = fminf(l[1], lo.y); l[2] = fminf(l[2], lo.z);
+        h[0] = fmaxf(h[0], hi.x); h[1] = fmaxf(h[1], hi.y); h[2] = fmaxf(h[2], hi.z);
+    }
+    uint32_t q[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float u = (pts[3 * (size_t)i + d] - (l[d] - margin)) / (h[d] - l[d] + 2.f * margin);
+        q[d] = (uint32_t)fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+    }
+    keys[i] = (int32_t)(spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2));
+}
+
 struct Best { float d2, d, b1, b2; uint32_t f; };
 
 __device__ __forceinline__ void scan_cluster(const TriRec* __restrict__ tris, uint32_t lo, uint32_t hi, float px, float py, float pz, Best& best) {
     for (uint32_t k = lo; k < hi; ++k) {
         const float4 sp = __ldg(reinterpret_cast<const float4*>(tris + k));         // bounding sphere
         const float dx = px - sp.x, dy = py - sp.y, dz = pz - sp.z;
-        if (sqrtf(dx * dx + dy * dy + dz * dz) - sp.w >= best.d) continue;           // its sphere cannot beat the best
+        const float reach = best.d + sp.w;                                           // |p-c| - r >= best  <=>  |p-c|^2 >= (best+r)^2
+        if (dx * dx + dy * dy + dz * dz >= reach * reach) continue;                  // its sphere cannot beat the best
         const float4 q0 = __ldg(reinterpret_cast<const float4*>(tris + k) + 1);
         const float4 q1 = __ldg(reinterpret_cast<const float4*>(tris + k) + 2);
         const float4 q2 = __ldg(reinterpret_cast<const float4*>(tris + k) + 3);
@@ -174,13 +200,14 @@ __device__ __forceinline__ uint32_t nearest_box(const Box* __restrict__ b, uint3
 
 // pts [n,3] -> can_pts [n,3], mask [n] (dist^2 < threshold), optional closest [n,3], face_id [n], dist2 [n].
 // T [n_T,4,4] row-major per-vertex transforms whose last row is (0,0,0,c).
-__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, uint32_t n, const MeshView m,
-                                                                const float* __restrict__ T, float threshold,
+__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, const int32_t* __restrict__ order, uint32_t n,
+                                                                const MeshView m, const float* __restrict__ T, float threshold,
                                                                 float* __restrict__ can_pts, float* __restrict__ mask,
                                                                 float* __restrict__ closest, int32_t* __restrict__ face_id,
                                                                 float* __restrict__ dist2_out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const uint32_t i = order ? (uint32_t)order[slot] : slot;      // spatially sorted queries keep a warp on the same boxes
     const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
     const TriRec* __restrict__ tris = m.tris;
     const uint32_t n_faces = m.n_faces;
@@ -312,12 +339,25 @@ int ac_warp_prepare_mesh(const float* verts, const int32_t* faces, uint32_t face
     return acb::launched();
 }
 
-int ac_warp_samples_to_canonical(const float* pts, uint32_t n_pts, const void* mesh, uint32_t n_faces, const float* T, float threshold,
-                                 float* can_pts, float* mask, float* closest, int32_t* face_id, float* dist2, void* stream) {
+int ac_warp_samples_to_canonical_ordered(const float* pts, const int32_t* order, uint32_t n_pts, const void* mesh, uint32_t n_faces,
+                                         const float* T, float threshold, float* can_pts, float* mask, float* closest, int32_t* face_id,
+                                         float* dist2, void* stream) {
     if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0) return AC_E_INVALID_ARG;
     if (n_pts == 0) return AC_OK;
-    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, mesh_view(mesh, n_faces), T, threshold, can_pts,
-                                                                                   mask, closest, face_id, dist2);
+    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, order, n_pts, mesh_view(mesh, n_faces), T, threshold,
+                                                                                   can_pts, mask, closest, face_id, dist2);
+    return acb::launched();
+}
+
+int ac_warp_samples_to_canonical(const float* pts, uint32_t n_pts, const void* mesh, uint32_t n_faces, const float* T, float threshold,
+                                 float* can_pts, float* mask, float* closest, int32_t* face_id, float* dist2, void* stream) {
+    return ac_warp_samples_to_canonical_ordered(pts, nullptr, n_pts, mesh, n_faces, T, threshold, can_pts, mask, closest, face_id, dist2, stream);
+}
+
+int ac_warp_query_keys(const float* pts, uint32_t n_pts, const void* mesh, uint32_t n_faces, float margin, int32_t* keys, void* stream) {
+    if (!pts || !mesh || !keys || n_faces == 0) return AC_E_INVALID_ARG;
+    if (n_pts == 0) return AC_OK;
+    query_keys_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_pts, mesh_view(mesh, n_faces), margin, keys);
     return acb::launched();
 }
 

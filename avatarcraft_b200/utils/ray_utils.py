@@ -12,6 +12,9 @@ from .. import _lib
 from .constant import DEFAULT_GEO_THRESH
 
 
+SORT_QUERIES_FROM = 1 << 14     # below this the sort costs more than the divergence it removes
+
+
 class PosedMesh:
     """Per-frame device copy of the posed SMPL surface: vertices, faces, per-vertex transforms and the
     64-byte triangle records (vertex, two edges, bounding sphere, ids) the warp kernel walks."""
@@ -57,9 +60,17 @@ def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMe
     closest = torch.empty_like(flat)
     face = torch.empty(n, dtype=torch.int32, device=flat.device) if return_query else None
     dist2 = torch.empty(n, device=flat.device) if return_query else None
-    _lib.check(_lib.lib().ac_warp_samples_to_canonical(_lib.ptr(flat), n, _lib.ptr(mesh.records), mesh.n_faces, _lib.ptr(mesh.Ts),
-                                                       float(threshold), _lib.ptr(can), _lib.ptr(mask), _lib.ptr(closest),
-                                                       _lib.ptr(face), _lib.ptr(dist2), _lib.stream_ptr()),
+    order = None
+    if n >= SORT_QUERIES_FROM:
+        # Visit the queries along a Morton curve: a warp's 32 points then share boxes and triangles (11.7 -> ~30 active
+        # lanes per instruction in the search); results land at the original indices.
+        keys = torch.empty(n, dtype=torch.int32, device=flat.device)
+        _lib.check(_lib.lib().ac_warp_query_keys(_lib.ptr(flat), n, _lib.ptr(mesh.records), mesh.n_faces, 0.25, _lib.ptr(keys),
+                                                 _lib.stream_ptr()), "ac_warp_query_keys")
+        order = torch.sort(keys)[1].to(torch.int32)
+    _lib.check(_lib.lib().ac_warp_samples_to_canonical_ordered(_lib.ptr(flat), _lib.ptr(order), n, _lib.ptr(mesh.records), mesh.n_faces,
+                                                               _lib.ptr(mesh.Ts), float(threshold), _lib.ptr(can), _lib.ptr(mask),
+                                                               _lib.ptr(closest), _lib.ptr(face), _lib.ptr(dist2), _lib.stream_ptr()),
                "ac_warp_samples_to_canonical")
     can = can.reshape(R, S, 3)
     dirs = can[:, 1:] - can[:, :-1]

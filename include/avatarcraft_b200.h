@@ -186,6 +186,14 @@ int ac_warp_prepare_mesh(const float *verts, const int32_t *faces, uint32_t face
 int ac_warp_samples_to_canonical(const float *pts, uint32_t n_pts, const void *mesh, uint32_t n_faces,
                                  const float *T, float threshold, float *can_pts, float *mask,
                                  float *closest, int32_t *face_id, float *dist2, void *stream);
+/* Same query with the points visited in the caller's `order` (a permutation of 0..n-1, or NULL): results are
+ * written at the original indices.  ac_warp_query_keys gives 30-bit Morton keys (inside the mesh's bounding box
+ * grown by `margin`) whose argsort is the order that keeps the 32 queries of a warp spatially adjacent. */
+int ac_warp_samples_to_canonical_ordered(const float *pts, const int32_t *order, uint32_t n_pts, const void *mesh,
+                                         uint32_t n_faces, const float *T, float threshold, float *can_pts,
+                                         float *mask, float *closest, int32_t *face_id, float *dist2, void *stream);
+int ac_warp_query_keys(const float *pts, uint32_t n_pts, const void *mesh, uint32_t n_faces, float margin,
+                       int32_t *keys, void *stream);
 int ac_mesh_guided_near_far(const float *rays_o, const float *rays_d, uint32_t n_rays, const float *verts,
                             uint32_t n_verts, float radius, float bound, float *near_far, void *stream);
 

@@ -46,6 +46,25 @@ def test_warp_samples_to_canonical_against_float64_oracle(body):
     assert dirs.shape == (64, 32, 3) and torch.isfinite(dirs[mask]).all()
 
 
+def test_morton_ordered_queries_equal_plain_order(body):
+    """The search is exact, so visiting the queries in Morton order (large batches) must not change a single result."""
+    from avatarcraft_b200.utils import ray_utils as ru
+    gen = torch.Generator().manual_seed(12)
+    v = torch.from_numpy(np.asarray(body["world_verts"], np.float32))
+    pts = (v[torch.randint(0, 6890, (40000,), generator=gen)] + torch.randn(40000, 3, generator=gen) * 0.15).reshape(1250, 32, 3).cuda()
+    mesh = ru.PosedMesh(body["world_verts"], body["faces"], body["Ts"], "cuda")
+    assert pts.shape[0] * pts.shape[1] >= ru.SORT_QUERIES_FROM
+    a = ru.warp_samples_to_canonical(pts, None, None, None, 0.05, mesh=mesh, return_query=True)
+    old, ru.SORT_QUERIES_FROM = ru.SORT_QUERIES_FROM, 1 << 40
+    try:
+        b = ru.warp_samples_to_canonical(pts, None, None, None, 0.05, mesh=mesh, return_query=True)
+    finally:
+        ru.SORT_QUERIES_FROM = old
+    for x, y in zip(a, b):
+        assert torch.equal(x, y) or (torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+    assert 0.2 < float(a[3].float().mean()) < 1.0
+
+
 def test_mesh_guided_near_far_against_oracle(body):
     from avatarcraft_b200.utils.ray_utils import geometry_guided_near_far
     o, d = syn.pinhole_rays(syn.orbit_pose(10.0), 64, 64)
