@@ -407,3 +407,54 @@ class NeRFNetwork(NeRFRenderer):
 
     def gradient(self, x, bound, epsilon=0.0005):
         return self.finite_difference_normals_approximator(x, bound, epsilon)
+
+    # ---- mesh export (reference: extract_fields / extract_geometry :706-764) -------------------------------------
+    @torch.no_grad()
+    def extract_fields(self, bound, resolution, slab=32):
+        """SDF on the `resolution`^3 lattice of [-bound, bound]^3 as a device tensor u[xi, yi, zi] -- the reference
+        chunks 256^3 blocks through eager torch and copies each to the host (:706-731); here lattice points are
+        generated on the device (ac_sdf_grid_points) and evaluated by the fused SDF query, slab by slab."""
+        import numpy as np
+        dev = self.encoder.embeddings.device
+        lo = np.array([-bound] * 3, dtype=np.float32); hi = np.array([bound] * 3, dtype=np.float32)
+        u = torch.empty(resolution, resolution, resolution, device=dev, dtype=torch.float32)
+        m = self._device_model()
+        L = _lib.lib()
+        for i0 in range(0, resolution, slab):
+            ni = min(slab, resolution - i0)
+            n = ni * resolution * resolution
+            pts = torch.empty(n, 3, device=dev); out = torch.empty(n, 16, device=dev)
+            _lib.check(L.ac_sdf_grid_points(lo.ctypes.data_as(ctypes.c_void_p), hi.ctypes.data_as(ctypes.c_void_p), resolution, i0, ni,
+                                            _lib.ptr(pts), _lib.stream_ptr()), "ac_sdf_grid_points")
+            _lib.check(L.ac_nsr_forward_sdf(ctypes.byref(m), _lib.ptr(pts), _lib.ptr(out), n, float(bound), _lib.stream_ptr()),
+                       "ac_nsr_forward_sdf")
+            u[i0:i0 + ni] = out[:, 0].reshape(ni, resolution, resolution)
+        return u
+
+    @torch.no_grad()
+    def extract_geometry(self, bound: float, resolution: int, threshold: float = 0.0, device=None):
+        """vertices [V,3] (world units), triangles [F,3] as numpy arrays, like the reference (:733-764).  The iso-surface
+        {sdf = threshold} is extracted on the device by marching tetrahedra (ac_iso_surface) and welded by lattice-edge
+        key; the reference calls PyMCubes on the host (not part of this image) -- same surface, different tessellation."""
+        import numpy as np
+        u = self.extract_fields(bound, resolution)
+        dev = u.device
+        lo = np.array([-bound] * 3, dtype=np.float32); hi = np.array([bound] * 3, dtype=np.float32)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        L = _lib.lib()
+
+        def run(cap, pos, key):
+            counter.zero_()
+            _lib.check(L.ac_iso_surface(_lib.ptr(u), lo.ctypes.data_as(ctypes.c_void_p), hi.ctypes.data_as(ctypes.c_void_p), resolution,
+                                        float(threshold), None if pos is None else _lib.ptr(pos), None if key is None else _lib.ptr(key),
+                                        cap, _lib.ptr(counter), _lib.stream_ptr()), "ac_iso_surface")
+            return int(counter.item())
+        n_tri = run(0, None, None)                                   # pass 1: count
+        if n_tri == 0:
+            return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int64)
+        pos = torch.empty(n_tri, 3, 3, device=dev); key = torch.empty(n_tri, 3, dtype=torch.int64, device=dev)
+        run(n_tri, pos, key)                                         # pass 2: emit
+        uniq, inv = torch.unique(key.reshape(-1), return_inverse=True)
+        verts = torch.empty(uniq.numel(), 3, device=dev)
+        verts[inv] = pos.reshape(-1, 3)                              # identical bits for every copy of a welded vertex
+        return verts.cpu().numpy(), inv.reshape(-1, 3).cpu().numpy()

@@ -34,6 +34,23 @@ def select_background(shape, key) -> torch.Tensor:
     return img.reshape(-1, 1).expand(side * side, 3).contiguous()
 
 
+def select_background_device(n_rays, key, device, seed=None, sigma=None) -> torch.Tensor:
+    """select_background on the device (one kernel, no host tensor, no H2D): [n_rays,3].  The noise background uses a
+    counter-based generator keyed by `seed` (drawn from torch's generator when None); the chessboard blur width
+    `sigma` is drawn U(0.1, 2.0) per call like torchvision's GaussianBlur when None."""
+    from .. import _lib
+    key = key % 4
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if key == NOISE_BKG else 0
+    if sigma is None:
+        sigma = float(torch.empty(1).uniform_(0.1, 2.0).item()) if key == CHESSBOARD_BKG else 1.0
+    out = torch.empty(n_rays, 3, device=device, dtype=torch.float32)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().ac_select_background(int(key), int(n_rays), int(seed), float(sigma), _lib.ptr(out), _lib.stream_ptr()),
+                   "ac_select_background")
+    return out
+
+
 def render_instantnsr_naive(net, rays_o, rays_d, rays_per_batch=6400, requires_grad=False, return_torch=True,
                             bkg_key: int = WHITE_BKG, render_can: bool = False, perturb: bool = True,
                             return_raw: bool = False, verts=None, faces=None, Ts=None, num_steps: int = 64,
@@ -48,8 +65,8 @@ def render_instantnsr_naive(net, rays_o, rays_d, rays_per_batch=6400, requires_g
     elif key == BLACK_BKG:
         bg = torch.zeros(total, 3, device=device)
     else:                                                           # generated per batch, like the reference
-        bg = torch.cat([select_background(rays_o[i:i + rays_per_batch].shape, bkg_key)
-                        for i in range(0, total, rays_per_batch)]).to(device)
+        bg = torch.cat([select_background_device(min(rays_per_batch, total - i), bkg_key, device)
+                        for i in range(0, total, rays_per_batch)])
     with torch.set_grad_enabled(requires_grad):
         if requires_grad and total > rays_per_batch:
             raise NotImplementedError("requires_grad=True renders one patch per call (as stylize.py:153-158 does)")

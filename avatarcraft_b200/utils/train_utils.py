@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from .constant import NSR_BOUND, WHITE_BKG
 from .distributed import allreduce_gradients, shard_patches
+from .optim import FlatAdam
 from .render_utils import render_instantnsr_naive
 
 
@@ -41,6 +42,10 @@ def stylize_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad,
             loss = loss + op * scale
             stats["opacity"].append(op.detach())
         loss.backward()
-    allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]])
-    optimizer.step()
+    if isinstance(optimizer, FlatAdam):            # flat buffers: ONE in-place all-reduce + ONE update launch
+        optimizer.all_reduce()
+        optimizer.step()
+    else:
+        allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]])
+        optimizer.step()
     return {k: (torch.stack(v).mean() if v else None) for k, v in stats.items()}

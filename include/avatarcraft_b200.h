@@ -225,6 +225,46 @@ int ac_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_ali
 int ac_compact_rays(uint32_t n_alive, int32_t *rays_alive, const int32_t *rays_alive_old, float *rays_t,
                     const float *rays_t_old, int32_t *alive_counter, void *stream);
 
+/* --------------------------------------------------------------------------------------
+ * The stages either side of the render core.
+ * ac_gen_rays: per-pixel rays generated on the device, row-major [H*W,3] float32.
+ *   c2w: HOST pointer to the 4x4 row-major float64 camera-to-world matrix (read at call time, passed by value).
+ *   Pixel coordinate of column i is x0 + x_step*i, of row j is y0 + y_step*j.
+ *   convention 0 = cap2rays / shot_rays (utils/render_utils.py:363-376, utils/ray_utils.py:25-37):
+ *     float64 back-projection of (x, y, 1) through K^-1 and c2w, float32 world point minus the float32 camera
+ *     centre, normalised;
+ *   convention 1 = SMPLDataset.gen_rays_pose (utils/SMPLDataset.py:86-103): float32 p = ((x-cx)/fx, -(y-cy)/fy, -1)
+ *     normalised and rotated by the pose.
+ * ac_select_background = select_background (utils/render_utils.py:953-987), out [n_rays,3]:
+ *   key%4: 0 white, 1 black, 2 gaussian grey N(0.5,0.1) clamped (counter-based generator keyed by `seed`; the
+ *   reference draws from torch's CPU generator, so only the distribution is comparable), 3 chessboard (0.8/0.2,
+ *   squares of side/10 pixels, n_rays must be a square) blurred with torchvision's GaussianBlur((5,9)) at `sigma`
+ *   (the reference draws sigma ~ U(0.1, 2.0) per call; the caller draws it here).
+ * ac_adam_step = torch.optim.Adam(lr, betas, eps; no weight decay, no amsgrad) (stylize.py:355-363) on one flat
+ *   fp32 buffer of n elements (16 B aligned pointers), `step` >= 1 the 1-based step count, gradients multiplied by
+ *   grad_scale first.  Entries whose gradient and both moments are zero are left untouched (their update is 0).
+ * ac_sdf_grid_points: the lattice of extract_fields (models/instant_nsr.py:706-731) for slabs [i0, i0+ni) of the
+ *   slowest axis: pts [(ni*res*res),3], index (i*res+j)*res+k <-> (X[i],Y[j],Z[k]), X = linspace(min, max, res).
+ *   bound_min / bound_max are HOST pointers to 3 floats.  Feed pts to ac_nsr_forward_sdf.
+ * ------------------------------------------------------------------------------------ */
+int ac_gen_rays(const double *c2w, double fx, double fy, double cx, double cy, uint32_t W, uint32_t H, double x0,
+                double x_step, double y0, double y_step, int convention, float *rays_o, float *rays_d, void *stream);
+int ac_select_background(int key, uint32_t n_rays, uint64_t seed, float sigma, float *out, void *stream);
+int ac_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr, float beta1,
+                 float beta2, float eps, uint32_t step, float grad_scale, void *stream);
+int ac_sdf_grid_points(const float *bound_min, const float *bound_max, uint32_t resolution, uint32_t i0, uint32_t ni,
+                       float *pts, void *stream);
+/* Iso-surface of a [res,res,res] lattice volume (index (i*res+j)*res+k) at `threshold` by marching tetrahedra --
+ * stands in for mcubes.marching_cubes in extract_geometry (models/instant_nsr.py:733-752; PyMCubes is not in the
+ * image).  Appends triangles through *counter (device uint64, caller zeroes): tri_pos [capacity,3,3] world positions,
+ * tri_key [capacity,3] = (lower lattice id << 32 | higher lattice id) of the edge each vertex lies on (the caller
+ * welds vertices by key).  *counter ends at the number of triangles FOUND; when it exceeds `capacity` only the first
+ * `capacity` were stored -- re-run with room (capacity 0 = count only).  Triangle normals point towards increasing
+ * field value.  bound_min / bound_max: HOST pointers to 3 floats. */
+int ac_iso_surface(const float *volume, const float *bound_min, const float *bound_max, uint32_t resolution,
+                   float threshold, float *tri_pos, int64_t *tri_key, uint64_t capacity, uint64_t *counter,
+                   void *stream);
+
 /* Unit test of the tensor-core layer in isolation: feats [128,32] fp32 x (sdf layer 0 feature
  * columns)^T -> out [128,64] pre-activations WITHOUT bias / xyz terms (3xTF32 tcgen05.mma). */
 int ac_nsr_debug_tc_layer(const float *feats, const float *mlp_blob, float *out, void *stream);

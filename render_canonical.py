@@ -9,17 +9,13 @@ avatarcraft_b200.  Same options (subset); `--weights_path` is a reference-layout
 import argparse
 import os
 
-import numpy as np
 import torch
 
 from avatarcraft_b200.models.instant_nsr import NeRFNetwork
 from avatarcraft_b200.utils import render_utils, synthetic
 from avatarcraft_b200.utils.camera_paths import default_360_path, rays_for_pose
+from avatarcraft_b200.utils.checkpoint import AsyncImageWriter
 from avatarcraft_b200.utils.constant import CAN_HEAD_CAMERA_DIST, CAN_HEAD_OFFSET, CANONICAL_CAMERA_DIST_VAL, NSR_BOUND
-
-
-def to_uint8(img):
-    return (np.clip(img, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
 
 
 def main():
@@ -47,19 +43,18 @@ def main():
     orbits = [("body", (0.0, 0.0, 0.0), CANONICAL_CAMERA_DIST_VAL + 0.26)]         # render_canonical.py:47-49 uses 1.7
     if opt.render_head:
         orbits.append(("head", (0.0, CAN_HEAD_OFFSET, 0.0), CAN_HEAD_CAMERA_DIST))
-    from PIL import Image
     for tag, center, dist in orbits:
-        frames = []
-        for i, pose in enumerate(default_360_path(center, dist, opt.n_views)):
+        # rays are generated on the device (ac_gen_rays); PNG/GIF encoding runs on a worker thread behind an async D2H copy
+        writer = AsyncImageWriter(gif_path=os.path.join(out_dir, f"{opt.exp_name}_{tag}.gif"))
+        poses = default_360_path(center, dist, opt.n_views)
+        for i, pose in enumerate(poses):
             o, d = rays_for_pose(pose, opt.render_w, opt.render_h, "cuda")
             with torch.no_grad():
                 rgb, _ = render_utils.render_instantnsr_naive(net, o, d, opt.rays_per_batch, requires_grad=False, render_can=True,
                                                               perturb=False, bound=NSR_BOUND)
-            img = to_uint8(rgb.reshape(opt.render_h, opt.render_w, 3).cpu().numpy())
-            Image.fromarray(img).save(os.path.join(out_dir, f"{opt.exp_name}_{tag}_{i:04d}.png"))
-            frames.append(Image.fromarray(img))
-        frames[0].save(os.path.join(out_dir, f"{opt.exp_name}_{tag}.gif"), save_all=True, append_images=frames[1:], duration=100, loop=0)
-        print(f"{tag}: {len(frames)} views -> {out_dir}")
+            writer.submit(rgb.reshape(opt.render_h, opt.render_w, 3), os.path.join(out_dir, f"{opt.exp_name}_{tag}_{i:04d}.png"))
+        writer.close()
+        print(f"{tag}: {len(poses)} views -> {out_dir}")
 
 
 if __name__ == "__main__":

@@ -22,6 +22,8 @@ from avatarcraft_b200.models.instant_nsr import NeRFNetwork
 from avatarcraft_b200.utils import render_utils, synthetic
 from avatarcraft_b200.utils.camera_paths import default_360_path, rays_for_pose
 from avatarcraft_b200.utils.constant import CANONICAL_CAMERA_DIST_TRAIN, NSR_BOUND
+from avatarcraft_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+from avatarcraft_b200.utils.optim import FlatAdam
 from avatarcraft_b200.utils.train_utils import stylize_patch_step
 
 
@@ -48,6 +50,8 @@ def main():
     ap.add_argument("--use_opacity", type=int, default=1)
     ap.add_argument("--guidance", type=str, default="target", choices=["target", "randn"])
     ap.add_argument("--i_save", type=int, default=1000)
+    ap.add_argument("--lr", type=float, default=5e-3)
+    ap.add_argument("--resume", type=str, default=None, help="a *.pth.tar written by this script (its .resume.pt is picked up)")
     opt = ap.parse_args()
 
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
@@ -60,11 +64,18 @@ def main():
     net_style, net_gt = net_style.cuda().train(), net_gt.cuda().eval()        # net_style is never .eval()ed (stylize.py:336)
     for p in net_gt.parameters():
         p.requires_grad_(False)
-    optimizer = torch.optim.Adam(net_style.parameters(), lr=5e-3)             # stylize.py:355-363
+    # Adam(lr 5e-3) + StepLR(epochs//2, 0.5) (stylize.py:355-363) on flat buffers: one all-reduce + one update launch
+    optimizer = FlatAdam(net_style.parameters(), lr=opt.lr)
     out_dir = os.path.join("style", "canonical_360", opt.exp_name)
     os.makedirs(out_dir, exist_ok=True)
-    H, W, step = opt.render_h, opt.render_w, 0
-    for epoch in range(opt.coarse_epochs + opt.fine_epochs):
+    H, W, step, first_epoch = opt.render_h, opt.render_w, 0, 0
+    n_epochs = opt.coarse_epochs + opt.fine_epochs
+    if opt.resume:                                                             # weights + optimizer moments + counters + RNG
+        info = load_checkpoint(opt.resume, net_style, optimizer)
+        step, first_epoch = info["step"], info["epoch"]
+        print(f"resumed from {opt.resume}: step {step}, epoch {first_epoch}, optimizer state {'restored' if info['resumed'] else 'fresh'}")
+    for epoch in range(first_epoch, n_epochs):
+        optimizer.param_groups[0]["lr"] = opt.lr * (0.5 ** (epoch // max(n_epochs // 2, 1)))
         stride = opt.subsample_scale if epoch < opt.coarse_epochs else min(1, opt.subsample_scale // 2) or 1
         poses = default_360_path((0.0, 0.0, 0.0), CANONICAL_CAMERA_DIST_TRAIN, opt.n_views)
         perm = torch.randperm(opt.n_views, generator=torch.Generator().manual_seed(epoch))      # same order on every rank
@@ -82,9 +93,9 @@ def main():
             if rank == 0 and step % 10 == 0:
                 print(f"epoch {epoch} step {step} eikonal {float(stats['eikonal'] or 0):.4f}")
             if rank == 0 and step % opt.i_save == 0:
-                torch.save(net_style.state_dict(), os.path.join(out_dir, f"{opt.exp_name}_{step:06d}.pth.tar"))
+                save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}_{step:06d}.pth.tar"), net_style, optimizer, step, epoch)
     if rank == 0:
-        torch.save(net_style.state_dict(), os.path.join(out_dir, f"{opt.exp_name}.pth.tar"))
+        save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}.pth.tar"), net_style, optimizer, step, n_epochs)
         print("saved", os.path.join(out_dir, f"{opt.exp_name}.pth.tar"))
     if world > 1:
         dist.destroy_process_group()
