@@ -12,7 +12,8 @@ sd = syn.synthetic_state_dict("trained", 43)
 net = NeRFNetwork(); net.load_state_dict(sd); net = net.cuda().train()
 gt = NeRFNetwork(); gt.load_state_dict(sd); gt = gt.cuda().eval()
 for p in gt.parameters(): p.requires_grad_(False)
-opt = torch.optim.Adam(net.parameters(), lr=5e-3)
+from avatarcraft_b200.utils.optim import FlatAdam
+opt = FlatAdam(net.parameters(), lr=5e-3)
 o, d = syn.pinhole_rays(syn.orbit_pose(30.0), 256, 256)
 o, d = o.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3).cuda(), d.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3).cuda()
 G = torch.randn(o.shape[0], 3, device="cuda")

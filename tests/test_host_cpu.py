@@ -1,0 +1,65 @@
+"""CPU suite for the host-side pieces around the hot path: checkpoint / resume wire format, the asynchronous image
+writer, and the refusal of the device-only stages to run without a GPU (no CPU fallback)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from avatarcraft_b200.utils import checkpoint as ckpt
+
+
+class _Opt:
+    def __init__(self):
+        self.s = {"step": 7, "lr": 2.5e-3, "betas": (0.9, 0.999), "eps": 1e-8, "exp_avg": torch.arange(8.0), "exp_avg_sq": torch.ones(8)}
+
+    def state_dict(self):
+        return self.s
+
+    def load_state_dict(self, sd):
+        self.s = sd
+
+
+def test_checkpoint_is_the_reference_wire_format_plus_resume_file(tmp_path):
+    net = torch.nn.Linear(3, 2)
+    path = str(tmp_path / "exp" / "exp_0007.pth.tar")
+    torch.manual_seed(123)
+    rpath = ckpt.save_checkpoint(path, net, _Opt(), step=7, epoch=2, extra={"view": 3})
+    expect_next = torch.rand(4)                                   # what the RNG produces right after the save
+    # the weights file is exactly torch.save(state_dict) -- what the reference's entry points load (stylize.py:255-260)
+    sd = torch.load(path, map_location="cpu")
+    assert set(sd.keys()) == {"weight", "bias"} and torch.equal(sd["weight"], net.weight.detach())
+    assert rpath == ckpt.resume_path(path) and os.path.exists(rpath)
+    net2, opt2 = torch.nn.Linear(3, 2), _Opt()
+    opt2.s = None
+    torch.manual_seed(999)
+    info = ckpt.load_checkpoint(path, net2, opt2)
+    assert info == {"step": 7, "epoch": 2, "extra": {"view": 3}, "resumed": True}
+    assert torch.equal(net2.weight, net.weight) and opt2.s["step"] == 7 and torch.equal(opt2.s["exp_avg"], torch.arange(8.0))
+    assert torch.equal(torch.rand(4), expect_next)                # RNG stream continues where it stopped
+    # a plain reference checkpoint (no resume file) loads too
+    plain = str(tmp_path / "plain.pth.tar")
+    torch.save(net.state_dict(), plain)
+    assert ckpt.load_checkpoint(plain, net2, _Opt())["resumed"] is False
+
+
+def test_async_image_writer_writes_png_and_gif(tmp_path):
+    from PIL import Image
+    w = ckpt.AsyncImageWriter(gif_path=str(tmp_path / "orbit.gif"))
+    frames = [torch.full((8, 12, 3), v) for v in (0.0, 0.5, 1.0)]
+    for i, f in enumerate(frames):
+        w.submit(f, str(tmp_path / "sub" / f"f_{i}.png"))
+    w.close()
+    for i, v in enumerate((0, 128, 255)):
+        img = np.asarray(Image.open(tmp_path / "sub" / f"f_{i}.png"))
+        assert img.shape == (8, 12, 3) and int(img[0, 0, 0]) == v
+    assert Image.open(tmp_path / "orbit.gif").n_frames == 3
+
+
+def test_device_only_stages_refuse_cpu():
+    from avatarcraft_b200.utils import ray_gen
+    from avatarcraft_b200.utils.optim import FlatAdam
+    with pytest.raises(RuntimeError):
+        ray_gen.pinhole_rays_device(np.eye(4), 8, 8, "cpu")
+    with pytest.raises(RuntimeError):
+        FlatAdam([torch.nn.Parameter(torch.zeros(4))])
