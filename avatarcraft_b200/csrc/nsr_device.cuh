@@ -89,8 +89,27 @@ __device__ __forceinline__ float2 grid_level_3d_k(const float2* __restrict__ tab
         s[6] = (hx0 ^ hy1 ^ hz1) & mask; s[7] = (hx1 ^ hy1 ^ hz1) & mask;
     }
     float2 v[8];
+#if defined(AC_PROBE_PAIR)
+    // TIMING PROBE ONLY (wrong values): every x-pair fetched with one 16-byte load -- the upper bound of what
+    // merging even-x corner pairs can save.  Never part of a shipped build.
+    if (HASHED && m.scale > AC_PROBE_PAIR) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+        for (int k = 0; k < 8; k += 2) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(t + (s[k] | 1u)));
+            v[k] = make_float2(q.x, q.y); v[k + 1] = make_float2(q.z, q.w);
+        }
+    } else
+#endif
+#if defined(AC_PROBE_SKIP)
+    if (HASHED && m.scale > AC_PROBE_SKIP) {      // TIMING PROBE ONLY: fine levels cost nothing
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = make_float2(px, py);
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+    }
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
