@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(256) forward_color_kernel(const float* __restr
 //   * the hash table: w * d(feature) scattered into the 8 corners of 16 levels with fp32
 //     red.global.add.v2 (same arithmetic as kernel_grid_backward, hashencoder.cu:223-308),
 //   * per-point layer deltas that the host turns into weight gradients with plain GEMMs:
-//       delta_a [B,64] = dL/d(pre-activation), hidden [B,64] = softplus output, feats [B,32].
+//       delta_a [64,B] = dL/d(pre-activation), hidden [64,B] = softplus output, feats [35,B] = the layer input (xyz | features)
+//     (unit-major: consecutive points are consecutive addresses, so every store of a warp is one 128 B line; the
+//     point-major layout cost 32 sectors per store instruction and most of this kernel's time).
 // softplus'(a) = sigmoid(100 a) (1 above torch's threshold 100a > 20).
 __global__ void __launch_bounds__(256) sdf_backward_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
                                                            const float* __restrict__ blob, float S, uint32_t H,
@@ -367,8 +369,8 @@ __global__ void __launch_bounds__(256) sdf_backward_kernel(const float2* __restr
                 dh = fmaf(w4.z, g[4 * q + 2], dh); dh = fmaf(w4.w, g[4 * q + 3], dh);
             }
             const float da = a * 100.0f > 20.0f ? dh : dh * sigmoidf(a * 100.0f);
-            delta_a[(size_t)b * kHidden + j] = da;
-            hidden[(size_t)b * kHidden + j] = h;
+            delta_a[(size_t)j * B + b] = da;            // unit-major [64][B]: a warp's 32 points write one 128 B line
+            hidden[(size_t)j * B + b] = h;
             const float4* __restrict__ wf = reinterpret_cast<const float4*>(w0f + j * 32);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -378,8 +380,7 @@ __global__ void __launch_bounds__(256) sdf_backward_kernel(const float2* __restr
             }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(feats + 32 * (size_t)b + 4 * q) = make_float4(in[3 + 4 * q], in[4 + 4 * q], in[5 + 4 * q], in[6 + 4 * q]);
+        for (int q = 0; q < 35; ++q) feats[(size_t)q * B + b] = in[q];         // input-major [35][B] = (x, y, z, 32 features), coalesced
         // scatter into the table
         const float two_b = 2.0f * bound;
         const float u = (px + bound) / two_b, v = (py + bound) / two_b, w = (pz + bound) / two_b;
@@ -563,8 +564,9 @@ uint64_t ac_nsr_render_workspace_bytes(uint32_t n_rays) { return (uint64_t)n_ray
 
 int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stream) {
     if (check_model(m) || !m->variance || !a) return AC_E_INVALID_ARG;
-    if (!a->rays_o || !a->rays_d || !a->rgb || !a->depth || !a->weight_sum || !a->normal || !a->eikonal || !a->workspace)
-        return AC_E_INVALID_ARG;
+    const bool sample_only = a->rgb == nullptr;          // documented in the header: z_vals is the only output
+    if (!a->rays_o || !a->rays_d || !a->workspace) return AC_E_INVALID_ARG;
+    if (sample_only ? (!a->z_vals || a->z_in) : (!a->depth || !a->weight_sum || !a->normal || !a->eikonal)) return AC_E_INVALID_ARG;
     const uint32_t T = a->num_steps + a->upsample_steps;
     if (a->num_steps < 2 || a->upsample_steps % 16 != 0 || T > (uint32_t)kMaxT) return AC_E_INVALID_ARG;
     if (a->workspace_bytes < ac_nsr_render_workspace_bytes(a->n_rays)) return AC_E_WORKSPACE;
@@ -574,11 +576,11 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
     static const bool use_simt = [] { const char* e = getenv("AC_RENDER_IMPL"); return e && e[0] == 's'; }();
     if (!use_simt) {   // tensor-core kernel (default); AC_RENDER_IMPL=simt keeps the SIMT kernel for A/B debugging
         int rc = acb::launch_render_tc(m, a, st);
-        if (rc) return rc;
+        if (rc || sample_only) return rc;
         eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(reinterpret_cast<float*>(a->workspace), a->n_rays, seg, a->eikonal);
         return acb::launched();
     }
-    if (a->z_in || a->pts_in || a->near_far_in) return AC_E_UNSUPPORTED;   // staged inputs: tensor-core kernel only
+    if (a->z_in || a->pts_in || a->near_far_in || sample_only) return AC_E_UNSUPPORTED;   // staged inputs / sampling-only: tensor-core kernel only
     RenderParams p;
     p.table = reinterpret_cast<const float2*>(m->embeddings);
     p.offsets = m->offsets; p.blob = m->mlp_blob; p.variance = m->variance;

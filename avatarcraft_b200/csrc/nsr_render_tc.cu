@@ -438,6 +438,13 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             T += 16;
         }
 
+        if (p.a.rgb == nullptr) {        // sampling-only launch (training path): the sorted depths are the result
+            if (ray_ok)
+                for (int k = lane; k < Ttot; k += 32) p.a.z_vals[(size_t)ray * Ttot + k] = zs[k];
+            __syncwarp();
+            continue;
+        }
+
         // ---- render core (:186-299), 32 section samples at a time in depth order ----
         // Per block: the 6 x 32 finite-difference points (:687-704) first, lanes packed as (sample, direction):
         // the six +-eps neighbours of a sample sit within 0.003 of each other, so on every level coarser than

@@ -57,7 +57,7 @@ class _SdfQuery(torch.autograd.Function):
         gout = gout.contiguous().float()
         f32 = dict(device=dev, dtype=torch.float32)
         grad_table = torch.zeros(ctx.emb_shape, **f32)
-        delta = torch.empty(B, 64, **f32); hid = torch.empty(B, 64, **f32); feats = torch.empty(B, 32, **f32)
+        delta = torch.empty(64, B, **f32); hid = torch.empty(64, B, **f32); feats = torch.empty(35, B, **f32)   # unit-major
         m = net._device_model()
         _lib.check(_lib.lib().ac_nsr_sdf_backward(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound,
                                                   _lib.ptr(grad_table), _lib.ptr(delta), _lib.ptr(hid), _lib.ptr(feats),
@@ -70,11 +70,11 @@ class _SdfQuery(torch.autograd.Function):
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
         try:
-            gw0 = torch.cat([delta.t() @ x, delta.t() @ feats], dim=1)
-            gw1 = gout.t() @ hid
+            gw0 = delta @ feats.t()                      # [64,35]: feats rows are (x, y, z, 32 hash features)
+            gw1 = (hid @ gout).t()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
-        return None, grad_table, gw0, delta.sum(0), gw1, gout.sum(0), None, None
+        return None, grad_table, gw0, delta.sum(1), gw1, gout.sum(0), None, None
 
 
 class SingleVarianceNetwork(nn.Module):
@@ -174,6 +174,26 @@ class NeRFRenderer(nn.Module):
                 color, alpha, z_vals)
 
     @torch.no_grad()
+    def _sample_depths(self, rays_o, rays_d, num_steps, upsample_steps, bound, jitter=None):
+        """Sorted sample depths [n, T] only: a sampling-only ac_nsr_render launch (rgb = NULL) that stops after the
+        importance rounds -- what the training path needs from the no-grad block of `run` (:175-185)."""
+        n, dev = rays_o.shape[0], rays_o.device
+        T = num_steps + upsample_steps
+        if jitter is not None:
+            jitter = jitter.to(dev, torch.float32).contiguous()
+        z = torch.empty(n, T, device=dev, dtype=torch.float32)
+        L = _lib.lib()
+        ws_bytes = int(L.ac_nsr_render_workspace_bytes(n))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        model = self._device_model()
+        a = _lib.NsrRenderArgs(rays_o=rays_o.data_ptr(), rays_d=rays_d.data_ptr(), jitter=None if jitter is None else jitter.data_ptr(),
+                               n_rays=n, num_steps=num_steps, upsample_steps=upsample_steps, eikonal_segment=0, bound=float(bound),
+                               cos_anneal_ratio=1.0, normal_epsilon_ratio=0.0, z_vals=z.data_ptr(), workspace=ws.data_ptr(),
+                               workspace_bytes=ws_bytes)
+        _lib.check(L.ac_nsr_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "ac_nsr_render (sampling only)")
+        return z
+
+    @torch.no_grad()
     def _run_warped(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio, normal_epsilon_ratio,
                     verts, faces, Ts, use_mesh_guide, per_sample_outputs, eikonal_segment):
         """render_can=False (models/instant_nsr.py:147-153,166-172,198-203,245-248): mesh-guided near/far, coarse
@@ -243,8 +263,7 @@ class NeRFRenderer(nn.Module):
             if z_override is not None:      # tests: differentiate at externally supplied sample depths
                 z = z_override.to(dev, torch.float32).contiguous()
             else:
-                z = NeRFRenderer.run(self, o[None], d[None], num_steps, bound, upsample_steps, None, cos_anneal_ratio,
-                                     normal_epsilon_ratio, perturb_overwrite=perturb_overwrite, jitter=jitter)[9]
+                z = self._sample_depths(o, d, num_steps, upsample_steps, bound, jitter)
             T = z.shape[1]
             near, far = near_far_from_bound(o, d, bound)
             gaps = torch.cat([z[:, 1:] - z[:, :-1], ((far - near) / num_steps).expand(n, 1)], -1)

@@ -108,8 +108,10 @@ int ac_nsr_forward_sdf(const ac_nsr_model *model, const float *x, float *out, ui
  * hash-table gradient into grad_table [n_entries,2] (caller zeroes; fp32 reductions as in
  * kernel_grid_backward, hashencoder.cu:223-308) and writes the per-point layer terms from which
  * the host forms the weight gradients with plain GEMMs:
- *   delta_a [B,64] = dL/d(hidden pre-activation), hidden [B,64] = softplus output, feats [B,32]
- *   => dW0 = delta_a^T [x | feats], db0 = sum delta_a, dW1 = grad_out^T hidden, db1 = sum grad_out. */
+ *   delta_a [64,B] = dL/d(hidden pre-activation), hidden [64,B] = softplus output, feats [35,B] = the layer's
+ *   input rows (x, y, z, 32 hash features)  (unit-major, so the kernel's stores are coalesced and the host GEMMs
+ *   read K-contiguous operands)
+ *   => dW0 = delta_a feats^T, db0 = row sums of delta_a, dW1 = grad_out^T hidden^T, db1 = sum grad_out. */
 int ac_nsr_sdf_backward(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B,
                         float bound, float *grad_table, float *delta_a, float *hidden, float *feats,
                         void *stream);
@@ -136,6 +138,9 @@ int ac_nsr_fd_gradient(const ac_nsr_model *model, const float *x, float *grad, u
  *     consecutive segment of `eikonal_segment` rays (0 = one segment = the whole launch).  The
  *     reference's driver renders 4096-ray batches and adds their means (render_utils.py:556-575);
  *     one launch with eikonal_segment = rays_per_batch reproduces that without 16 launches.
+ * Sampling only: with rgb == NULL the launch stops after the importance rounds and writes just z_vals [n,T]
+ *   (the training path needs the sample depths, not the image, models/instant_nsr.py:175-185) -- 112 of the 1008
+ *   SDF evaluations per ray.  depth / weight_sum / normal / eikonal are then not written.
  * workspace: >= ac_nsr_render_workspace_bytes(n_rays) bytes, 16 B aligned.
  * Constraints: num_steps in [2,128], upsample_steps a multiple of 16, T <= 128. */
 typedef struct ac_nsr_render_args {

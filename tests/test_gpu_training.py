@@ -149,3 +149,17 @@ def test_stylize_patch_step_updates_parameters_like_the_reference_loop():
         assert torch.isfinite(p.grad).all()
     moved = sum(float((p.detach() - before[k]).abs().sum()) for k, p in net_b.named_parameters())
     assert moved > 0 and stats["eikonal"] is not None and stats["opacity"] is not None
+
+
+def test_sampling_only_launch_returns_the_render_launch_depths():
+    """rgb = NULL stops the fused kernel after the importance rounds: same depths, bit for bit, as the full launch."""
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    from avatarcraft_b200.utils import synthetic as syn
+    o, d = syn.pinhole_rays(syn.orbit_pose(30.0), 48, 48)
+    o, d = o.cuda(), d.cuda()
+    jit = torch.rand(o.shape[0], 64, generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        full = net.run(o[None], d[None], 64, 1.6, 64, None, 1.0, 0.0, jitter=jit)[9]
+        only = net._sample_depths(o, d, 64, 64, 1.6, jit)
+    assert torch.equal(full, only)
