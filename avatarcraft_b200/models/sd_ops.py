@@ -75,3 +75,18 @@ def attention(q, k, v, heads, scale):
     vh = v.reshape(B, -1, heads, d).transpose(1, 2)
     p = torch.softmax((qh @ kh.transpose(-1, -2)) * scale, dim=-1)
     return (p @ vh).transpose(1, 2).reshape(B, Lq, inner)
+
+
+def to_activation_layout(x):
+    """Native path: activations are NHWC in memory (torch channels_last) so that a [B,H,W,C] image is also the
+    [B*H*W, C] row-major GEMM operand / token matrix.  Autograd path: unchanged."""
+    if use_native(x):
+        return x.float().contiguous(memory_format=torch.channels_last)
+    return x
+
+
+def cat_channels(a, b):
+    """Skip connection concat along channels."""
+    if use_native(a):
+        return _n().cat_channels(a, b)
+    return torch.cat([a, b], dim=1)
