@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("AC_LIB_PATH") or os.path.join(_PKG, "libavatarcraft_b200.so")   # AC_LIB_PATH: tuning variants
-SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu", "raymarch_ops.cu", "frame_ops.cu"]
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu", "raymarch_ops.cu", "frame_ops.cu", "sd_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -63,7 +63,7 @@ class NsrRenderArgs(ctypes.Structure):
                 ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64)]
 
 
-_V, _U32, _F, _I, _D = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_double
+_V, _U32, _F, _I, _D, _I64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_double, ctypes.c_int64
 _SIGNATURES = {
     "ac_version": (ctypes.c_char_p, []),
     "ac_last_cuda_error": (ctypes.c_char_p, []),
@@ -99,6 +99,13 @@ _SIGNATURES = {
     "ac_adam_step": (_I, [_V, _V, _V, _V, ctypes.c_uint64, _F, _F, _F, _F, _U32, _F, _V]),
     "ac_sdf_grid_points": (_I, [_V, _V, _U32, _U32, _U32, _V, _V]),
     "ac_iso_surface": (_I, [_V, _V, _V, _U32, _F, _V, _V, ctypes.c_uint64, _V, _V]),
+    "ac_sd_gemm_f16": (_I, [_V, _V, _V, _V, _I, _V, _V, _I, _I, _I, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I64, _I64, _I64, _V]),
+    "ac_sd_group_norm_stats": (_I, [_V, _I, _I, _I, _I, _F, _V, _V, _V]),
+    "ac_sd_im2col_f16": (_I, [_V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _V, _V, _I, _I, _V, _V]),
+    "ac_sd_layer_norm_f16": (_I, [_V, _I, _I, _V, _V, _F, _V, _V]),
+    "ac_sd_geglu_f16": (_I, [_V, _I64, _I, _V, _V]),
+    "ac_sd_softmax_f16": (_I, [_V, _I64, _I, _I64, _I64, _F, _V, _V]),
+    "ac_sd_cast_f16": (_I, [_V, _I64, _V, _V]),
     "ac_nsr_debug_tc_layer": (_I, [_V, _V, _V, _V]),
     "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V, _V, _V]),
 }

@@ -1,0 +1,426 @@
+// sd_ops.cu -- native forward path of the Stable-Diffusion UNet the SDS step evaluates without gradients
+// (reference: models/diffusion.py:121-132 calls diffusers' UNet2DConditionModel).  sm_100a.
+//
+// Activations are fp32 NHWC ([B*H*W, C] row-major == the token matrix of the transformer blocks); every GEMM operand is
+// fp16 and every contraction runs on the 5th-generation tensor cores:
+//
+//   ac_sd_gemm_f16      C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ group_bias[m / rows_per_group, N]) (+ residual[M,N])
+//                       tcgen05.mma kind::f16, M128 x N128 x K16, fp32 accumulators in TMEM (128 columns), operands
+//                       staged by cp.async (16 B, zero-filled past M / N / K) straight into the K-major no-swizzle
+//                       core-matrix layout, 3-stage ring released by tcgen05.commit -> mbarrier; batched through
+//                       blockIdx.z with a two-level (outer, inner) stride so per-head slices of [B, L, heads*d] need
+//                       no copies.  Linear layers, 1x1 convs, 3x3 convs (after im2col), Q K^T and P V all use it.
+//   producers           write the fp16 A operand of the next GEMM: GroupNorm(+SiLU) applied on the fly inside the
+//                       im2col of a 3x3 conv (stride 1/2, optional nearest x2 up-sampling of the source),
+//                       GroupNorm -> fp16, LayerNorm -> fp16, GEGLU -> fp16, softmax -> fp16, plain cast.
+//
+// HBM traffic is irrelevant at these sizes (the largest activation is 10 MB); the GEMMs are L2-bandwidth / tensor bound.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/avatarcraft_b200.h"
+#include "launch_util.cuh"
+#include "tc05.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// GEMM
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand per stage
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 64;    // + barriers + TMEM slot
+constexpr int GEMM_THREADS = 128;
+
+struct GemmParams {
+    const __half* A; const __half* W;
+    const float* bias; const float* group_bias; const float* residual;
+    void* C;
+    int M, N, K;
+    long long lda, ldw, ldc, ldr;
+    int rows_per_group;
+    int batch_inner;
+    long long sAo, sAi, sWo, sWi, sCo, sCi;
+    int out_f16;
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One 128 x 64 fp16 tile (rows row0.., columns k0..) of a row-major matrix -> K-major no-swizzle core-matrix layout:
+// 16-byte chunk c of row r at c*2048 + r*16.  A warp instruction covers 8 rows x 4 chunks: every 32 B sector it
+// touches is consumed whole, and the 8 lanes of a shared-memory phase hit 8 distinct 16 B bank groups.
+__device__ __forceinline__ void load_tile(uint32_t dst, const __half* __restrict__ base, long long ld, int rows, int K, int row0, int k0,
+                                          int warp, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int u = warp * 8 + i;
+        const int r = (u >> 1) * 8 + (lane & 7);
+        const int c = (u & 1) * 4 + (lane >> 3);
+        const int row = row0 + r, k = k0 + c * 8;
+        int bytes = (K - k) * 2;
+        bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+        if (row >= rows) bytes = 0;
+        const __half* src = bytes > 0 ? base + (long long)row * ld + k : base;
+        cp_async_16(dst + c * 2048 + r * 16, src, bytes);
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_kernel(const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* free_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + STAGES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int zo = blockIdx.z / p.batch_inner, zi = blockIdx.z % p.batch_inner;
+    const __half* A = p.A + zo * p.sAo + zi * p.sAi;
+    const __half* W = p.W + zo * p.sWo + zi * p.sWi;
+    const long long c_off = zo * p.sCo + zi * p.sCi;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) tc05::mbar_init(free_bar + s, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc<BN>(tmem_slot);
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t smem_s = tc05::smem_u32(smem);
+
+    const int KT = (p.K + BK - 1) / BK;
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) {
+            load_tile(smem_s + s * STAGE_BYTES, A, p.lda, p.M, p.K, m0, s * BK, warp, lane);
+            load_tile(smem_s + s * STAGE_BYTES + TILE_BYTES, W, p.ldw, p.N, p.K, n0, s * BK, warp, lane);
+        }
+        cp_async_commit();
+    }
+    constexpr uint32_t idesc = tc05::idesc_f16(BM, BN);
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();                    // this thread's copies of tile kt have landed
+        tc05::fence_proxy_async_smem();                 // ... and are visible to the tensor core's (async-proxy) reads
+        tc05::fence_before_sync();
+        __syncthreads();
+        const int stage = kt % STAGES;
+        if (tid == 0) {
+            tc05::fence_after_sync();
+            const uint32_t a_s = smem_s + stage * STAGE_BYTES, b_s = a_s + TILE_BYTES;
+#pragma unroll
+            for (uint32_t s = 0; s < BK / 16; ++s)
+                tc05::mma_f16(tmem, tc05::smem_desc(a_s + s * 4096u, 2048u, 128u), tc05::smem_desc(b_s + s * 4096u, 2048u, 128u), idesc,
+                              (kt | (int)s) != 0 ? 1u : 0u);
+            tc05::mma_commit(free_bar + stage);          // arrives when the MMAs that read this stage are done
+        }
+        const int nk = kt + STAGES - 1;                  // refill the stage tile kt-1 used
+        if (nk < KT) {
+            if (kt >= 1) tc05::mbar_wait(free_bar + (kt - 1) % STAGES, (uint32_t)(((kt - 1) / STAGES) & 1));
+            const int ns = nk % STAGES;
+            load_tile(smem_s + ns * STAGE_BYTES, A, p.lda, p.M, p.K, m0, nk * BK, warp, lane);
+            load_tile(smem_s + ns * STAGE_BYTES + TILE_BYTES, W, p.ldw, p.N, p.K, n0, nk * BK, warp, lane);
+        }
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+    tc05::mbar_wait(free_bar + (KT - 1) % STAGES, (uint32_t)(((KT - 1) / STAGES) & 1));     // the last commit covers every MMA
+    tc05::fence_after_sync();
+
+    // ---- epilogue: TMEM lane = output row; 16 columns per tcgen05.ld ----
+    const int row = m0 + warp * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* gb = (p.group_bias && row < p.M) ? p.group_bias + (long long)(row / p.rows_per_group) * p.N : nullptr;
+#pragma unroll 1
+    for (int q = 0; q < BN / 16; ++q) {
+        float acc[16];
+        tc05::tmem_ld16(trow + q * 16, acc);            // warp-collective: every lane executes it
+        const int n = n0 + q * 16;
+        if (row >= p.M || n >= p.N) continue;
+        const int nv = p.N - n < 16 ? p.N - n : 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < nv) {
+                float v = acc[j];
+                if (p.bias) v += p.bias[n + j];
+                if (gb) v += gb[n + j];
+                if (p.residual) v += p.residual[(long long)row * p.ldr + n + j];
+                acc[j] = v;
+            }
+        }
+        if (p.out_f16) {
+            __half* dst = reinterpret_cast<__half*>(p.C) + c_off + (long long)row * p.ldc + n;
+            if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                uint4 lo, hi;
+                lo.x = tc05::pack_f16x2(acc[0], acc[1]); lo.y = tc05::pack_f16x2(acc[2], acc[3]);
+                lo.z = tc05::pack_f16x2(acc[4], acc[5]); lo.w = tc05::pack_f16x2(acc[6], acc[7]);
+                hi.x = tc05::pack_f16x2(acc[8], acc[9]); hi.y = tc05::pack_f16x2(acc[10], acc[11]);
+                hi.z = tc05::pack_f16x2(acc[12], acc[13]); hi.w = tc05::pack_f16x2(acc[14], acc[15]);
+                reinterpret_cast<uint4*>(dst)[0] = lo; reinterpret_cast<uint4*>(dst)[1] = hi;
+            } else {
+                for (int j = 0; j < nv; ++j) dst[j] = __float2half_rn(acc[j]);
+            }
+        } else {
+            float* dst = reinterpret_cast<float*>(p.C) + c_off + (long long)row * p.ldc + n;
+            if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            } else {
+                for (int j = 0; j < nv; ++j) dst[j] = acc[j];
+            }
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<BN>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Producers (all HBM-streaming, one element group per thread, 16-byte stores)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// GroupNorm statistics over NHWC: grid (chunks, B).  A thread owns channel c (+ blockDim strides) over a chunk of pixels,
+// so a warp reads consecutive channels of one pixel; per-channel partials fold into their group in shared memory and
+// leave through fp64 atomics: sums[b][g] = (sum, sum of squares).
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, int G, int px_per_block, double* __restrict__ sums) {
+    extern __shared__ double sh[];                      // [G][2]
+    const int b = blockIdx.y, cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f, ss = 0.f;
+        const float* col = x + ((long long)b * HW + p0) * C + c;
+        for (int p = p0; p < p1; ++p, col += C) { const float v = *col; s += v; ss = fmaf(v, v, ss); }
+        atomicAdd(&sh[2 * (c / cpg)], (double)s);
+        atomicAdd(&sh[2 * (c / cpg) + 1], (double)ss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(long long)b * 2 * G + i], sh[i]);
+}
+
+// (sum, sumsq) -> (mean, rstd), in place as floats: stats[b][g] = (mean, rstd).
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, int n, double count, float eps, float* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mean = sums[2 * i] / count;
+    double var = sums[2 * i + 1] / count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+struct NormArgs {          // optional GroupNorm(+SiLU) applied while reading the source
+    const float* stats;    // [B][G][2] (mean, rstd) or NULL
+    const float* gamma; const float* beta;
+    int G, act;
+};
+
+__device__ __forceinline__ void norm8(float (&v)[8], const NormArgs& nm, int b, int c0, int C) {
+    if (!nm.stats) return;
+    const int cpg = C / nm.G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j, g = c / cpg;
+        const float mean = nm.stats[((long long)b * nm.G + g) * 2], rstd = nm.stats[((long long)b * nm.G + g) * 2 + 1];
+        float y = (v[j] - mean) * rstd * nm.gamma[c] + nm.beta[c];
+        v[j] = nm.act ? silu(y) : y;
+    }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 o;
+    o.x = tc05::pack_f16x2(v[0], v[1]); o.y = tc05::pack_f16x2(v[2], v[3]);
+    o.z = tc05::pack_f16x2(v[4], v[5]); o.w = tc05::pack_f16x2(v[6], v[7]);
+    return o;
+}
+
+// NHWC fp32 [B,Hs,Ws,C] -> fp16 [B*Ho*Wo, ks*ks*Cp] (K index = (ky*ks + kx)*Cp + c; Cp = C rounded up to 8, zero padded),
+// zero padding `pad` on the top/left (bottom/right implied by Ho, Wo), stride 1/2, optional nearest x2 up-sampling of the
+// source (Upsample2D), optional GroupNorm(+SiLU) on the fly.  ks = 1 is the plain normalise-and-cast producer.
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, int B, int Hs, int Ws, int C, int Cp, int ks, int stride, int pad,
+                                                     int up, int Ho, int Wo, const NormArgs nm, __half* __restrict__ out) {
+    const int chunks = Cp / 8;
+    const long long total = (long long)B * Ho * Wo * ks * ks * chunks;
+    const int Hin = up ? Hs * 2 : Hs, Win = up ? Ws * 2 : Ws;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % chunks);
+        long long r = t / chunks;
+        const int tap = (int)(r % (ks * ks)); r /= ks * ks;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const int iy = oy * stride + tap / ks - pad, ix = ox * stride + tap % ks - pad;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+            const int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
+            const float* src = x + (((long long)b * Hs + sy) * Ws + sx) * C + ch * 8;
+            if (ch * 8 + 8 <= C && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                const float4 a = reinterpret_cast<const float4*>(src)[0], c4 = reinterpret_cast<const float4*>(src)[1];
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
+                norm8(v, nm, b, ch * 8, C);
+            } else {
+                for (int j = 0; j < 8; ++j) {
+                    if (ch * 8 + j < C) {
+                        float one[8] = {src[j], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (nm.stats) {
+                            const int c = ch * 8 + j, g = c / (C / nm.G);
+                            const float y = (one[0] - nm.stats[((long long)b * nm.G + g) * 2]) * nm.stats[((long long)b * nm.G + g) * 2 + 1] * nm.gamma[c] + nm.beta[c];
+                            one[0] = nm.act ? silu(y) : y;
+                        }
+                        v[j] = one[0];
+                    }
+                }
+            }
+        }
+        reinterpret_cast<uint4*>(out)[t] = pack8(v);
+    }
+}
+
+// LayerNorm over the last axis, fp32 [M,C] -> fp16 [M,C]; one warp per row, two passes over registers/L1.
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, __half* __restrict__ out) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* xr = x + (long long)row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; ss = fmaf(d, d, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)C + eps);
+    for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = __float2half_rn((xr[c] - mean) * rstd * gamma[c] + beta[c]);
+}
+
+// GEGLU: x [M, 2I] fp32 -> fp16 [M, I] = value * gelu(gate), exact (erf) GELU like F.gelu.
+__global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ x, long long M, int I, __half* __restrict__ out) {
+    const long long total = M * I;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long m = t / I;
+        const int i = (int)(t - m * I);
+        const float v = x[m * 2 * I + i], g = x[m * 2 * I + I + i];
+        out[t] = __float2half_rn(v * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f))));
+    }
+}
+
+// Row softmax of scale * scores: fp32 [rows, L] (row stride ld_in) -> fp16 [rows, ld_out] (columns >= L zeroed).
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ s, long long rows, int L, long long ld_in, long long ld_out, float scale,
+                                                      __half* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* sr = s + row * ld_in;
+    float mx = -INFINITY;
+    for (int c = lane; c < L; c += 32) mx = fmaxf(mx, sr[c] * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < L; c += 32) sum += __expf(sr[c] * scale - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    __half* orow = out + row * ld_out;
+    for (int c = lane; c < (int)ld_out; c += 32) orow[c] = c < L ? __float2half_rn(__expf(sr[c] * scale - mx) * inv) : __half(0.f);
+}
+
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ out) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) out[t] = __float2half_rn(x[t]);
+}
+
+inline int grid_for(long long work, int block, int per_sm) {
+    const long long want = (work + block - 1) / block;
+    const long long cap = (long long)acb::sm_count() * per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float* group_bias, int rows_per_group, const float* residual,
+                   void* C, int out_f16, int M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int64_t ldr, int batch_outer,
+                   int batch_inner, int64_t sAo, int64_t sAi, int64_t sWo, int64_t sWi, int64_t sCo, int64_t sCi, void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || batch_outer <= 0 || batch_inner <= 0) return AC_E_INVALID_ARG;
+    if ((lda & 7) || (ldw & 7) || (sAo & 7) || (sAi & 7) || (sWo & 7) || (sWi & 7)) return AC_E_INVALID_ARG;     // 16 B operand rows
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return AC_E_INVALID_ARG;
+    if (group_bias && rows_per_group <= 0) return AC_E_INVALID_ARG;
+    if ((batch_outer > 1 || batch_inner > 1) && (residual || group_bias)) return AC_E_UNSUPPORTED;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; }
+    GemmParams p;
+    p.A = reinterpret_cast<const __half*>(A); p.W = reinterpret_cast<const __half*>(W);
+    p.bias = bias; p.group_bias = group_bias; p.residual = residual; p.C = C;
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.ldr = ldr;
+    p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.batch_inner = batch_inner;
+    p.sAo = sAo; p.sAi = sAi; p.sWo = sWo; p.sWi = sWi; p.sCo = sCo; p.sCi = sCi; p.out_f16 = out_f16;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch_outer * batch_inner);
+    if (grid.y > 65535 || grid.z > 65535) return AC_E_INVALID_ARG;
+    sd_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(p);
+    return acb::launched();
+}
+
+int ac_sd_group_norm_stats(const float* x, int B, int HW, int C, int G, float eps, double* sums_workspace, float* stats, void* stream) {
+    if (!x || !sums_workspace || !stats || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) return AC_E_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * B * G, st) != cudaSuccess) return acb::cuda_fail();
+    const int px = 64;
+    dim3 grid((HW + px - 1) / px, B);
+    gn_stats_kernel<<<grid, 256, sizeof(double) * 2 * G, st>>>(x, HW, C, G, px, sums_workspace);
+    int rc = acb::launched();
+    if (rc) return rc;
+    gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(sums_workspace, B * G, (double)HW * (C / G), eps, stats);
+    return acb::launched();
+}
+
+int ac_sd_im2col_f16(const float* x, int B, int Hs, int Ws, int C, int ksize, int stride, int pad, int upsample2x, int Ho, int Wo,
+                     const float* gn_stats, const float* gn_gamma, const float* gn_beta, int gn_groups, int gn_silu, void* out, void* stream) {
+    if (!x || !out || B <= 0 || Hs <= 0 || Ws <= 0 || C <= 0 || Ho <= 0 || Wo <= 0 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2))
+        return AC_E_INVALID_ARG;
+    if (gn_stats && (!gn_gamma || !gn_beta || gn_groups <= 0 || C % gn_groups)) return AC_E_INVALID_ARG;
+    NormArgs nm; nm.stats = gn_stats; nm.gamma = gn_gamma; nm.beta = gn_beta; nm.G = gn_groups > 0 ? gn_groups : 1; nm.act = gn_silu;
+    const int Cp = (C + 7) / 8 * 8;
+    const long long total = (long long)B * Ho * Wo * ksize * ksize * (Cp / 8);
+    im2col_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, B, Hs, Ws, C, Cp, ksize, stride, pad, upsample2x, Ho, Wo, nm,
+                                                                             reinterpret_cast<__half*>(out));
+    return acb::launched();
+}
+
+int ac_sd_layer_norm_f16(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* out, void* stream) {
+    if (!x || !gamma || !beta || !out || M <= 0 || C <= 0) return AC_E_INVALID_ARG;
+    layer_norm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, M, C, gamma, beta, eps, reinterpret_cast<__half*>(out));
+    return acb::launched();
+}
+
+int ac_sd_geglu_f16(const float* x, int64_t M, int inner, void* out, void* stream) {
+    if (!x || !out || M <= 0 || inner <= 0) return AC_E_INVALID_ARG;
+    geglu_kernel<<<grid_for(M * inner, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, M, inner, reinterpret_cast<__half*>(out));
+    return acb::launched();
+}
+
+int ac_sd_softmax_f16(const float* scores, int64_t rows, int L, int64_t ld_in, int64_t ld_out, float scale, void* out, void* stream) {
+    if (!scores || !out || rows <= 0 || L <= 0 || ld_in < L || ld_out < L) return AC_E_INVALID_ARG;
+    const long long blocks = (rows + 7) / 8;
+    if (blocks > 0x7FFFFFFFll) return AC_E_INVALID_ARG;
+    softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, rows, L, ld_in, ld_out, scale, reinterpret_cast<__half*>(out));
+    return acb::launched();
+}
+
+int ac_sd_cast_f16(const float* x, int64_t n, void* out, void* stream) {
+    if (!x || !out || n <= 0) return AC_E_INVALID_ARG;
+    cast_f16_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<__half*>(out));
+    return acb::launched();
+}
+
+}  // extern "C"

@@ -6,10 +6,10 @@ this image, so this is a from-scratch restatement of the published architecture:
 names and shapes follow the diffusers checkpoints (`unet/diffusion_pytorch_model.*`, `vae/...`), so real weights
 load with `load_state_dict` when they are available.
 
-Every dense op goes through `sd_ops`: on a CUDA device under `torch.no_grad()` (the UNet forward of the SDS step is
-no-grad, models/diffusion.py:121-132) they run on the hand-written sm_100a kernels of libavatarcraft_b200.so
-(csrc/sd_ops.cu: fused GroupNorm+SiLU, LayerNorm, GEGLU, softmax, tcgen05 GEMM); when autograd is recording (the VAE
-encoder, whose input gradient IS the SDS gradient) they are torch ops, so the backward exists."""
+These modules hold the parameters and define the autograd / torch-op forward (`sd_ops`): the VAE encoder, whose input
+gradient IS the SDS gradient, needs a backward.  The no-grad UNet evaluation of the SDS step on a CUDA device does not
+run these forwards: `UNet2DConditionModel.forward` hands it to models/sd_native.py, the hand-written sm_100a kernels
+(csrc/sd_ops.cu: tcgen05 GEMMs fed by fused GroupNorm/SiLU/im2col, LayerNorm, GEGLU, softmax producers)."""
 import math
 
 import torch

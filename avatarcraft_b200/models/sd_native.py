@@ -1,0 +1,233 @@
+"""Native (sm_100a) forward of the Stable-Diffusion UNet for the SDS step: walks a `UNet2DConditionModel`'s parameters
+and evaluates it with the kernels of csrc/sd_ops.cu -- tcgen05 GEMMs fed by fused GroupNorm/SiLU/im2col, LayerNorm,
+GEGLU, softmax producers.  Same arithmetic graph as `UNet2DConditionModel.forward` (the autograd / torch-op path),
+with fp16 GEMM operands and fp32 accumulation; tests/test_gpu_sds.py compares the two on identical weights.
+
+Layout: activations are contiguous fp32 [B, H, W, C] (== the [B*H*W, C] token matrix); fp16 copies of the weights
+(conv kernels permuted to [N, ky, kx, C]) are cached per parameter and refreshed when the parameter's version changes.
+No fallback: every op raises if libavatarcraft_b200.so is missing or a tensor is not on a CUDA device."""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+from .sd_blocks import timestep_embedding
+
+_W16 = {}
+
+
+def _check(rc, what):
+    _lib.check(rc, what)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _w16(param, kind):
+    """fp16 GEMM operand of a weight: 'linear' [N,K]; 'conv1' [N,C,1,1] -> [N,C]; 'conv3' [N,C,3,3] -> [N,3,3,Cp]."""
+    key = (id(param), kind)
+    hit = _W16.get(key)
+    if hit is not None and hit[0] == (param.data_ptr(), param._version):
+        return hit[1]
+    w = param.detach()
+    if kind == "conv3":
+        N, C = w.shape[0], w.shape[1]
+        Cp = (C + 7) // 8 * 8
+        buf = torch.zeros(N, 3, 3, Cp, device=w.device, dtype=torch.float16)
+        buf[..., :C] = w.permute(0, 2, 3, 1)
+        w16 = buf.reshape(N, 9 * Cp)
+    elif kind == "conv1":
+        w16 = w.reshape(w.shape[0], w.shape[1]).to(torch.float16).contiguous()
+    else:
+        w16 = w.to(torch.float16).contiguous()
+    if w16.shape[1] % 8:                       # operand rows must be 16 B multiples
+        w16 = F.pad(w16, (0, 8 - w16.shape[1] % 8)).contiguous()
+    _W16[key] = ((param.data_ptr(), param._version), w16)
+    return w16
+
+
+def gemm(A16, W16, M, N, K, bias=None, group_bias=None, rows_per_group=0, residual=None, out_f16=False, out=None,
+         lda=None, ldw=None, ldc=None, batch=(1, 1), sA=(0, 0), sW=(0, 0), sC=(0, 0)):
+    """Thin wrapper of ac_sd_gemm_f16 (see include/avatarcraft_b200.h)."""
+    dev = A16.device
+    if out is None:
+        out = torch.empty(M, N, device=dev, dtype=torch.float16 if out_f16 else torch.float32)
+    lda = A16.stride(-2) if lda is None else lda
+    ldw = W16.stride(-2) if ldw is None else ldw
+    ldc = N if ldc is None else ldc
+    _check(_lib.lib().ac_sd_gemm_f16(_p(A16), _p(W16), _p(bias), _p(group_bias), int(rows_per_group), _p(residual), _p(out), int(out_f16),
+                                     int(M), int(N), int(K), int(lda), int(ldw), int(ldc), int(N if residual is not None else 0),
+                                     int(batch[0]), int(batch[1]), int(sA[0]), int(sA[1]), int(sW[0]), int(sW[1]), int(sC[0]), int(sC[1]),
+                                     _lib.stream_ptr()), "ac_sd_gemm_f16")
+    return out
+
+
+def cast16(x):
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    _check(_lib.lib().ac_sd_cast_f16(_p(x), x.numel(), _p(out), _lib.stream_ptr()), "ac_sd_cast_f16")
+    return out
+
+
+def gn_stats(x, groups, eps):
+    """x [B,H,W,C] fp32 -> stats [B,G,2] (mean, rstd)."""
+    B, H, W, C = x.shape
+    ws = torch.empty(2 * B * groups, device=x.device, dtype=torch.float64)
+    stats = torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
+    _check(_lib.lib().ac_sd_group_norm_stats(_p(x), B, H * W, C, groups, float(eps), _p(ws), _p(stats), _lib.stream_ptr()), "ac_sd_group_norm_stats")
+    return stats
+
+
+def im2col(x, ksize, stride=1, pad=0, up=False, Ho=None, Wo=None, norm=None):
+    """x [B,Hs,Ws,C] fp32 -> fp16 [B*Ho*Wo, k*k*Cp]; norm = (GroupNormAct module) applies GroupNorm(+SiLU) on the fly."""
+    B, Hs, Ws, C = x.shape
+    Hin, Win = (2 * Hs, 2 * Ws) if up else (Hs, Ws)
+    Ho = Hin if Ho is None else Ho
+    Wo = Win if Wo is None else Wo
+    Cp = (C + 7) // 8 * 8
+    out = torch.empty(B * Ho * Wo, ksize * ksize * Cp, device=x.device, dtype=torch.float16)
+    st = gam = bet = None
+    G = act = 0
+    if norm is not None:
+        st = gn_stats(x, norm.num_groups, norm.eps)
+        gam, bet, G, act = norm.weight.detach(), norm.bias.detach(), norm.num_groups, int(norm.act)
+    _check(_lib.lib().ac_sd_im2col_f16(_p(x), B, Hs, Ws, C, ksize, stride, pad, int(up), Ho, Wo, _p(st), _p(gam), _p(bet), G, act, _p(out),
+                                       _lib.stream_ptr()), "ac_sd_im2col_f16")
+    return out, Ho, Wo
+
+
+def conv(x, mod, norm=None, up=False, group_bias=None, residual=None):
+    """Conv2d module `mod` (1x1 or 3x3, stride 1/2, padding 0/1) on NHWC x, optionally fused with a preceding
+    GroupNorm(+SiLU), a nearest x2 up-sampling, a per-(batch, channel) bias and a residual add.  -> [B,Ho,Wo,N] fp32."""
+    B, Hs, Ws, C = x.shape
+    k, stride, pad = mod.kernel_size[0], mod.stride[0], mod.padding[0]
+    Hin, Win = (2 * Hs, 2 * Ws) if up else (Hs, Ws)
+    Ho = (Hin + 2 * pad - k) // stride + 1
+    Wo = (Win + 2 * pad - k) // stride + 1
+    A, Ho, Wo = im2col(x, k, stride, pad, up, Ho, Wo, norm)
+    W16 = _w16(mod.weight, "conv3" if k == 3 else "conv1")
+    N, K = mod.out_channels, A.shape[1]
+    res = None if residual is None else residual.reshape(-1, N)
+    out = gemm(A, W16, B * Ho * Wo, N, K, bias=None if mod.bias is None else mod.bias.detach(), group_bias=group_bias,
+               rows_per_group=Ho * Wo, residual=res)
+    return out.reshape(B, Ho, Wo, N)
+
+
+def linear(x16, mod, M, residual=None, out_f16=False):
+    """Linear module on an fp16 operand [M, K] -> [M, N]."""
+    W16 = _w16(mod.weight, "linear")
+    return gemm(x16, W16, M, mod.out_features, mod.in_features, bias=None if mod.bias is None else mod.bias.detach(), residual=residual,
+                out_f16=out_f16)
+
+
+def layer_norm16(x, mod):
+    M, C = x.shape
+    out = torch.empty(M, C, device=x.device, dtype=torch.float16)
+    _check(_lib.lib().ac_sd_layer_norm_f16(_p(x), M, C, _p(mod.weight.detach()), _p(mod.bias.detach()), float(mod.eps), _p(out), _lib.stream_ptr()),
+           "ac_sd_layer_norm_f16")
+    return out
+
+
+def attention(xq16, ctx16, attn, B, Lq, Lk, residual):
+    """Multi-head attention of module `attn` (to_q/to_k/to_v/to_out.0): xq16 [B*Lq, Cq] fp16, ctx16 [B*Lk, Cc] fp16
+    -> to_out(softmax(q k^T * scale) v) + residual, fp32 [B*Lq, Cq].  Two batched GEMMs around the softmax kernel; V is
+    produced already transposed ([B, inner, Lk]) by swapping the GEMM operands, so P V needs no transpose."""
+    dev = xq16.device
+    heads = attn.heads
+    inner = attn.to_q.out_features
+    d = inner // heads
+    Cc = ctx16.shape[1]
+    Lp = (Lk + 7) // 8 * 8
+    q = linear(xq16, attn.to_q, B * Lq, out_f16=True)                                   # [B*Lq, inner]
+    k = linear(ctx16, attn.to_k, B * Lk, out_f16=True)                                  # [B*Lk, inner]
+    vT = torch.zeros(B, inner, Lp, device=dev, dtype=torch.float16) if Lp != Lk else torch.empty(B, inner, Lp, device=dev, dtype=torch.float16)
+    gemm(_w16(attn.to_v.weight, "linear"), ctx16, inner, Lk, Cc, out_f16=True, out=vT, ldc=Lp, batch=(B, 1), sA=(0, 0), sW=(Lk * Cc, 0),
+         sC=(inner * Lp, 0))
+    scores = torch.empty(B, heads, Lq, Lp, device=dev, dtype=torch.float32)
+    gemm(q, k, Lq, Lk, d, out=scores, lda=inner, ldw=inner, ldc=Lp, batch=(B, heads), sA=(Lq * inner, d), sW=(Lk * inner, d),
+         sC=(heads * Lq * Lp, Lq * Lp))
+    probs = torch.empty(B, heads, Lq, Lp, device=dev, dtype=torch.float16)
+    _check(_lib.lib().ac_sd_softmax_f16(_p(scores), B * heads * Lq, Lk, Lp, Lp, float(attn.scale), _p(probs), _lib.stream_ptr()), "ac_sd_softmax_f16")
+    o16 = torch.empty(B * Lq, inner, device=dev, dtype=torch.float16)
+    gemm(probs, vT, Lq, d, Lk, out_f16=True, out=o16, lda=Lp, ldw=Lp, ldc=inner, batch=(B, heads), sA=(heads * Lq * Lp, Lq * Lp),
+         sW=(inner * Lp, d * Lp), sC=(Lq * inner, d))
+    return linear(o16, attn.to_out[0], B * Lq, residual=residual)
+
+
+def transformer(x, mod, ctx16, B_ctx_len):
+    """Transformer2DModel on NHWC x [B,H,W,C] -> same shape."""
+    B, H, W, C = x.shape
+    L, M = H * W, B * H * W
+    A, _, _ = im2col(x, 1, norm=mod.norm)                                            # GroupNorm (no act) -> fp16 [M, C]
+    pin = mod.proj_in
+    Wp = _w16(pin.weight, "linear" if mod.use_linear else "conv1")
+    h = gemm(A, Wp, M, Wp.shape[0], C, bias=pin.bias.detach())                           # [M, inner] fp32
+    for blk in mod.transformer_blocks:
+        n1 = layer_norm16(h, blk.norm1)
+        h = attention(n1, n1, blk.attn1, B, L, L, residual=h)
+        n2 = layer_norm16(h, blk.norm2)
+        h = attention(n2, ctx16, blk.attn2, B, L, B_ctx_len, residual=h)
+        n3 = layer_norm16(h, blk.norm3)
+        u = linear(n3, blk.ff.net[0].proj, M)                                            # [M, 8C] fp32
+        inner_ff = u.shape[1] // 2
+        g16 = torch.empty(M, inner_ff, device=x.device, dtype=torch.float16)
+        _check(_lib.lib().ac_sd_geglu_f16(_p(u), M, inner_ff, _p(g16), _lib.stream_ptr()), "ac_sd_geglu_f16")
+        h = linear(g16, blk.ff.net[2], M, residual=h)
+    pout = mod.proj_out
+    Wo = _w16(pout.weight, "linear" if mod.use_linear else "conv1")
+    out = gemm(cast16(h), Wo, M, C, h.shape[1], bias=pout.bias.detach(), residual=x.reshape(M, C))
+    return out.reshape(B, H, W, C)
+
+
+def resnet(x, mod, temb_act16):
+    """ResnetBlock2D on NHWC: conv1(silu(norm1 x)) + time projection -> conv2(silu(norm2 .)) + shortcut(x)."""
+    B = x.shape[0]
+    gb = None
+    if mod.time_emb_proj is not None and temb_act16 is not None:
+        gb = linear(temb_act16, mod.time_emb_proj, B)                                    # [B, Cout] fp32, added in conv1's epilogue
+    h = conv(x, mod.conv1, norm=mod.norm1, group_bias=gb)
+    sc = x if mod.conv_shortcut is None else conv(x, mod.conv_shortcut)
+    return conv(h, mod.conv2, norm=mod.norm2, residual=sc)
+
+
+@torch.no_grad()
+def unet_forward(unet, sample, timestep, encoder_hidden_states):
+    """UNet2DConditionModel.forward on the native kernels: sample [B,Cin,H,W] -> [B,Cout,H,W] fp32."""
+    if not sample.is_cuda:
+        raise RuntimeError("sd_native.unet_forward needs CUDA tensors (no CPU path)")
+    cfg = unet.config
+    B = sample.shape[0]
+    with torch.cuda.device(sample.device):
+        t = torch.as_tensor(timestep, device=sample.device).reshape(-1).expand(B)
+        emb16 = cast16(timestep_embedding(t, cfg.block_out_channels[0]))
+        te = unet.time_embedding
+        temb = linear(cast16(F.silu(linear(emb16, te.linear_1, B))), te.linear_2, B)
+        temb_act16 = cast16(F.silu(temb))
+        ctx = encoder_hidden_states.float().contiguous()
+        Lc = ctx.shape[1]
+        ctx16 = cast16(ctx.reshape(B * Lc, -1))
+        h = conv(sample.float().permute(0, 2, 3, 1).contiguous(), unet.conv_in)
+        skips = [h]
+        for blk in unet.down_blocks:
+            for j, res in enumerate(blk.resnets):
+                h = resnet(h, res, temb_act16)
+                if blk.attentions is not None:
+                    h = transformer(h, blk.attentions[j], ctx16, Lc)
+                skips.append(h)
+            if hasattr(blk, "downsamplers"):
+                h = conv(h, blk.downsamplers[0].conv)
+                skips.append(h)
+        h = resnet(h, unet.mid_block.resnets[0], temb_act16)
+        h = transformer(h, unet.mid_block.attentions[0], ctx16, Lc)
+        h = resnet(h, unet.mid_block.resnets[1], temb_act16)
+        for blk in unet.up_blocks:
+            for j, res in enumerate(blk.resnets):
+                h = resnet(torch.cat([h, skips.pop()], dim=-1), res, temb_act16)
+                if blk.attentions is not None:
+                    h = transformer(h, blk.attentions[j], ctx16, Lc)
+            if hasattr(blk, "upsamplers"):
+                h = conv(h, blk.upsamplers[0].conv, up=True)
+        out = conv(h, unet.conv_out, norm=unet.conv_norm_out)
+        return out.permute(0, 3, 1, 2).contiguous()

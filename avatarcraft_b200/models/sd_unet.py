@@ -110,12 +110,15 @@ class UNet2DConditionModel(nn.Module):
     def forward(self, sample, timestep, encoder_hidden_states):
         """sample [B,Cin,H,W], timestep scalar / [1] / [B], encoder_hidden_states [B,77,D] -> [B,Cout,H,W]
         (the reference reads `.sample` of diffusers' output object: see UNetOutput)."""
+        if sd_ops.use_native(sample):                           # no-grad CUDA call: the hand-written sm_100a kernels
+            from . import sd_native
+            return UNetOutput(sd_native.unet_forward(self, sample, timestep, encoder_hidden_states))
         B = sample.shape[0]
         t = torch.as_tensor(timestep, device=sample.device).reshape(-1).expand(B)
         temb = self.time_embedding(timestep_embedding(t, self.config.block_out_channels[0]).to(sample.dtype))
         temb_act = F.silu(temb)                                 # every resnet applies SiLU before its projection
         ctx = encoder_hidden_states
-        h = self.conv_in(sd_ops.to_activation_layout(sample))
+        h = self.conv_in(sample)
         skips = [h]
         for blk in self.down_blocks:
             for j, res in enumerate(blk.resnets):

@@ -270,6 +270,38 @@ int ac_iso_surface(const float *volume, const float *bound_min, const float *bou
                    float threshold, float *tri_pos, int64_t *tri_key, uint64_t capacity, uint64_t *counter,
                    void *stream);
 
+/* --------------------------------------------------------------------------------------
+ * Stable-Diffusion UNet forward for the SDS step (reference: models/diffusion.py:121-132 calls diffusers'
+ * UNet2DConditionModel under torch.no_grad(); third-party, parity unpinned).  Activations fp32 NHWC; GEMM operands
+ * fp16 (`void *` = __half), fp32 accumulation in TMEM.
+ * ac_sd_gemm_f16: C[M,N] = A[M,K] W[N,K]^T (+ bias[N]) (+ group_bias[m / rows_per_group][N]) (+ residual[M,N], row
+ *   stride ldr); C fp32 or fp16 (out_f16) with row stride ldc.  lda/ldw and the batch strides of A/W are multiples of
+ *   8 halves and the pointers 16 B aligned; M, N, K are arbitrary (tiles are zero-filled).  Batch index
+ *   z in [0, batch_outer*batch_inner): operand offsets (z / batch_inner) * s?o + (z % batch_inner) * s?i (elements).
+ * Producers of fp16 operands (all take fp32 inputs):
+ *   ac_sd_group_norm_stats  NHWC [B,HW,C] -> stats [B,G,2] = (mean, rstd); sums_workspace: 2*B*G doubles.
+ *   ac_sd_im2col_f16        NHWC [B,Hs,Ws,C] -> [B*Ho*Wo, k*k*Cp] (K index (ky*k+kx)*Cp + c, Cp = C rounded up to 8),
+ *                           k in {1,3}, stride in {1,2}, zero pad `pad` top/left, optional nearest x2 up-sampling of the
+ *                           source, optional GroupNorm(+SiLU) from `gn_stats` applied on the fly.
+ *   ac_sd_layer_norm_f16, ac_sd_geglu_f16 (value * gelu(gate), x [M, 2*inner]), ac_sd_softmax_f16 (softmax(scale * s)
+ *   over L columns, output row stride ld_out with zeroed padding), ac_sd_cast_f16.
+ * ------------------------------------------------------------------------------------ */
+int ac_sd_gemm_f16(const void *A, const void *W, const float *bias, const float *group_bias, int rows_per_group,
+                   const float *residual, void *C, int out_f16, int M, int N, int K, int64_t lda, int64_t ldw,
+                   int64_t ldc, int64_t ldr, int batch_outer, int batch_inner, int64_t sAo, int64_t sAi, int64_t sWo,
+                   int64_t sWi, int64_t sCo, int64_t sCi, void *stream);
+int ac_sd_group_norm_stats(const float *x, int B, int HW, int C, int G, float eps, double *sums_workspace, float *stats,
+                           void *stream);
+int ac_sd_im2col_f16(const float *x, int B, int Hs, int Ws, int C, int ksize, int stride, int pad, int upsample2x,
+                     int Ho, int Wo, const float *gn_stats, const float *gn_gamma, const float *gn_beta, int gn_groups,
+                     int gn_silu, void *out, void *stream);
+int ac_sd_layer_norm_f16(const float *x, int M, int C, const float *gamma, const float *beta, float eps, void *out,
+                         void *stream);
+int ac_sd_geglu_f16(const float *x, int64_t M, int inner, void *out, void *stream);
+int ac_sd_softmax_f16(const float *scores, int64_t rows, int L, int64_t ld_in, int64_t ld_out, float scale, void *out,
+                      void *stream);
+int ac_sd_cast_f16(const float *x, int64_t n, void *out, void *stream);
+
 /* Unit test of the tensor-core layer in isolation: feats [128,32] fp32 x (sdf layer 0 feature
  * columns)^T -> out [128,64] pre-activations WITHOUT bias / xyz terms (3xTF32 tcgen05.mma). */
 int ac_nsr_debug_tc_layer(const float *feats, const float *mlp_blob, float *out, void *stream);
