@@ -45,6 +45,7 @@ struct GemmParams {
     int batch_inner;
     long long sAo, sAi, sWo, sWi, sCo, sCi;
     int out_f16;
+    int splits;            // split-K slices (blockIdx.z, batch == 1 only): partial sums meet in fp32 atomics on a zeroed C
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
@@ -79,7 +80,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_kernel(const GemmParams 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + STAGES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int zo = blockIdx.z / p.batch_inner, zi = blockIdx.z % p.batch_inner;
+    const int split = p.splits > 1 ? (int)blockIdx.z : 0;
+    const int zb = p.splits > 1 ? 0 : (int)blockIdx.z;
+    const int zo = zb / p.batch_inner, zi = zb % p.batch_inner;
     const __half* A = p.A + zo * p.sAo + zi * p.sAi;
     const __half* W = p.W + zo * p.sWo + zi * p.sWi;
     const long long c_off = zo * p.sCo + zi * p.sCi;
@@ -95,11 +98,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_kernel(const GemmParams 
     const uint32_t tmem = *tmem_slot;
     const uint32_t smem_s = tc05::smem_u32(smem);
 
-    const int KT = (p.K + BK - 1) / BK;
+    const int KT_all = (p.K + BK - 1) / BK;
+    const int kt_begin = (int)((long long)KT_all * split / p.splits), kt_end = (int)((long long)KT_all * (split + 1) / p.splits);
+    const int KT = kt_end - kt_begin;                    // k-tiles of this CTA (>= 1: the host keeps splits <= KT_all)
+    const int kbase = kt_begin * BK;
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < KT) {
-            load_tile(smem_s + s * STAGE_BYTES, A, p.lda, p.M, p.K, m0, s * BK, warp, lane);
-            load_tile(smem_s + s * STAGE_BYTES + TILE_BYTES, W, p.ldw, p.N, p.K, n0, s * BK, warp, lane);
+            load_tile(smem_s + s * STAGE_BYTES, A, p.lda, p.M, p.K, m0, kbase + s * BK, warp, lane);
+            load_tile(smem_s + s * STAGE_BYTES + TILE_BYTES, W, p.ldw, p.N, p.K, n0, kbase + s * BK, warp, lane);
         }
         cp_async_commit();
     }
@@ -123,8 +129,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_kernel(const GemmParams 
         if (nk < KT) {
             if (kt >= 1) tc05::mbar_wait(free_bar + (kt - 1) % STAGES, (uint32_t)(((kt - 1) / STAGES) & 1));
             const int ns = nk % STAGES;
-            load_tile(smem_s + ns * STAGE_BYTES, A, p.lda, p.M, p.K, m0, nk * BK, warp, lane);
-            load_tile(smem_s + ns * STAGE_BYTES + TILE_BYTES, W, p.ldw, p.N, p.K, n0, nk * BK, warp, lane);
+            load_tile(smem_s + ns * STAGE_BYTES, A, p.lda, p.M, p.K, m0, kbase + nk * BK, warp, lane);
+            load_tile(smem_s + ns * STAGE_BYTES + TILE_BYTES, W, p.ldw, p.N, p.K, n0, kbase + nk * BK, warp, lane);
         }
         cp_async_commit();
     }
@@ -132,47 +138,66 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_kernel(const GemmParams 
     tc05::mbar_wait(free_bar + (KT - 1) % STAGES, (uint32_t)(((KT - 1) / STAGES) & 1));     // the last commit covers every MMA
     tc05::fence_after_sync();
 
-    // ---- epilogue: TMEM lane = output row; 16 columns per tcgen05.ld ----
-    const int row = m0 + warp * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const float* gb = (p.group_bias && row < p.M) ? p.group_bias + (long long)(row / p.rows_per_group) * p.N : nullptr;
-#pragma unroll 1
-    for (int q = 0; q < BN / 16; ++q) {
-        float acc[16];
-        tc05::tmem_ld16(trow + q * 16, acc);            // warp-collective: every lane executes it
-        const int n = n0 + q * 16;
-        if (row >= p.M || n >= p.N) continue;
-        const int nv = p.N - n < 16 ? p.N - n : 16;
+    // ---- epilogue ----
+    // TMEM lane = output row.  Rows are parked in shared memory (the operand ring is idle now; 132-float pitch keeps the
+    // 16-byte stores of a quarter-warp on distinct banks) so that the global side is row-contiguous: one warp instruction
+    // reads/writes 512 B of one output row (bias, per-row-group bias, residual and the store / split-K reduction).
+    float* stage = reinterpret_cast<float*>(smem);
+    constexpr int PITCH = BN + 4;
+    {
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        float* srow = stage + (warp * 32 + lane) * PITCH;
+#pragma unroll 2
+        for (int q = 0; q < BN / 16; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(trow + q * 16, acc);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (j < nv) {
-                float v = acc[j];
-                if (p.bias) v += p.bias[n + j];
-                if (gb) v += gb[n + j];
-                if (p.residual) v += p.residual[(long long)row * p.ldr + n + j];
-                acc[j] = v;
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(srow + q * 16)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+    }
+    __syncthreads();
+    const bool lead = split == 0;                        // split-K: the first slice carries bias / residual
+    const int n = n0 + lane * 4;
+    const int nv = p.N - n < 4 ? p.N - n : 4;            // valid columns of this lane's float4 (<= 0: none)
+    const bool vec_ok = nv == 4 && (p.ldc & 3) == 0 && (c_off & 3) == 0;
+    float bz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias && lead)
+        for (int j = 0; j < 4; ++j) if (j < nv) bz[j] = p.bias[n + j];
+#pragma unroll 1
+    for (int r = warp; r < BM; r += GEMM_THREADS / 32) {
+        const int row = m0 + r;
+        if (row >= p.M || nv <= 0) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stage + r * PITCH + lane * 4);
+        float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
+        if (lead && p.group_bias) {
+            const float* gb = p.group_bias + (long long)(row / p.rows_per_group) * p.N + n;
+            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += gb[j];
+        }
+        if (lead && p.residual) {
+            const float* rs = p.residual + (long long)row * p.ldr + n;
+            if (nv == 4 && (p.ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rs);
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            } else {
+                for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rs[j];
             }
         }
-        if (p.out_f16) {
-            __half* dst = reinterpret_cast<__half*>(p.C) + c_off + (long long)row * p.ldc + n;
-            if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                uint4 lo, hi;
-                lo.x = tc05::pack_f16x2(acc[0], acc[1]); lo.y = tc05::pack_f16x2(acc[2], acc[3]);
-                lo.z = tc05::pack_f16x2(acc[4], acc[5]); lo.w = tc05::pack_f16x2(acc[6], acc[7]);
-                hi.x = tc05::pack_f16x2(acc[8], acc[9]); hi.y = tc05::pack_f16x2(acc[10], acc[11]);
-                hi.z = tc05::pack_f16x2(acc[12], acc[13]); hi.w = tc05::pack_f16x2(acc[14], acc[15]);
-                reinterpret_cast<uint4*>(dst)[0] = lo; reinterpret_cast<uint4*>(dst)[1] = hi;
+        const long long at = c_off + (long long)row * p.ldc + n;
+        if (p.splits > 1) {
+            float* dst = reinterpret_cast<float*>(p.C) + at;
+            for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
+        } else if (p.out_f16) {
+            __half* dst = reinterpret_cast<__half*>(p.C) + at;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                uint2 o; o.x = tc05::pack_f16x2(v[0], v[1]); o.y = tc05::pack_f16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(dst) = o;
             } else {
-                for (int j = 0; j < nv; ++j) dst[j] = __float2half_rn(acc[j]);
+                for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = __float2half_rn(v[j]);
             }
         } else {
-            float* dst = reinterpret_cast<float*>(p.C) + c_off + (long long)row * p.ldc + n;
-            if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            } else {
-                for (int j = 0; j < nv; ++j) dst[j] = acc[j];
-            }
+            float* dst = reinterpret_cast<float*>(p.C) + at;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = v[j];
         }
     }
     tc05::fence_before_sync();
@@ -189,20 +214,22 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // so a warp reads consecutive channels of one pixel; per-channel partials fold into their group in shared memory and
 // leave through fp64 atomics: sums[b][g] = (sum, sum of squares).
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, int G, int px_per_block, double* __restrict__ sums) {
-    extern __shared__ double sh[];                      // [G][2]
+    extern __shared__ float shf[];                      // [C][2] per-channel partials of this block's pixels
     const int b = blockIdx.y, cpg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
-    __syncthreads();
     const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f, ss = 0.f;
         const float* col = x + ((long long)b * HW + p0) * C + c;
         for (int p = p0; p < p1; ++p, col += C) { const float v = *col; s += v; ss = fmaf(v, v, ss); }
-        atomicAdd(&sh[2 * (c / cpg)], (double)s);
-        atomicAdd(&sh[2 * (c / cpg) + 1], (double)ss);
+        shf[2 * c] = s; shf[2 * c + 1] = ss;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(long long)b * 2 * G + i], sh[i]);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s = 0.0, ss = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += (double)shf[2 * c]; ss += (double)shf[2 * c + 1]; }
+        atomicAdd(&sums[((long long)b * G + g) * 2], s);
+        atomicAdd(&sums[((long long)b * G + g) * 2 + 1], ss);
+    }
 }
 
 // (sum, sumsq) -> (mean, rstd), in place as floats: stats[b][g] = (mean, rstd).
@@ -366,6 +393,20 @@ int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float*
     p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.batch_inner = batch_inner;
     p.sAo = sAo; p.sAi = sAi; p.sWo = sWo; p.sWi = sWi; p.sCo = sCo; p.sCi = sCi; p.out_f16 = out_f16;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch_outer * batch_inner);
+    // Split-K when the output tiles alone cannot fill the machine (weight-streaming GEMMs: a handful of tiles, K in the
+    // thousands): about two CTAs per SM, at least 4 k-tiles each; fp32 outputs only (partials meet in atomics).
+    p.splits = 1;
+    const long long tiles = (long long)grid.x * grid.y, KT_all = (K + BK - 1) / BK;
+    if (grid.z == 1 && !out_f16 && tiles < acb::sm_count() && KT_all >= 8) {
+        long long want = (2LL * acb::sm_count() + tiles - 1) / tiles;
+        if (want > KT_all / 4) want = KT_all / 4;
+        if (want > 1) {
+            p.splits = (int)want;
+            grid.z = (unsigned)want;
+            if (ldc == N) { if (cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream) != cudaSuccess) return acb::cuda_fail(); }
+            else { if (cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, (cudaStream_t)stream) != cudaSuccess) return acb::cuda_fail(); }
+        }
+    }
     if (grid.y > 65535 || grid.z > 65535) return AC_E_INVALID_ARG;
     sd_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(p);
     return acb::launched();
@@ -375,9 +416,9 @@ int ac_sd_group_norm_stats(const float* x, int B, int HW, int C, int G, float ep
     if (!x || !sums_workspace || !stats || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) return AC_E_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * B * G, st) != cudaSuccess) return acb::cuda_fail();
-    const int px = 64;
+    const int px = HW >= 2048 ? 32 : (HW >= 256 ? 8 : 2);     // enough blocks to fill the machine at every resolution
     dim3 grid((HW + px - 1) / px, B);
-    gn_stats_kernel<<<grid, 256, sizeof(double) * 2 * G, st>>>(x, HW, C, G, px, sums_workspace);
+    gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(x, HW, C, G, px, sums_workspace);
     int rc = acb::launched();
     if (rc) return rc;
     gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(sums_workspace, B * G, (double)HW * (C / G), eps, stats);
