@@ -90,12 +90,16 @@ class StableDiffusion(nn.Module):
         if version not in ("1.5", "2.0"):
             raise ValueError("sd_version must be '1.5' or '2.0' (models/diffusion.py:45-49)")
         cfg = unet_config or (UNetConfig.sd2_depth() if self.use_depth else UNetConfig.sd15())
-        with torch.random.fork_rng(devices=[]):
-            torch.manual_seed(seed)                          # random-init networks are reproducible across ranks
+        on_cuda = self.device.type == "cuda"
+        # modules are created (and randomly initialised) directly on the target device: 0.94 G parameters take seconds
+        # on the GPU and most of a minute on the host; the seed makes the random networks identical on every rank
+        with torch.random.fork_rng(devices=[self.device] if on_cuda else []), torch.device(self.device):
+            torch.manual_seed(seed)
             self.vae = vae if vae is not None else AutoencoderKL()
             self.unet = unet if unet is not None else UNet2DConditionModel(cfg)
             self.text_encoder = text_encoder if text_encoder is not None else HashTextEncoder(cfg.cross_attention_dim)
         self.tokenizer = tokenizer
+        self.cfg_parallel = True                             # multi-GPU: split the classifier-free-guidance pair over ranks
         if weights_dir is not None:
             self._load_diffusers_dir(weights_dir)
         self.to(self.device)
@@ -143,11 +147,24 @@ class StableDiffusion(nn.Module):
         """grad = clamp(w(t) (eps_cfg - noise), -1, 1) with w = 1 - abar_t (:121-146); no autograd."""
         with torch.no_grad():
             latents_noisy = self.scheduler.add_noise(latents, noise, t)
-            latent_model_input = torch.cat([latents_noisy] * 2)
-            if self.use_depth and pred_depth is not None:
-                latent_model_input = torch.cat([latent_model_input, pred_depth], dim=1)
-            noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=text_embeddings).sample
-            noise_pred_uncond, noise_pred_text = noise_pred.chunk(2)
+            import torch.distributed as dist
+            if self.cfg_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() >= 2:
+                # the (uncond, text) pair is the one piece of the SD step that shards (SURVEY.md 8e): even ranks evaluate
+                # the unconditional half, odd ranks the text half, one all-gather of the [1,4,64,64] prediction (64 KB)
+                half = dist.get_rank() % 2
+                x = latents_noisy
+                if self.use_depth and pred_depth is not None:
+                    x = torch.cat([x, pred_depth[:1]], dim=1)
+                mine = self.unet(x, t, encoder_hidden_states=text_embeddings[half:half + 1]).sample.contiguous()
+                parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+                dist.all_gather(parts, mine)
+                noise_pred_uncond, noise_pred_text = parts[0], parts[1]
+            else:
+                latent_model_input = torch.cat([latents_noisy] * 2)
+                if self.use_depth and pred_depth is not None:
+                    latent_model_input = torch.cat([latent_model_input, pred_depth], dim=1)
+                noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=text_embeddings).sample
+                noise_pred_uncond, noise_pred_text = noise_pred.chunk(2)
             noise_pred = noise_pred_uncond + guidance_scale * (noise_pred_text - noise_pred_uncond)
             w = 1 - self.alphas[t]
             return (w * (noise_pred - noise)).clamp(-1, 1)
@@ -166,6 +183,17 @@ class StableDiffusion(nn.Module):
         noise = torch.randn_like(latents)
         grad = self.sds_latent_gradient(latents.detach(), text_embeddings, t, noise, guidance_scale, pred_depth)
         latents.backward(gradient=grad, retain_graph=True)
+
+    def pixel_gradient(self, text_embeddings, rgb_rows, h, w, guidance_scale=100, seed=None):
+        """Trainer-facing form of the step (stylize.py:120-131): rgb_rows [h*w,3] (the no-grad pass-1 render) ->
+        d(SDS)/d(rgb) [h*w,3].  `seed` makes the step's random draws (t, posterior sample, noise) identical on every
+        rank of a multi-GPU job, so replicated VAE work agrees bit for bit and no broadcast is needed."""
+        if seed is not None:
+            torch.manual_seed(int(seed))
+        img = rgb_rows.detach().reshape(1, h, w, 3).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        with torch.enable_grad():
+            self.mannual_backward(text_embeddings, img, guidance_scale)
+        return img.grad[0].permute(1, 2, 0).reshape(h * w, 3).contiguous()
 
     def calc_grad(self, text_embeddings, pred_rgb: torch.Tensor, guidance_scale=100) -> torch.Tensor:
         """Same step, returning d(SDS)/d(pred_rgb) as a tensor (:154-216)."""

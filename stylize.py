@@ -4,10 +4,13 @@ avatarcraft_b200: per view, pass 1 renders the (sub-sampled) image without gradi
 into a pixel gradient, pass 2 re-renders 4096-ray patches with gradients and back-propagates pixel gradient +
 eikonal + opacity-vs-frozen-copy, ONE gradient all-reduce (multi-GPU), Adam(lr 5e-3).
 
-The Stable-Diffusion SDS guidance (models/diffusion.py:92-149) is third-party code + weights that are not available
-offline; `--guidance` selects a stand-in with the same interface ([1,3,h,w] image -> d(loss)/d(image)):
+`--guidance` selects what turns the pass-1 image into a pixel gradient:
+  sds      score distillation through avatarcraft_b200.models.diffusion.StableDiffusion (models/diffusion.py:92-149):
+           VAE encode with gradient, UNet on the native tcgen05 kernels, classifier-free guidance.  The HF weights are
+           not available offline: `--sd_weights <diffusers dir>` loads them, otherwise the networks are random-init
+           (right cost, meaningless images)
   target   pulls the render towards a fixed colour tint (deterministic, for smoke tests)
-  randn    unit Gaussian pixel gradient (the bench's stand-in)
+  randn    unit Gaussian pixel gradient
 Launch with torchrun for multi-GPU: patches are sharded across ranks.
 
     python stylize.py --synthetic --exp_name demo --n_views 4 --coarse_epochs 1 --fine_epochs 0
@@ -48,7 +51,11 @@ def main():
     ap.add_argument("--batch_size", type=int, default=4096)
     ap.add_argument("--w_eikonal", type=float, default=0.01)
     ap.add_argument("--use_opacity", type=int, default=1)
-    ap.add_argument("--guidance", type=str, default="target", choices=["target", "randn"])
+    ap.add_argument("--guidance", type=str, default="target", choices=["target", "randn", "sds"])
+    ap.add_argument("--prompt", type=str, default="a 3D rendering of a knight in bronze armour")
+    ap.add_argument("--sd_version", type=str, default="1.5", choices=["1.5", "2.0"])
+    ap.add_argument("--sd_weights", type=str, default=None, help="diffusers-format directory (unet/, vae/); random init when absent")
+    ap.add_argument("--guidance_scale", type=float, default=100.0)
     ap.add_argument("--i_save", type=int, default=1000)
     ap.add_argument("--lr", type=float, default=5e-3)
     ap.add_argument("--resume", type=str, default=None, help="a *.pth.tar written by this script (its .resume.pt is picked up)")
@@ -66,6 +73,11 @@ def main():
         p.requires_grad_(False)
     # Adam(lr 5e-3) + StepLR(epochs//2, 0.5) (stylize.py:355-363) on flat buffers: one all-reduce + one update launch
     optimizer = FlatAdam(net_style.parameters(), lr=opt.lr)
+    sd_guide = text_emb = None
+    if opt.guidance == "sds":                                                  # stylize.py:340-352 setup_loss + :100 text embeds
+        from avatarcraft_b200.models.diffusion import StableDiffusion
+        sd_guide = StableDiffusion("cuda", opt.sd_version, weights_dir=opt.sd_weights)
+        text_emb = sd_guide.get_text_embeds(opt.prompt)
     out_dir = os.path.join("style", "canonical_360", opt.exp_name)
     os.makedirs(out_dir, exist_ok=True)
     H, W, step, first_epoch = opt.render_h, opt.render_w, 0, 0
@@ -85,8 +97,11 @@ def main():
             h, w = H // stride, W // stride
             with torch.no_grad():                                                                # pass 1 (stylize.py:115)
                 rgb, _ = render_utils.render_instantnsr_naive(net_style, o, d, opt.batch_size, render_can=True, perturb=True)
-            g = guidance(opt.guidance, rgb.reshape(h, w, 3).permute(2, 0, 1)[None], step)        # [1,3,h,w]
-            pixel_grad = g[0].permute(1, 2, 0).reshape(-1, 3).contiguous()
+            if sd_guide is not None:                                                             # SDS (models/diffusion.py:92-149)
+                pixel_grad = sd_guide.pixel_gradient(text_emb, rgb, h, w, opt.guidance_scale, seed=1_000_003 * (epoch + 1) + step)
+            else:
+                g = guidance(opt.guidance, rgb.reshape(h, w, 3).permute(2, 0, 1)[None], step)    # [1,3,h,w]
+                pixel_grad = g[0].permute(1, 2, 0).reshape(-1, 3).contiguous()
             stats = stylize_patch_step(net_style, net_gt, optimizer, o, d, pixel_grad, batch_size=opt.batch_size,
                                        w_eikonal=opt.w_eikonal, use_opacity=bool(opt.use_opacity), rank=rank, world=world)
             step += 1

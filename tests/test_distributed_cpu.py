@@ -68,3 +68,43 @@ def test_two_rank_patch_step_equals_single_process(n, bs):
         assert reduced == sum(p.numel() for p in model.parameters())
         # relative to the largest entry; (600, 600) = ONE patch split over both ranks with mean_scale 1/2 each
         assert err < 1e-5, (rank, err)
+
+
+def _cfg_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from avatarcraft_b200.models import diffusion, sd_vae
+    from tests.test_sds_cpu import _StubUNet
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    sd = diffusion.StableDiffusion("cpu", "1.5", unet=_StubUNet(), vae=sd_vae.AutoencoderKL.tiny(), text_encoder=diffusion.HashTextEncoder(32))
+    emb = torch.stack([torch.full((77, 32), 0.2), torch.full((77, 32), 0.5)])
+    rgb = torch.rand(16 * 16, 3, generator=torch.Generator().manual_seed(5))
+    g = sd.pixel_gradient(emb, rgb, 16, 16, guidance_scale=100, seed=11)
+    q.put((rank, g))
+    dist.destroy_process_group()
+
+
+def test_cfg_pair_split_over_two_ranks_equals_single_process():
+    """the SD step does not shard by rays; the (uncond, text) UNet pair does.  Two gloo ranks, each
+    evaluating one half + one all-gather, must reproduce the single-process pixel gradient bit for bit."""
+    import torch
+    import torch.multiprocessing as mp
+    from avatarcraft_b200.models import diffusion, sd_vae
+    from tests.test_sds_cpu import _StubUNet
+    torch.manual_seed(0)
+    sd = diffusion.StableDiffusion("cpu", "1.5", unet=_StubUNet(), vae=sd_vae.AutoencoderKL.tiny(), text_encoder=diffusion.HashTextEncoder(32))
+    emb = torch.stack([torch.full((77, 32), 0.2), torch.full((77, 32), 0.5)])
+    rgb = torch.rand(16 * 16, 3, generator=torch.Generator().manual_seed(5))
+    want = sd.pixel_gradient(emb, rgb, 16, 16, guidance_scale=100, seed=11)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_cfg_worker, args=(r, 2, 29571, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+    assert torch.equal(got[0], got[1]) and torch.allclose(got[0], want, atol=1e-7) and float(want.abs().max()) > 0
