@@ -57,24 +57,26 @@ class _SdfQuery(torch.autograd.Function):
         gout = gout.contiguous().float()
         f32 = dict(device=dev, dtype=torch.float32)
         grad_table = torch.zeros(ctx.emb_shape, **f32)
-        delta = torch.empty(64, B, **f32); hid = torch.empty(64, B, **f32); feats = torch.empty(35, B, **f32)   # unit-major
+        delta = torch.empty(64, B, **f32); hid = torch.empty(64, B, **f32); feats = torch.empty(36, B, **f32)    # unit-major
         m = net._device_model()
         _lib.check(_lib.lib().ac_nsr_sdf_backward(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound,
                                                   _lib.ptr(grad_table), _lib.ptr(delta), _lib.ptr(hid), _lib.ptr(feats),
                                                   _lib.stream_ptr()), "ac_nsr_sdf_backward")
-        # Weight gradients: four skinny GEMMs with K = number of points (3.7 M per 4096-ray patch).  They run as
-        # TF32 tensor-core GEMMs (fp32 accumulate): each is a sum over millions of points, so the 2^-11 operand
-        # rounding averages out (measured: gradients still within 0.5 % of the fp32 oracle elementwise), and the
-        # fp32 SIMT sgemm they replace cost 5.3 ms of a 21 ms step.  (The reference's pinned torch 1.8 ran ALL its
-        # nn.Linear GEMMs in TF32 on A100, environment.yml:17.)
+        # Weight gradients: two skinny GEMMs with K = number of points (3.7 M per 4096-ray patch).  They run as TF32
+        # tensor-core GEMMs (fp32 accumulate): each entry is a sum over millions of points, so the 2^-11 operand
+        # rounding averages out (gradients within 0.5 % of the fp32 oracle elementwise), and the fp32 SIMT sgemm they
+        # replace cost 5.3 ms of a 21 ms step.  (The reference's pinned torch 1.8 ran ALL its nn.Linear GEMMs in TF32 on
+        # A100, environment.yml:17.)  bf16 operands were measured too: 1.8 ms faster per patch, but 2 % error on the bias
+        # gradients (their terms cancel) -- rejected.  The ones row of `feats` yields db0 from the same GEMM.
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
         try:
-            gw0 = delta @ feats.t()                      # [64,35]: feats rows are (x, y, z, 32 hash features)
+            gw0b = delta @ feats.t()                     # [64,36] = [dW0 | db0]
             gw1 = (hid @ gout).t()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
-        return None, grad_table, gw0, delta.sum(1), gw1, gout.sum(0), None, None
+        gw0, gb0 = gw0b[:, :35].contiguous(), gw0b[:, 35].contiguous()
+        return None, grad_table, gw0, gb0, gw1, gout.sum(0), None, None
 
 
 class SingleVarianceNetwork(nn.Module):

@@ -57,3 +57,19 @@ def allreduce_gradients(params, group=None) -> int:
         at += n
     assert flat.device == dev
     return flat.numel()
+
+
+def render_rays_sharded(render_fn, rays_o, rays_d, rank: int, world: int, group=None):
+    """Pass 1 of a multi-GPU step: every rank renders its contiguous block of rays with `render_fn(o, d) -> rgb [m,3]`
+    and the blocks are exchanged with ONE all-gather (12 B per ray), so each rank holds the whole image for the
+    guidance.  Rays are independent (no cross-ray term in `run`), so the result equals the single-process render."""
+    n = rays_o.shape[0]
+    if world <= 1 or not (dist.is_available() and dist.is_initialized()):
+        return render_fn(rays_o, rays_d)
+    if n % world:
+        raise ValueError("render_rays_sharded needs n_rays divisible by the world size")
+    s, e = shard_rays(n, rank, world)
+    mine = render_fn(rays_o[s:e], rays_d[s:e]).contiguous()
+    full = torch.empty(n, mine.shape[1], device=mine.device, dtype=mine.dtype)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full

@@ -235,10 +235,12 @@ def run_ours(args):
     try:
         if os.environ.get("AC_BENCH_SKIP_SDS"):          # profiling runs (ncu) only want the render launches
             raise RuntimeError("skipped (AC_BENCH_SKIP_SDS)")
-        sds = measure_train(10, 3, world, rank, dev)
-        sds = {k: sds[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches")}
-        full = measure_train(5, 3, world, rank, dev, sd_guidance=True)
-        sds["with_sd_guidance"] = {k: full[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "gpu_launches")}
+        full = measure_train(3, 3, world, rank, dev, sd_guidance=True)       # BASELINE.json configs[2] with the guidance in the loop
+        sds = {k: full[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches")}
+        nerf = measure_train(3, 3, world, rank, dev)                          # the same step with a stand-in pixel gradient
+        sds["nerf_side_only"] = {k: nerf[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches")}
+        c = measure_train(10, 3, world, rank, dev, coarse=True)               # coarse stage (one 4096-ray patch), stand-in gradient
+        sds["coarse_stage_nerf_side_only"] = {k: c[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches")}
     except Exception as e:           # never lose the headline line to the secondary workload
         sds = {"metric": "sds_style_steps_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
     torch.set_grad_enabled(False)
@@ -284,11 +286,14 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_train(steps, warmup, world, rank, dev, sd_guidance=False):
-    """Secondary workload (BASELINE.json configs[2]): one stylisation optimiser step on 4096 rays (the
-    coarse stage of stylize.py): pass 1 no-grad render, pass 2 patch re-render with gradients + eikonal +
-    opacity vs a frozen copy, ONE in-place gradient all-reduce, ONE flat Adam launch.  The SDS pixel gradient is randn
-    (seed 44): the Stable-Diffusion guidance is un-vendored third-party code with weights that are not available offline.
+def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=False):
+    """Secondary workload (BASELINE.json configs[2]): one stylisation optimiser step of stylize.py on a 256x256 view =
+    65 536 rays = 16 patches of batch_size 4096 (or, `coarse`, the stride-4 sub-sampled view = one patch):
+    pass 1 no-grad render (ray-sharded + one all-gather), the pixel gradient, pass 2 patch re-renders with gradients +
+    eikonal + opacity vs a frozen copy (patch-sharded), ONE in-place gradient all-reduce, ONE flat Adam launch.
+    `sd_guidance`: the pixel gradient comes from the SDS guidance (SD-1.5-shaped UNet on the native tcgen05 path + VAE
+    encoder forward/backward; random weights -- the HF checkpoints are not available offline); otherwise a fixed randn
+    tensor stands in and the number is the NeRF side of the step alone.
     Returns the JSON dict (process group must already exist when world > 1)."""
     import torch
     import torch.distributed as dist
@@ -304,8 +309,12 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False):
     for p in gt.parameters():
         p.requires_grad_(False)
     opt = FlatAdam(net.parameters(), lr=5e-3)
+    from avatarcraft_b200.utils.distributed import render_rays_sharded
     o, d = frame_rays(0)
-    o, d = o.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3).to(dev), d.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3).to(dev)   # stride-4 = 4096 rays
+    side = 64 if coarse else 256
+    if coarse:            # coarse stage of stylize.py: the 256x256 view sub-sampled with stride 4 = ONE 4096-ray patch
+        o, d = o.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3), d.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3)
+    o, d = o.contiguous().to(dev), d.contiguous().to(dev)      # fine stage (BASELINE.json configs[2]): 65 536 rays = 16 patches of 4096
     G = torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(44)).to(dev)
     torch.manual_seed(1000 + rank)
     sd = emb = None
@@ -316,12 +325,13 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False):
     count = [0]
 
     def step():
-        with torch.no_grad():
-            rgb, _ = render_instantnsr_naive(net, o, d, rays_per_batch=4096, render_can=True, perturb=True)   # pass 1
+        with torch.no_grad():                                                                            # pass 1, ray-sharded + one all-gather
+            rgb = render_rays_sharded(lambda a, b: render_instantnsr_naive(net, a, b, rays_per_batch=4096, render_can=True, perturb=True)[0],
+                                      o, d, rank, world)
         g = G
         if sd is not None:
             count[0] += 1
-            g = sd.pixel_gradient(emb, rgb, 64, 64, 100.0, seed=77 + count[0])                            # SDS (models/diffusion.py:92-149)
+            g = sd.pixel_gradient(emb, rgb, side, side, 100.0, seed=77 + count[0])                        # SDS (models/diffusion.py:92-149)
         with torch.enable_grad():
             stylize_patch_step(net, gt, opt, o, d, g, batch_size=4096, rank=rank, world=world)           # pass 2 + allreduce + Adam
 
@@ -342,11 +352,13 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False):
     return {"metric": "sds_style_steps_per_sec", "value": steps / (float(ms) * 1e-3), "unit": "steps/s", "n_gpus": world,
             "steps": steps, "warmup": max(warmup, 3), "ms_per_step": float(ms) / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "stylize.py coarse-stage step: 4096 rays (256x256 stride 4), 64+64 samples, pass1 + pass2 "
+            "config": {"workload": ("stylize.py coarse-stage step: 4096 rays (256x256 stride 4)" if coarse else
+                                    "stylize.py step on a 256x256 view: 65 536 rays = 16 patches of batch_size 4096") + ", 64+64 samples, pass1 + pass2 "
                                    "(grad, eikonal 0.01, opacity vs frozen copy) + grad all-reduce + Adam; pixel gradient " +
                                    ("from the SDS guidance: SD-1.5-shaped UNet (859.5 M params, random init, native tcgen05 forward on the "
                                     "(uncond, text) pair) + VAE encoder forward/backward at 512x512" if sd_guidance else "randn seed 44 (guidance excluded)"),
-                       "parallelism": f"patch/ray shard x{world} + one 49 MB all-reduce"},
+                       "parallelism": f"pass 1 ray-sharded + all-gather, pass 2 patch-sharded x{world}, one 49 MB gradient all-reduce, "
+                                      "SD guidance: classifier-free pair split over ranks, VAE replicated"},
             "gpu_launches": int(_lib.lib().ac_launch_count() - l0)}
 
 
@@ -357,7 +369,7 @@ def run_train(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    line = measure_train(args.steps, args.warmup, world, rank, torch.device("cuda", local), sd_guidance=args.sd_guidance)
+    line = measure_train(args.steps, args.warmup, world, rank, torch.device("cuda", local), sd_guidance=args.sd_guidance, coarse=args.coarse)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -371,6 +383,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="render", choices=["render", "train"])
+    ap.add_argument("--coarse", action="store_true", help="--workload train: the coarse stage (one 4096-ray patch) instead of the 256x256 view")
     ap.add_argument("--sd_guidance", action="store_true", help="--workload train: put the SD UNet + VAE guidance inside the step")
     args = ap.parse_args()
     if args.workload == "train" and args.impl == "ours":

@@ -108,10 +108,11 @@ int ac_nsr_forward_sdf(const ac_nsr_model *model, const float *x, float *out, ui
  * hash-table gradient into grad_table [n_entries,2] (caller zeroes; fp32 reductions as in
  * kernel_grid_backward, hashencoder.cu:223-308) and writes the per-point layer terms from which
  * the host forms the weight gradients with plain GEMMs:
- *   delta_a [64,B] = dL/d(hidden pre-activation), hidden [64,B] = softplus output, feats [35,B] = the layer's
- *   input rows (x, y, z, 32 hash features)  (unit-major, so the kernel's stores are coalesced and the host GEMMs
- *   read K-contiguous operands)
- *   => dW0 = delta_a feats^T, db0 = row sums of delta_a, dW1 = grad_out^T hidden^T, db1 = sum grad_out. */
+ *   delta_a [64,B] = dL/d(hidden pre-activation), hidden [64,B] = softplus output, feats [36,B] = the layer's
+ *   input rows (x, y, z, 32 hash features, 1), fp32, unit-major (so the kernel's stores are coalesced and the host
+ *   GEMMs read K-contiguous operands)
+ *   => [dW0 | db0] = delta_a feats^T  ([64,36]: the ones row yields the bias gradient), dW1 = (hidden grad_out)^T,
+ *   db1 = column sums of grad_out. */
 int ac_nsr_sdf_backward(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B,
                         float bound, float *grad_table, float *delta_a, float *hidden, float *feats,
                         void *stream);

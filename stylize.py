@@ -26,6 +26,7 @@ from avatarcraft_b200.utils import render_utils, synthetic
 from avatarcraft_b200.utils.camera_paths import default_360_path, rays_for_pose
 from avatarcraft_b200.utils.constant import CANONICAL_CAMERA_DIST_TRAIN, NSR_BOUND
 from avatarcraft_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+from avatarcraft_b200.utils.distributed import render_rays_sharded
 from avatarcraft_b200.utils.optim import FlatAdam
 from avatarcraft_b200.utils.train_utils import stylize_patch_step
 
@@ -95,8 +96,9 @@ def main():
             o, d = rays_for_pose(poses[vi], W, H, "cuda")
             o, d = o.reshape(H, W, 3)[::stride, ::stride].reshape(-1, 3).contiguous(), d.reshape(H, W, 3)[::stride, ::stride].reshape(-1, 3).contiguous()
             h, w = H // stride, W // stride
-            with torch.no_grad():                                                                # pass 1 (stylize.py:115)
-                rgb, _ = render_utils.render_instantnsr_naive(net_style, o, d, opt.batch_size, render_can=True, perturb=True)
+            with torch.no_grad():                                                                # pass 1 (stylize.py:115), ray-sharded
+                fn = lambda a, b: render_utils.render_instantnsr_naive(net_style, a, b, opt.batch_size, render_can=True, perturb=True)[0]
+                rgb = render_rays_sharded(fn, o, d, rank, world) if o.shape[0] % world == 0 else fn(o, d)
             if sd_guide is not None:                                                             # SDS (models/diffusion.py:92-149)
                 pixel_grad = sd_guide.pixel_gradient(text_emb, rgb, h, w, opt.guidance_scale, seed=1_000_003 * (epoch + 1) + step)
             else:
