@@ -15,10 +15,12 @@
 //                       GroupNorm -> fp16, LayerNorm -> fp16, GEGLU -> fp16, softmax -> fp16, plain cast.
 //
 // HBM traffic is irrelevant at these sizes (the largest activation is 10 MB); the GEMMs are L2-bandwidth / tensor bound.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/avatarcraft_b200.h"
 #include "launch_util.cuh"
@@ -32,7 +34,7 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand per stage
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 64;    // + barriers + TMEM slot
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 128;   // + barriers + TMEM slot
 constexpr int GEMM_THREADS = 128;
 
 struct GemmParams {
@@ -71,6 +73,72 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const __half* __restrict
         if (row >= rows) bytes = 0;
         const __half* src = bytes > 0 ? base + (long long)row * ld + k : base;
         cp_async_16(dst + c * 2048 + r * 16, src, bytes);
+    }
+}
+
+// Epilogue shared by both main loops.  TMEM lane = output row.  Rows are parked in shared memory (the operand ring is
+// idle now; 132-float pitch keeps the 16-byte stores of a quarter-warp on distinct banks) so that the global side is
+// row-contiguous: one warp instruction reads/writes 512 B of one output row (bias, per-row-group bias, residual and the
+// store / split-K reduction).
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, unsigned char* smem, uint32_t tmem, int m0, int n0, long long c_off, int split,
+                                              int warp, int lane) {
+    float* stage = reinterpret_cast<float*>(smem);
+    constexpr int PITCH = BN + 4;
+    {
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        float* srow = stage + (warp * 32 + lane) * PITCH;
+#pragma unroll 2
+        for (int q = 0; q < BN / 16; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(trow + q * 16, acc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(srow + q * 16)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+    }
+    __syncthreads();
+    const bool lead = split == 0;                        // split-K: the first slice carries bias / residual
+    const int n = n0 + lane * 4;
+    const int nv = p.N - n < 4 ? p.N - n : 4;            // valid columns of this lane's float4 (<= 0: none)
+    const bool vec_ok = nv == 4 && (p.ldc & 3) == 0 && (c_off & 3) == 0;
+    float bz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias && lead)
+        for (int j = 0; j < 4; ++j) if (j < nv) bz[j] = p.bias[n + j];
+#pragma unroll 1
+    for (int r = warp; r < BM; r += GEMM_THREADS / 32) {
+        const int row = m0 + r;
+        if (row >= p.M || nv <= 0) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stage + r * PITCH + lane * 4);
+        float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
+        if (lead && p.group_bias) {
+            const float* gb = p.group_bias + (long long)(row / p.rows_per_group) * p.N + n;
+            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += gb[j];
+        }
+        if (lead && p.residual) {
+            const float* rs = p.residual + (long long)row * p.ldr + n;
+            if (nv == 4 && (p.ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rs);
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            } else {
+                for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rs[j];
+            }
+        }
+        const long long at = c_off + (long long)row * p.ldc + n;
+        if (p.splits > 1) {
+            float* dst = reinterpret_cast<float*>(p.C) + at;
+            for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
+        } else if (p.out_f16) {
+            __half* dst = reinterpret_cast<__half*>(p.C) + at;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                uint2 o; o.x = tc05::pack_f16x2(v[0], v[1]); o.y = tc05::pack_f16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(dst) = o;
+            } else {
+                for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = __float2half_rn(v[j]);
+            }
+        } else {
+            float* dst = reinterpret_cast<float*>(p.C) + at;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = v[j];
+        }
     }
 }
 
@@ -138,71 +206,121 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_kernel(const GemmParams 
     tc05::mbar_wait(free_bar + (KT - 1) % STAGES, (uint32_t)(((KT - 1) / STAGES) & 1));     // the last commit covers every MMA
     tc05::fence_after_sync();
 
-    // ---- epilogue ----
-    // TMEM lane = output row.  Rows are parked in shared memory (the operand ring is idle now; 132-float pitch keeps the
-    // 16-byte stores of a quarter-warp on distinct banks) so that the global side is row-contiguous: one warp instruction
-    // reads/writes 512 B of one output row (bias, per-row-group bias, residual and the store / split-K reduction).
-    float* stage = reinterpret_cast<float*>(smem);
-    constexpr int PITCH = BN + 4;
-    {
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        float* srow = stage + (warp * 32 + lane) * PITCH;
-#pragma unroll 2
-        for (int q = 0; q < BN / 16; ++q) {
-            float acc[16];
-            tc05::tmem_ld16(trow + q * 16, acc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(srow + q * 16)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-    }
-    __syncthreads();
-    const bool lead = split == 0;                        // split-K: the first slice carries bias / residual
-    const int n = n0 + lane * 4;
-    const int nv = p.N - n < 4 ? p.N - n : 4;            // valid columns of this lane's float4 (<= 0: none)
-    const bool vec_ok = nv == 4 && (p.ldc & 3) == 0 && (c_off & 3) == 0;
-    float bz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.bias && lead)
-        for (int j = 0; j < 4; ++j) if (j < nv) bz[j] = p.bias[n + j];
-#pragma unroll 1
-    for (int r = warp; r < BM; r += GEMM_THREADS / 32) {
-        const int row = m0 + r;
-        if (row >= p.M || nv <= 0) continue;
-        const float4 a4 = *reinterpret_cast<const float4*>(stage + r * PITCH + lane * 4);
-        float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
-        if (lead && p.group_bias) {
-            const float* gb = p.group_bias + (long long)(row / p.rows_per_group) * p.N + n;
-            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += gb[j];
-        }
-        if (lead && p.residual) {
-            const float* rs = p.residual + (long long)row * p.ldr + n;
-            if (nv == 4 && (p.ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rs);
-                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-            } else {
-                for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rs[j];
-            }
-        }
-        const long long at = c_off + (long long)row * p.ldc + n;
-        if (p.splits > 1) {
-            float* dst = reinterpret_cast<float*>(p.C) + at;
-            for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
-        } else if (p.out_f16) {
-            __half* dst = reinterpret_cast<__half*>(p.C) + at;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-                uint2 o; o.x = tc05::pack_f16x2(v[0], v[1]); o.y = tc05::pack_f16x2(v[2], v[3]);
-                *reinterpret_cast<uint2*>(dst) = o;
-            } else {
-                for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = __float2half_rn(v[j]);
-            }
-        } else {
-            float* dst = reinterpret_cast<float*>(p.C) + at;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            else for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = v[j];
-        }
-    }
+    gemm_epilogue(p, smem, tmem, m0, n0, c_off, split, warp, lane);
     tc05::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc05::tmem_dealloc<BN>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA main loop (default).  The cp.async ring above keeps the LSU / L1 data pipe 70 % busy moving operands (ncu r01i);
+// here one elected thread issues `cp.async.bulk.tensor` 4-D tile loads (128 rows x 64 halves, SWIZZLE_128B, out-of-bounds
+// rows / columns zero-filled by the TMA unit) that complete on a per-stage "full" mbarrier, a second elected thread
+// issues the tcgen05.mma's on SWIZZLE_128B K-major descriptors and releases stages through tcgen05.commit -> "empty"
+// mbarrier: no __syncthreads and no LSU traffic in the loop.  Tensor dims: (K, rows, batch_inner, batch_outer).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc05::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(tc05::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// K-major SWIZZLE_128B operand tile (rows of 128 B, 8-row groups 1024 B apart, 1024 B aligned base).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                                   const GemmParams p, const int a_zi, const int a_zo, const int w_zi, const int w_zo) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* done_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int split = p.splits > 1 ? (int)blockIdx.z : 0;
+    const int zb = p.splits > 1 ? 0 : (int)blockIdx.z;
+    const int zo = zb / p.batch_inner, zi = zb % p.batch_inner;
+    const long long c_off = zo * p.sCo + zi * p.sCi;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { tc05::mbar_init(full_bar + s, 1); tc05::mbar_init(empty_bar + s, 1); }
+        tc05::mbar_init(done_bar, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc<BN>(tmem_slot);
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t smem_s = tc05::smem_u32(smem);
+
+    const int KT_all = (p.K + BK - 1) / BK;
+    const int kt_begin = (int)((long long)KT_all * split / p.splits), kt_end = (int)((long long)KT_all * (split + 1) / p.splits);
+    const int KT = kt_end - kt_begin;
+
+    if (warp == 0 && lane == 0) {                       // ---- TMA producer ----
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            if (kt >= STAGES) tc05::mbar_wait(empty_bar + s, (uint32_t)(((kt / STAGES) - 1) & 1));
+            mbar_expect_tx(full_bar + s, STAGE_BYTES);
+            const int k0 = (kt_begin + kt) * BK;
+            tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, k0, m0, a_zi ? zi : 0, a_zo ? zo : 0);
+            tma_load_4d(smem_s + s * STAGE_BYTES + TILE_BYTES, &tmW, full_bar + s, k0, n0, w_zi ? zi : 0, w_zo ? zo : 0);
+        }
+    } else if (warp == 1 && lane == 0) {                // ---- MMA issuer ----
+        constexpr uint32_t idesc = tc05::idesc_f16(BM, BN);
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            tc05::mbar_wait(full_bar + s, (uint32_t)((kt / STAGES) & 1));
+            tc05::fence_after_sync();
+            const uint64_t da = smem_desc_sw128(smem_s + s * STAGE_BYTES), db = smem_desc_sw128(smem_s + s * STAGE_BYTES + TILE_BYTES);
+#pragma unroll
+            for (uint32_t k4 = 0; k4 < BK / 16; ++k4)   // +32 B along K inside the 128 B swizzle atom = +2 in the address field
+                tc05::mma_f16(tmem, da + 2ull * k4, db + 2ull * k4, idesc, (kt | (int)k4) != 0 ? 1u : 0u);
+            tc05::mma_commit(empty_bar + s);
+        }
+        tc05::mma_commit(done_bar);
+    }
+    __syncwarp();
+    tc05::mbar_wait(done_bar, 0u);
+    tc05::fence_after_sync();
+    __syncthreads();                                     // every warp has seen the last MMA complete before the ring is reused
+    gemm_epilogue(p, smem, tmem, m0, n0, c_off, split, warp, lane);
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<BN>(tmem);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+// fp16 [bo][bi][rows][K] view with element strides (ld, s_i, s_o); a zero batch stride (operand shared by the batch)
+// collapses that dimension (the kernel then always asks for coordinate 0).  Returns false if the driver refuses.
+inline bool make_operand_map(CUtensorMap* map, const void* base, int K, int rows, long long ld, int bi, long long s_i, int bo, long long s_o,
+                             int* use_zi, int* use_zo) {
+    *use_zi = (bi > 1 && s_i != 0) ? 1 : 0;
+    *use_zo = (bo > 1 && s_o != 0) ? 1 : 0;
+    const cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(*use_zi ? bi : 1), (cuuint64_t)(*use_zo ? bo : 1)};
+    const cuuint64_t row_bytes = (cuuint64_t)ld * 2;
+    const cuuint64_t strides[3] = {row_bytes, *use_zi ? (cuuint64_t)s_i * 2 : row_bytes, *use_zo ? (cuuint64_t)s_o * 2 : row_bytes};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)BM, 1u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -408,7 +526,19 @@ int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float*
         }
     }
     if (grid.y > 65535 || grid.z > 65535) return AC_E_INVALID_ARG;
-    sd_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(p);
+    static const bool use_cp_async = [] { const char* e = getenv("AC_SD_GEMM"); return e && e[0] == 'c'; }();   // A/B switch: AC_SD_GEMM=cpasync
+    if (use_cp_async) {
+        sd_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(p);
+        return acb::launched();
+    }
+    static bool attr2 = false;
+    if (!attr2) { cudaFuncSetAttribute(sd_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr2 = true; }
+    CUtensorMap tmA, tmW;
+    int a_zi, a_zo, w_zi, w_zo;
+    if (!make_operand_map(&tmA, A, K, M, lda, batch_inner, sAi, batch_outer, sAo, &a_zi, &a_zo) ||
+        !make_operand_map(&tmW, W, K, N, ldw, batch_inner, sWi, batch_outer, sWo, &w_zi, &w_zo))
+        return AC_E_UNSUPPORTED;                         // no silent fallback: the caller sees the failure
+    sd_gemm_tma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p, a_zi, a_zo, w_zi, w_zo);
     return acb::launched();
 }
 

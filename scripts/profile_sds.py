@@ -25,7 +25,7 @@ with torch.no_grad():
         unet(x, t, encoder_hidden_states=emb)
         torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=10, max_name_column_width=60))
-ev = sorted([e for e in prof.events() if "sd_gemm_kernel" in e.name], key=lambda e: e.time_range.start)
+ev = sorted([e for e in prof.events() if "sd_gemm" in e.name], key=lambda e: e.time_range.start)
 assert len(ev) == len(shapes), (len(ev), len(shapes))
 census = collections.OrderedDict()
 for s, e in zip(shapes, ev):
