@@ -1,0 +1,227 @@
+// nsr_train_tc.cu -- fused backward of NeRFNetwork.forward_sdf with the weight gradients on the tensor cores (sm_100a).
+//
+// The first backward kernel (nsr_kernels.cu: sdf_backward_kernel) writes three per-point layer terms (delta_a [64,B],
+// hidden [64,B], feats [36,B] = 2.4 GB per 4096-ray patch) that two cuBLAS GEMMs then reduce over the 3.7 M points.
+// Here the reduction happens where the terms are produced:
+//
+//   per 128 points (one 4-warp group, thread = point):
+//     A [128 x 128pts] fp16 = rows 0..63  delta_j * s_d        (dL/d hidden pre-activation, scaled into fp16 range)
+//                             rows 64..127 hidden_j
+//     B [ 64 x 128pts] fp16 = rows 0..35  layer input (x, y, z, 32 hash features, 1), rows 36..47 zero,
+//                             rows 48..63 grad_out_o * s_g
+//     D [128 x 64] (TMEM, fp32) += A B^T         8 x tcgen05.mma.kind::f16 M128 N64 K16, K = the 128 points
+//   D[0..63][0..35]   = sum_pts delta_j in_i  = s_d [dW0 | db0]        (the ones row of the input gives the bias gradient)
+//   D[64..127][48..63] = sum_pts hidden_j g_o = s_g dW1^T              (the other two quadrants are never read)
+//
+// The accumulator stays in TMEM for the whole persistent loop; each group adds its 3 328 useful entries to the global
+// gradients once, at the end.  Operand precision: fp16 (11 significant bits, the class of the TF32 GEMMs this replaces),
+// products exact in fp32, fp32 accumulation; the power-of-two scales s_d, s_g (device scalars computed by the caller from
+// max|grad_out| and the layer-1 weights, no host sync) keep delta and grad_out inside the fp16 range whatever the loss
+// scale is (the trainer multiplies one loss term by 1e5, stylize.py:190).
+// Table scatter, forward recompute and arithmetic are those of sdf_backward_kernel.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/avatarcraft_b200.h"
+#include "launch_util.cuh"
+#include "nsr_device.cuh"
+#include "tc05.cuh"
+
+using namespace acb;
+
+namespace {
+
+constexpr int kGroupsT = 4;                              // 4-warp groups per CTA (512 threads, one CTA per SM)
+constexpr int kThreadsT = 128 * kGroupsT;
+constexpr int kMlpFloats = OFF_C0;                       // W0 [64][36] | B0 [64] | W1T [64][16] | B1 [16] -- all this kernel reads
+constexpr uint32_t A_BYTES = 128 * 128 * 2, B_BYTES = 64 * 128 * 2;
+constexpr size_t T_SW = 0;
+constexpr size_t T_LV = T_SW + kMlpFloats * sizeof(float);
+constexpr size_t T_W0F = (T_LV + kLevels * sizeof(LevelMeta) + 15) / 16 * 16;
+constexpr size_t T_TILES = (T_W0F + 64 * 32 * sizeof(float) + 1023) / 1024 * 1024;
+constexpr size_t T_BARS = T_TILES + (size_t)kGroupsT * (A_BYTES + B_BYTES);
+constexpr size_t T_TOTAL = T_BARS + kGroupsT * 8 + 16;
+static_assert(T_TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(kMlpFloats % 4 == 0, "float4 staging");
+
+// element (row r, point k) of a K-major no-swizzle tile with `rows` rows: 16-byte chunk k/8 at (k/8)*rows*16 + r*16
+__device__ __forceinline__ void put(unsigned char* tile, int rows, int r, int k, float v) {
+    *reinterpret_cast<__half*>(tile + (k >> 3) * rows * 16 + r * 16 + (k & 7) * 2) = __float2half_rn(v);
+}
+
+__global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                                       const float* __restrict__ blob, float S, uint32_t H,
+                                                                       const float* __restrict__ x, const float* __restrict__ gout, uint32_t B,
+                                                                       float bound, const float* __restrict__ scales, float* __restrict__ grad_table,
+                                                                       float* __restrict__ grad_w0b, float* __restrict__ grad_w1) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sw = reinterpret_cast<float*>(smem + T_SW);
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + T_LV);
+    float* w0f = reinterpret_cast<float*>(smem + T_W0F);          // [64][32] feature columns of W0, 16 B aligned rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T_BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroupsT);
+    const int tid = threadIdx.x, warp = tid >> 5, group = warp >> 2, k = tid & 127;     // k = this thread's column (point) in its group's tiles
+    unsigned char* At = smem + T_TILES + (size_t)group * (A_BYTES + B_BYTES);
+    unsigned char* Bt = At + A_BYTES;
+
+    for (int i = tid; i < kMlpFloats / 4; i += blockDim.x) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(blob) + i);
+    for (int i = tid; i < 64 * 32; i += blockDim.x) w0f[i] = __ldg(blob + OFF_W0 + (i >> 5) * kSdfInPad + 3 + (i & 31));
+    if (tid < kLevels) lv[tid] = make_level_meta(offsets, tid, S, H, 3);
+    if (tid == 0) {
+        for (int g = 0; g < kGroupsT; ++g) tc05::mbar_init(bars + g, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc<64 * kGroupsT>(tmem_slot);
+    // rows 36..47 of B never change: zero them once (rows 0..35 and 48..63 are rewritten every round)
+    for (int r = 36; r < 48; ++r) put(Bt, 64, r, k, 0.f);
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem = *tmem_slot + (uint32_t)group * 64u;      // this group's 64 accumulator columns
+    const uint32_t a_s = tc05::smem_u32(At), b_s = tc05::smem_u32(Bt);
+    const float s_d = scales[0], s_g = scales[1];
+    uint32_t phase = 0;
+    bool pending = false;
+
+    for (uint32_t base = blockIdx.x * kThreadsT; base < B; base += gridDim.x * kThreadsT) {     // uniform trip count per CTA
+        const uint32_t b = base + tid;
+        const bool valid = b < B;
+        float in[kSdfInPad];
+        float g[16];
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (valid) {
+            px = x[3 * (size_t)b]; py = x[3 * (size_t)b + 1]; pz = x[3 * (size_t)b + 2];
+            encode_point(table, lv, bound, px, py, pz, in);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(gout + 16 * (size_t)b + 4 * q);
+                g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kSdfInPad; ++q) in[q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) g[q] = 0.f;
+        }
+        if (pending) {                                   // the previous round's MMAs have consumed the tiles
+            tc05::mbar_wait(bars + group, phase);
+            phase ^= 1u;
+            pending = false;
+        }
+        float din[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) din[q] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < kHidden; ++j) {
+            const float4* __restrict__ wr = reinterpret_cast<const float4*>(sw + OFF_W0 + j * kSdfInPad);
+            float a = sw[OFF_B0 + j];
+#pragma unroll
+            for (int q = 0; q < kSdfInPad / 4; ++q) {
+                const float4 w4 = wr[q];
+                a = fmaf(w4.x, in[4 * q + 0], a); a = fmaf(w4.y, in[4 * q + 1], a);
+                a = fmaf(w4.z, in[4 * q + 2], a); a = fmaf(w4.w, in[4 * q + 3], a);
+            }
+            const float h = softplus100(a);
+            const float4* __restrict__ w1 = reinterpret_cast<const float4*>(sw + OFF_W1T + j * 16);
+            float dh = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = w1[q];
+                dh = fmaf(w4.x, g[4 * q], dh); dh = fmaf(w4.y, g[4 * q + 1], dh);
+                dh = fmaf(w4.z, g[4 * q + 2], dh); dh = fmaf(w4.w, g[4 * q + 3], dh);
+            }
+            const float da = a * 100.0f > 20.0f ? dh : dh * sigmoidf(a * 100.0f);
+            put(At, 128, j, k, valid ? da * s_d : 0.f);
+            put(At, 128, 64 + j, k, valid ? h : 0.f);
+            const float4* __restrict__ wf = reinterpret_cast<const float4*>(w0f + j * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 w4 = wf[q];
+                din[4 * q + 0] = fmaf(w4.x, da, din[4 * q + 0]); din[4 * q + 1] = fmaf(w4.y, da, din[4 * q + 1]);
+                din[4 * q + 2] = fmaf(w4.z, da, din[4 * q + 2]); din[4 * q + 3] = fmaf(w4.w, da, din[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 35; ++q) put(Bt, 64, q, k, in[q]);
+        put(Bt, 64, 35, k, valid ? 1.0f : 0.f);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) put(Bt, 64, 48 + q, k, g[q] * s_g);
+        // hand the tiles to the tensor core: D += A B^T over this round's 128 points
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_sync();
+        tc05::named_bar_sync(1 + group, 128);
+        if (k == 0) {
+            tc05::fence_after_sync();
+            constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
+#pragma unroll
+            for (uint32_t s = 0; s < 8; ++s)             // K = 128 points = 8 x (K = 16): chunks 2s, 2s+1
+                tc05::mma_f16(tmem, tc05::smem_desc(a_s + s * 4096u, 2048u, 128u), tc05::smem_desc(b_s + s * 2048u, 1024u, 128u),
+                              idesc, (base != blockIdx.x * kThreadsT || s != 0) ? 1u : 0u);
+            tc05::mma_commit(bars + group);
+        }
+        pending = true;
+        if (!valid) continue;
+        // scatter into the table (same arithmetic as kernel_grid_backward, hashencoder.cu:223-308)
+        const float two_b = 2.0f * bound;
+        const float u = (px + bound) / two_b, v = (py + bound) / two_b, w = (pz + bound) / two_b;
+        if ((u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f)) continue;
+#pragma unroll
+        for (int l = 0; l < kLevels; ++l) {
+            const LevelMeta m = lv[l];
+            float fx = fmaf(u, m.scale, 0.5f), fy = fmaf(v, m.scale, 0.5f), fz = fmaf(w, m.scale, 0.5f);
+            const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+            const uint32_t ix = (uint32_t)flx, iy = (uint32_t)fly, iz = (uint32_t)flz;
+            fx -= flx; fy -= fly; fz -= flz;
+            float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
+            const float gx = din[2 * l], gy = din[2 * l + 1];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t cx = ix + (c & 1), cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
+                uint32_t slot;
+                if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
+                else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
+                const float wgt = (((c & 1) ? fx : 1.0f - fx) * ((c & 2) ? fy : 1.0f - fy)) * ((c & 4) ? fz : 1.0f - fz);
+                atomicAdd(dst + slot, make_float2(wgt * gx, wgt * gy));
+            }
+        }
+    }
+    // ---- flush this group's accumulator: row = TMEM lane = unit ----
+    if (pending) tc05::mbar_wait(bars + group, phase);
+    tc05::fence_after_sync();
+    if (blockIdx.x * kThreadsT < B) {                    // CTAs without work never issued an MMA: nothing to add
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int r = k;                                 // 0..127
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(trow + q * 16, acc);
+            if (r < 64) {                                // [dW0 | db0] * s_d: columns 0..35
+                for (int c = 0; c < 16; ++c) { const int col = q * 16 + c; if (col < 36) atomicAdd(grad_w0b + r * 36 + col, acc[c]); }
+            } else if (q == 3) {                         // dW1^T * s_g: columns 48..63 -> grad_w1[o][j]
+                for (int c = 0; c < 16; ++c) atomicAdd(grad_w1 + c * 64 + (r - 64), acc[c]);
+            }
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<64 * kGroupsT>(*tmem_slot);
+}
+
+}  // namespace
+
+extern "C" int ac_nsr_sdf_backward_fused(const ac_nsr_model* m, const float* x, const float* grad_out, uint32_t B, float bound,
+                                         const float* scales, float* grad_table, float* grad_w0b, float* grad_w1, void* stream) {
+    if (!m || !m->embeddings || !m->offsets || !m->mlp_blob || !x || !grad_out || !scales || !grad_table || !grad_w0b || !grad_w1)
+        return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sdf_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_TOTAL); attr = true; }
+    const uint32_t want = (B + kThreadsT - 1) / kThreadsT;
+    const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
+    sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, grad_out, B,
+        bound, scales, grad_table, grad_w0b, grad_w1);
+    return acb::launched();
+}

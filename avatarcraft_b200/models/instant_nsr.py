@@ -9,6 +9,7 @@ What differs from the reference, by design:
 State-dict keys/shapes are identical, so reference checkpoints load as is.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -57,24 +58,36 @@ class _SdfQuery(torch.autograd.Function):
         gout = gout.contiguous().float()
         f32 = dict(device=dev, dtype=torch.float32)
         grad_table = torch.zeros(ctx.emb_shape, **f32)
-        delta = torch.empty(64, B, **f32); hid = torch.empty(64, B, **f32); feats = torch.empty(36, B, **f32)    # unit-major
         m = net._device_model()
-        _lib.check(_lib.lib().ac_nsr_sdf_backward(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound,
-                                                  _lib.ptr(grad_table), _lib.ptr(delta), _lib.ptr(hid), _lib.ptr(feats),
-                                                  _lib.stream_ptr()), "ac_nsr_sdf_backward")
-        # Weight gradients: two skinny GEMMs with K = number of points (3.7 M per 4096-ray patch).  They run as TF32
-        # tensor-core GEMMs (fp32 accumulate): each entry is a sum over millions of points, so the 2^-11 operand
-        # rounding averages out (gradients within 0.5 % of the fp32 oracle elementwise), and the fp32 SIMT sgemm they
-        # replace cost 5.3 ms of a 21 ms step.  (The reference's pinned torch 1.8 ran ALL its nn.Linear GEMMs in TF32 on
-        # A100, environment.yml:17.)  bf16 operands were measured too: 1.8 ms faster per patch, but 2 % error on the bias
-        # gradients (their terms cancel) -- rejected.  The ones row of `feats` yields db0 from the same GEMM.
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            gw0b = delta @ feats.t()                     # [64,36] = [dW0 | db0]
-            gw1 = (hid @ gout).t()
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        if os.environ.get("AC_TRAIN_IMPL", "") == "terms":          # A/B: per-point layer terms + two TF32 GEMMs (the first version)
+            delta = torch.empty(64, B, **f32); hid = torch.empty(64, B, **f32); feats = torch.empty(36, B, **f32)    # unit-major
+            _lib.check(_lib.lib().ac_nsr_sdf_backward(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound,
+                                                      _lib.ptr(grad_table), _lib.ptr(delta), _lib.ptr(hid), _lib.ptr(feats),
+                                                      _lib.stream_ptr()), "ac_nsr_sdf_backward")
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                gw0b = delta @ feats.t()                     # [64,36] = [dW0 | db0]
+                gw1 = (hid @ gout).t()
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        else:
+            # Weight gradients reduced inside the kernel on the tensor cores (fp16 operands, fp32 accumulation in TMEM over
+            # the persistent loop): no per-point layer terms (2.4 GB per patch) and no GEMM launches.  The power-of-two
+            # scales keep delta / grad_out inside the fp16 range whatever the loss scale (stylize.py:190 multiplies one term
+            # by 1e5); they are device scalars, so nothing synchronises.
+            w1 = torch._weight_norm(net.sdf_net[1].weight_v.detach(), net.sdf_net[1].weight_g.detach(), 0)
+            gmax = gout.abs().amax().clamp_min(1e-30)
+            c1 = w1.abs().sum(0).amax().clamp_min(1e-30)
+            e_g = torch.floor(torch.log2(30000.0 / gmax)).clamp(-100.0, 100.0)
+            e_d = torch.floor(torch.log2(30000.0 / (gmax * c1))).clamp(-100.0, 100.0)
+            scales = torch.exp2(torch.stack([e_d, e_g])).float().contiguous()
+            acc0 = torch.zeros(64, 36, **f32); acc1 = torch.zeros(16, 64, **f32)
+            _lib.check(_lib.lib().ac_nsr_sdf_backward_fused(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound, _lib.ptr(scales),
+                                                            _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.stream_ptr()),
+                       "ac_nsr_sdf_backward_fused")
+            gw0b = acc0 / scales[0]
+            gw1 = acc1 / scales[1]
         gw0, gb0 = gw0b[:, :35].contiguous(), gw0b[:, 35].contiguous()
         return None, grad_table, gw0, gb0, gw1, gout.sum(0), None, None
 

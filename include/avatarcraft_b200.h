@@ -116,6 +116,13 @@ int ac_nsr_forward_sdf(const ac_nsr_model *model, const float *x, float *out, ui
 int ac_nsr_sdf_backward(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B,
                         float bound, float *grad_table, float *delta_a, float *hidden, float *feats,
                         void *stream);
+/* Same backward with the weight gradients reduced in the kernel (tcgen05, accumulators in TMEM across the persistent
+ * loop) instead of written out as per-point terms: grad_w0b [64,36] += s_d * [dW0 | db0], grad_w1 [16,64] += s_g * dW1
+ * (both accumulated into; caller zeroes), grad_table as above.  scales: DEVICE pointer to (s_d, s_g), powers of two that
+ * bring delta and grad_out into the fp16 range of the tensor-core operands: any s_d <= 30000 / (max|grad_out| *
+ * max_j sum_o |W1[o][j]|) and s_g <= 30000 / max|grad_out|; the caller divides the results by them. */
+int ac_nsr_sdf_backward_fused(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B, float bound,
+                              const float *scales, float *grad_table, float *grad_w0b, float *grad_w1, void *stream);
 /* NeRFNetwork.forward_color (models/instant_nsr.py:644-663, use_viewdirs=False):
  * x [B,3], normal [B,3], geo_feat [B,15] -> rgb [B,3]. */
 int ac_nsr_forward_color(const ac_nsr_model *model, const float *x, const float *normal,
