@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __rest
 }
 
 }  // namespace
-namespace acb { int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStream_t st); }
+namespace acb {
+int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStream_t st);
+int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st);
+}
 namespace {
 
 int grid_for(uint32_t B, int block, int per_sm) {
@@ -522,6 +525,9 @@ static int check_model(const ac_nsr_model* m) {
 int ac_nsr_forward_sdf(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, void* stream) {
     if (check_model(m) || !x || !out) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
+    // Tensor-core kernel for anything but tiny batches (AC_SDF_IMPL=simt keeps the fp32 SIMT kernel for A/B debugging).
+    static const bool use_simt = [] { const char* e = getenv("AC_SDF_IMPL"); return e && e[0] == 's'; }();
+    if (!use_simt && B >= 4096) return acb::launch_forward_sdf_tc(m, x, out, B, bound, (cudaStream_t)stream);
     if (int rc = refresh_c_sdf(m->mlp_blob, (cudaStream_t)stream)) return rc;
     forward_sdf_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->log2_per_level_scale,

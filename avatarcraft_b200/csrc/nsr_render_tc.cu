@@ -568,6 +568,64 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     if (warp == 0) tc05::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// NeRFNetwork.forward_sdf on a flat point list with the same tensor-core group machinery as the render kernel
+// (thread = point, four warps = one 128-row MMA tile): 3.7 M points per training patch, 2x the SIMT kernel's rate.
+// Staging is the render kernel's prologue restricted to what the SDF network needs.
+__global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                                          const float* __restrict__ blob, float S, uint32_t H,
+                                                                          const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
+    unsigned char* bt = smem + SM_B;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroups);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, group = warp >> 2;
+    if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(offsets, threadIdx.x, S, H, 3);
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x)
+        stage_b_tile(bt + B_W0_HI, bt + B_W0_LO, i >> 5, i & 31, __ldg(blob + OFF_W0 + (i >> 5) * kSdfInPad + 3 + (i & 31)));
+    if (threadIdx.x == 0) {
+        for (int gI = 0; gI < kGroups; ++gI) tc05::mbar_init(bars + gI, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc<kTmemCols>(tmem_slot);
+    tc05::fence_proxy_async_smem();
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    Group g;
+    g.a = smem + SM_A + (size_t)group * 16384;
+    g.a_s = tc05::smem_u32(g.a);
+    g.b_s = tc05::smem_u32(bt);
+    g.bar = bars + group;
+    g.phase = 0;
+    g.row = (warp & 3) * 32 + lane;
+    g.tmem = tmem_base + (uint32_t)group * 64u + ((uint32_t)((warp & 3) * 32) << 16);
+    g.bar_id = 1 + group;
+    {
+        bool ok = true;
+        for (int l = 0; l < kLevels; ++l) ok = ok && (lv[l].hashed == (l < 5 ? 0u : 1u));
+        g.std_layout = ok;
+    }
+    const uint32_t per_cta = kGroups * 128;
+    for (uint32_t base = blockIdx.x * per_cta; base < B; base += gridDim.x * per_cta) {      // uniform trip count per CTA
+        const uint32_t b = base + threadIdx.x;
+        const bool valid = b < B;
+        const uint32_t bb = valid ? b : B - 1;           // padding threads re-evaluate the last point (every thread joins the MMA round)
+        const float px = x[3 * (size_t)bb], py = x[3 * (size_t)bb + 1], pz = x[3 * (size_t)bb + 2];
+        float o16[16];
+        group_sdf_eval<true>(g, table, lv, bound, px, py, pz, o16);
+        if (valid) {
+            float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)b);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 // Unit-test kernel for the tensor-core layer alone: feats [128,32] (fp32) x W0[:,3:35]^T -> acc [128,64] (fp16x3).
 __global__ void __launch_bounds__(128, 1) debug_tc_layer_kernel(const float* __restrict__ feats, const float* __restrict__ blob,
                                                                 float* __restrict__ out) {
@@ -628,6 +686,21 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
     const uint32_t want = (n_quads + kGroups - 1) / kGroups;
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
     nsr_render_tc_kernel<<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p);
+    return acb::launched();
+}
+}  // namespace acb
+
+namespace acb {
+int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(forward_sdf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); attr = true; }
+    if (cudaMemcpyToSymbolAsync(c_w, m->mlp_blob + OFF_EPI, EPI_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return acb::cuda_fail();
+    const uint32_t per_cta = kGroups * 128;
+    const uint32_t want = (B + per_cta - 1) / per_cta;
+    const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
+    forward_sdf_tc_kernel<<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob,
+                                                                  m->log2_per_level_scale, m->base_resolution, x, out, B, bound);
     return acb::launched();
 }
 }  // namespace acb
