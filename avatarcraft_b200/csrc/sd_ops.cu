@@ -461,22 +461,53 @@ __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ x,
 }
 
 // Row softmax of scale * scores: fp32 [rows, L] (row stride ld_in) -> fp16 [rows, ld_out] (columns >= L zeroed).
+// One warp per row; the row is read once from HBM/L2 (16-byte loads, 512 B per warp instruction, when the row is
+// 16 B aligned) and twice more from L1.
 __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ s, long long rows, int L, long long ld_in, long long ld_out, float scale,
                                                       __half* __restrict__ out) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* sr = s + row * ld_in;
-    float mx = -INFINITY;
+    __half* orow = out + row * ld_out;
+    const bool vec = (L & 3) == 0 && (ld_in & 3) == 0 && (ld_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(s) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+    float mx = -INFINITY, sum = 0.f;
+    if (vec) {
+        const float4* s4 = reinterpret_cast<const float4*>(sr);
+        const int L4 = L >> 2;
+#pragma unroll 4
+        for (int c = lane; c < L4; c += 32) { const float4 v = s4[c]; mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); }
+        mx *= scale;                                     // scale > 0: max commutes with the scaling
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll 4
+        for (int c = lane; c < L4; c += 32) {
+            const float4 v = s4[c];
+            sum += __expf(v.x * scale - mx) + __expf(v.y * scale - mx) + __expf(v.z * scale - mx) + __expf(v.w * scale - mx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        uint2* o2 = reinterpret_cast<uint2*>(orow);
+#pragma unroll 4
+        for (int c = lane; c < L4; c += 32) {
+            const float4 v = s4[c];
+            uint2 p;
+            p.x = tc05::pack_f16x2(__expf(v.x * scale - mx) * inv, __expf(v.y * scale - mx) * inv);
+            p.y = tc05::pack_f16x2(__expf(v.z * scale - mx) * inv, __expf(v.w * scale - mx) * inv);
+            o2[c] = p;
+        }
+        for (int c = L + lane; c < (int)ld_out; c += 32) orow[c] = __half(0.f);
+        return;
+    }
     for (int c = lane; c < L; c += 32) mx = fmaxf(mx, sr[c] * scale);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
     for (int c = lane; c < L; c += 32) sum += __expf(sr[c] * scale - mx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
-    __half* orow = out + row * ld_out;
     for (int c = lane; c < (int)ld_out; c += 32) orow[c] = c < L ? __float2half_rn(__expf(sr[c] * scale - mx) * inv) : __half(0.f);
 }
 
@@ -581,7 +612,7 @@ int ac_sd_geglu_f16(const float* x, int64_t M, int inner, void* out, void* strea
 }
 
 int ac_sd_softmax_f16(const float* scores, int64_t rows, int L, int64_t ld_in, int64_t ld_out, float scale, void* out, void* stream) {
-    if (!scores || !out || rows <= 0 || L <= 0 || ld_in < L || ld_out < L) return AC_E_INVALID_ARG;
+    if (!scores || !out || rows <= 0 || L <= 0 || ld_in < L || ld_out < L || !(scale > 0.0f)) return AC_E_INVALID_ARG;
     const long long blocks = (rows + 7) / 8;
     if (blocks > 0x7FFFFFFFll) return AC_E_INVALID_ARG;
     softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, rows, L, ld_in, ld_out, scale, reinterpret_cast<__half*>(out));

@@ -150,3 +150,23 @@ def test_extract_geometry_is_a_closed_surface_on_the_zero_set():
     p0, p1, p2 = verts[tris[:, 0]].astype(np.float64), verts[tris[:, 1]].astype(np.float64), verts[tris[:, 2]].astype(np.float64)
     vol = float(np.einsum("ij,ij->i", p0, np.cross(p1, p2)).sum() / 6.0)
     assert 0.2 < vol < 1.2, vol
+
+
+def test_error_codes_of_the_new_entry_points():
+    """Invalid arguments come back as AC_E_INVALID_ARG (the shim raises RuntimeError), never as a launch."""
+    import ctypes
+    from avatarcraft_b200 import _lib
+    L = _lib.lib()
+    t = torch.zeros(64, device="cuda")
+    n0 = L.ac_launch_count()
+    assert L.ac_gen_rays(None, 1.0, 1.0, 0.0, 0.0, 4, 4, 0.0, 1.0, 0.0, 1.0, 0, _lib.ptr(t), _lib.ptr(t), None) == _lib.AC_E_INVALID_ARG
+    m = np.eye(4)
+    assert L.ac_gen_rays(m.ctypes.data_as(ctypes.c_void_p), 1.0, 1.0, 0.0, 0.0, 4, 4, 0.0, 1.0, 0.0, 1.0, 7, _lib.ptr(t), _lib.ptr(t), None) == _lib.AC_E_INVALID_ARG
+    assert L.ac_select_background(0, 0, 0, 1.0, _lib.ptr(t), None) == _lib.AC_E_INVALID_ARG
+    assert L.ac_adam_step(_lib.ptr(t), _lib.ptr(t), _lib.ptr(t), _lib.ptr(t), 64, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == _lib.AC_E_INVALID_ARG   # step 0
+    assert L.ac_adam_step(ctypes.c_void_p(t.data_ptr() + 4), _lib.ptr(t), _lib.ptr(t), _lib.ptr(t), 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == _lib.AC_E_INVALID_ARG   # misaligned
+    assert L.ac_sd_gemm_f16(_lib.ptr(t), _lib.ptr(t), None, None, 0, None, _lib.ptr(t), 0, 4, 4, 4, 3, 8, 4, 0, 1, 1, 0, 0, 0, 0, 0, 0, None) == _lib.AC_E_INVALID_ARG   # lda % 8
+    assert L.ac_sd_softmax_f16(_lib.ptr(t), 4, 8, 4, 8, 1.0, _lib.ptr(t), None) == _lib.AC_E_INVALID_ARG      # ld_in < L
+    assert L.ac_launch_count() == n0
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.AC_E_INVALID_ARG, "x")

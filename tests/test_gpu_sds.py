@@ -88,6 +88,10 @@ def test_producers_against_torch():
     p16 = torch.empty(64, 80, device="cuda", dtype=torch.float16)
     _lib.check(_lib.lib().ac_sd_softmax_f16(sd_native._p(s), 64, 77, 80, 80, 0.3, sd_native._p(p16), _lib.stream_ptr()), "softmax")
     assert float((p16[:, :77].float() - torch.softmax(s[:, :77] * 0.3, -1)).abs().max()) < 1e-3 and float(p16[:, 77:].abs().max()) == 0.0
+    s2 = torch.randn(40, 1024, generator=g).cuda() * 4                                  # 16-byte path
+    p2 = torch.empty(40, 1024, device="cuda", dtype=torch.float16)
+    _lib.check(_lib.lib().ac_sd_softmax_f16(sd_native._p(s2), 40, 1024, 1024, 1024, 0.158, sd_native._p(p2), _lib.stream_ptr()), "softmax")
+    assert float((p2.float() - torch.softmax(s2 * 0.158, -1)).abs().max()) < 1e-3 and abs(float(p2.float().sum(-1).mean()) - 1.0) < 2e-3
 
 
 @pytest.mark.parametrize("linear_proj", [False, True])

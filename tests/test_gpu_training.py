@@ -163,3 +163,40 @@ def test_sampling_only_launch_returns_the_render_launch_depths():
         full = net.run(o[None], d[None], 64, 1.6, 64, None, 1.0, 0.0, jitter=jit)[9]
         only = net._sample_depths(o, d, 64, 64, 1.6, jit)
     assert torch.equal(full, only)
+
+
+def test_fused_backward_equals_layer_term_backward():
+    """The two C entry points of the SDF backward -- weight gradients reduced in-kernel on the tensor cores vs per-point
+    layer terms reduced by GEMMs -- on the same points and upstream gradient, including a 1e5 loss scale (stylize.py:190)."""
+    import ctypes
+    from avatarcraft_b200 import _lib
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    gen = torch.Generator().manual_seed(9)
+    B = 50000
+    x = ((torch.rand(B, 3, generator=gen) * 2 - 1) * 1.6).cuda()
+    x[:7] = 1.7                                                                    # out-of-range points: zero features, no scatter
+    m = net._device_model()
+    L = _lib.lib()
+    for loss_scale in (1.0, 1e5):
+        gout = (torch.randn(B, 16, generator=gen) * loss_scale).cuda()
+        gout[B // 2:, 1:] = 0.0                                                    # finite-difference points only carry d/d(sdf)
+        gt_a = torch.zeros_like(net.encoder.embeddings); gt_b = torch.zeros_like(gt_a)
+        delta = torch.empty(64, B, device="cuda"); hid = torch.empty(64, B, device="cuda"); feats = torch.empty(36, B, device="cuda")
+        _lib.check(L.ac_nsr_sdf_backward(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, 1.6, _lib.ptr(gt_a), _lib.ptr(delta), _lib.ptr(hid),
+                                         _lib.ptr(feats), _lib.stream_ptr()), "terms")
+        ref0 = (delta.double() @ feats.double().t()).float()
+        ref1 = (hid.double() @ gout.double()).t().float()
+        w1 = torch._weight_norm(net.sdf_net[1].weight_v.detach(), net.sdf_net[1].weight_g.detach(), 0)
+        gmax = gout.abs().amax(); c1 = w1.abs().sum(0).amax()
+        scales = torch.exp2(torch.floor(torch.log2(torch.stack([30000.0 / (gmax * c1), 30000.0 / gmax])))).float().contiguous()
+        acc0 = torch.zeros(64, 36, device="cuda"); acc1 = torch.zeros(16, 64, device="cuda")
+        _lib.check(L.ac_nsr_sdf_backward_fused(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, 1.6, _lib.ptr(scales), _lib.ptr(gt_b),
+                                               _lib.ptr(acc0), _lib.ptr(acc1), _lib.stream_ptr()), "fused")
+        got0, got1 = acc0 / scales[0], acc1 / scales[1]
+        assert torch.isfinite(got0).all() and torch.isfinite(got1).all()
+        assert rel_l2(got0.cpu().numpy(), ref0.cpu().numpy()) < 2e-3 and rel_l2(got1.cpu().numpy(), ref1.cpu().numpy()) < 2e-3
+        # the table scatter is the same arithmetic; only the order of the fp32 reductions differs
+        assert rel_l2(gt_b.cpu().numpy(), gt_a.cpu().numpy()) < 1e-5
+    assert L.ac_nsr_sdf_backward_fused(ctypes.byref(m), None, _lib.ptr(gout), B, 1.6, _lib.ptr(scales), _lib.ptr(gt_b), _lib.ptr(acc0),
+                                       _lib.ptr(acc1), _lib.stream_ptr()) == _lib.AC_E_INVALID_ARG
