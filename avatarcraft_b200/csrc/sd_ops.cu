@@ -324,6 +324,198 @@ inline bool make_operand_map(CUtensorMap* map, const void* base, int K, int rows
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Fused attention: softmax(scale * Q K^T) V for one (batch, head, 128-query tile) per CTA, without the [Lq, Lk] score
+// matrix ever leaving the SM (the unfused path writes 1.07 GB of fp32 scores + 0.54 GB of fp16 probabilities per
+// 64x64 self-attention layer).  Two passes over the key tiles:
+//   pass 1   S = Q K_j^T on tcgen05 (accumulator in TMEM), thread = query row: running max m and sum l (online softmax
+//            statistics only -- no output, so nothing has to be rescaled later);
+//   pass 2   S again, P = exp(scale S - m) / l written as the fp16 SWIZZLE_128B A operand, O += P V_j on tcgen05 with the
+//            accumulator resident in TMEM; O -> fp16 -> [B, Lq, heads*d].
+// Recomputing S costs one extra (cheap, K = head_dim) MMA per tile and removes every read-modify-write of O.
+// Operands arrive by TMA (Q once, K and V^T double-buffered one tile ahead); one elected thread issues TMA and MMA, all
+// 128 threads do the softmax arithmetic; the tile loop is synchronous (two CTAs per SM overlap each other's latencies
+// when head_dim <= 64).  V^T [B, heads*d, Lk] is what the value projection GEMM already produces (swapped operands).
+// ------------------------------------------------------------------------------------------------------------------
+struct FlashParams {
+    __half* out;            // [B, Lq, ld_out], head h at column h*d
+    long long ld_out;
+    int Lq, Lk, d, dn;      // dn = d rounded up to 16 (N of the P V MMA)
+    float scale;
+};
+
+template <int KA>           // 64-wide K atoms covering the head dim (1: d <= 64, 2: d <= 128)
+__global__ void __launch_bounds__(128) sd_flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                            const __grid_constant__ CUtensorMap tmVt, const FlashParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr uint32_t QK_ATOM = 128 * 128;              // 128 rows x 128 B
+    const uint32_t v_atom = (uint32_t)p.dn * 128u, v_stage = 2u * v_atom;
+    unsigned char* sQ = smem;
+    unsigned char* sK = sQ + KA * QK_ATOM;               // 2 stages
+    unsigned char* sV = sK + 2 * KA * QK_ATOM;           // 2 stages
+    unsigned char* sP = sV + 2 * v_stage;                // 2 atoms of [128 x 64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * QK_ATOM);
+    uint64_t* qfull = bars; uint64_t* kfull = bars + 1; uint64_t* vfull = bars + 3; uint64_t* mma_bar = bars + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) tc05::mbar_init(bars + i, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc<256>(tmem_slot);
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem = *tmem_slot, tS = tmem, tO = tmem + 128u;
+    const uint32_t trow = (uint32_t)(warp * 32) << 16;   // this thread's TMEM lane quarter
+    const uint32_t sQ_s = tc05::smem_u32(sQ), sK_s = tc05::smem_u32(sK), sV_s = tc05::smem_u32(sV), sP_s = tc05::smem_u32(sP);
+    const int T = (p.Lk + 127) / 128;
+    const int ksteps = (p.d + 15) / 16;                  // K = 16 steps of the S MMA
+    uint32_t kph[2] = {0u, 0u}, vph[2] = {0u, 0u}, mph = 0u;
+
+    auto load_k = [&](int j, int st) {
+        mbar_expect_tx(kfull + st, KA * QK_ATOM);
+        for (int a = 0; a < KA; ++a) tma_load_4d(sK_s + (st * KA + a) * QK_ATOM, &tmK, kfull + st, a * 64, j * 128, h, b);
+    };
+    auto load_v = [&](int j, int st) {
+        mbar_expect_tx(vfull + st, v_stage);
+        for (int a = 0; a < 2; ++a) tma_load_4d(sV_s + st * v_stage + a * v_atom, &tmVt, vfull + st, j * 128 + a * 64, 0, h, b);
+    };
+    auto issue_s = [&](int st) {                          // S = Q K^T for the tile in stage st
+        constexpr uint32_t idesc = tc05::idesc_f16(128, 128);
+        for (int s = 0; s < ksteps; ++s) {
+            const int a = s >> 2, k4 = s & 3;
+            tc05::mma_f16(tS, smem_desc_sw128(sQ_s + a * QK_ATOM) + 2ull * k4, smem_desc_sw128(sK_s + (st * KA + a) * QK_ATOM) + 2ull * k4, idesc,
+                          s != 0 ? 1u : 0u);
+        }
+        tc05::mma_commit(mma_bar);
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(qfull, KA * QK_ATOM);
+        for (int a = 0; a < KA; ++a) tma_load_4d(sQ_s + a * QK_ATOM, &tmQ, qfull, a * 64, q0, h, b);
+        load_k(0, 0);
+    }
+    // ---- pass 1: row statistics ----
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        if (tid == 0) {
+            if (j + 1 < T) load_k(j + 1, st ^ 1);        // that stage's last reader (S of tile j-1) completed before the last barrier
+            if (j == 0) tc05::mbar_wait(qfull, 0u);
+            tc05::mbar_wait(kfull + st, kph[st]); kph[st] ^= 1u;
+            tc05::fence_after_sync();
+            issue_s(st);
+        }
+        tc05::mbar_wait(mma_bar, mph); mph ^= 1u;
+        __syncwarp();                                     // lane 0 of warp 0 rejoins before the warp-collective TMEM loads
+        tc05::fence_after_sync();
+        const int ncols = min(128, p.Lk - j * 128);
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(tS + trow + q * 16, acc);
+            if (q * 16 >= ncols) continue;
+            float cm = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) if (q * 16 + c < ncols) cm = fmaxf(cm, acc[c] * p.scale);
+            const float mn = fmaxf(m, cm);
+            float add = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) if (q * 16 + c < ncols) add += __expf(acc[c] * p.scale - mn);
+            l = l * __expf(m - mn) + add;
+            m = mn;
+        }
+        tc05::fence_before_sync();
+        __syncthreads();                                  // everyone has read S before the next tile's MMA overwrites it
+    }
+    const float inv_l = 1.0f / l;
+    // ---- pass 2: O = P V ----
+    if (tid == 0) { tc05::fence_after_sync(); load_k(0, 0); load_v(0, 0); }
+    const uint32_t idesc_o = tc05::idesc_f16(128, (uint32_t)p.dn);
+    const int r = tid;                                    // query row of this thread = TMEM lane
+    for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        if (tid == 0) {
+            if (j + 1 < T) { load_k(j + 1, st ^ 1); load_v(j + 1, st ^ 1); }
+            tc05::mbar_wait(kfull + st, kph[st]); kph[st] ^= 1u;
+            tc05::fence_after_sync();
+            issue_s(st);
+        }
+        tc05::mbar_wait(mma_bar, mph); mph ^= 1u;
+        __syncwarp();                                     // lane 0 of warp 0 rejoins before the warp-collective TMEM loads
+        tc05::fence_after_sync();
+        const int ncols = min(128, p.Lk - j * 128);
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(tS + trow + q * 16, acc);
+            float pr[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pr[c] = (q * 16 + c < ncols) ? __expf(acc[c] * p.scale - m) * inv_l : 0.f;
+            // kv columns q*16 .. q*16+15 -> atom (q >> 2), 16-byte chunks 2*(q & 3), +1 of this row, XOR-swizzled by row % 8
+            unsigned char* rowp = sP + (q >> 2) * QK_ATOM + (r >> 3) * 1024 + (r & 7) * 128;
+            const int ch = 2 * (q & 3);
+            uint4 lo, hi;
+            lo.x = tc05::pack_f16x2(pr[0], pr[1]); lo.y = tc05::pack_f16x2(pr[2], pr[3]); lo.z = tc05::pack_f16x2(pr[4], pr[5]); lo.w = tc05::pack_f16x2(pr[6], pr[7]);
+            hi.x = tc05::pack_f16x2(pr[8], pr[9]); hi.y = tc05::pack_f16x2(pr[10], pr[11]); hi.z = tc05::pack_f16x2(pr[12], pr[13]); hi.w = tc05::pack_f16x2(pr[14], pr[15]);
+            *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = lo;
+            *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) << 4)) = hi;
+        }
+        tc05::fence_proxy_async_smem();
+        tc05::fence_before_sync();
+        __syncthreads();                                  // P complete and visible to the tensor core; S fully consumed
+        if (tid == 0) {
+            tc05::fence_after_sync();
+            tc05::mbar_wait(vfull + st, vph[st]); vph[st] ^= 1u;
+            tc05::fence_after_sync();
+            for (int s = 0; s < 8; ++s) {                 // K = 128 keys = 8 x 16
+                const int a = s >> 2, k4 = s & 3;
+                tc05::mma_f16(tO, smem_desc_sw128(sP_s + a * QK_ATOM) + 2ull * k4, smem_desc_sw128(sV_s + st * v_stage + a * v_atom) + 2ull * k4, idesc_o,
+                              (j | s) != 0 ? 1u : 0u);
+            }
+            tc05::mma_commit(mma_bar);
+        }
+        tc05::mbar_wait(mma_bar, mph); mph ^= 1u;         // P, this V stage and S are free again
+        __syncwarp();
+        tc05::fence_after_sync();
+    }
+    // ---- epilogue: O row -> fp16 (the TMEM loads are warp-collective: every lane executes them, only valid rows store) ----
+    {
+        const bool row_ok = q0 + r < p.Lq;
+        __half* dst = p.out + ((long long)b * p.Lq + (row_ok ? q0 + r : 0)) * p.ld_out + (long long)h * p.d;
+#pragma unroll 1
+        for (int q = 0; q < p.dn / 16; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(tO + trow + q * 16, acc);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int c = q * 16 + half * 8;
+                if (row_ok && c + 8 <= p.d) {
+                    uint4 o;
+                    o.x = tc05::pack_f16x2(acc[half * 8 + 0], acc[half * 8 + 1]); o.y = tc05::pack_f16x2(acc[half * 8 + 2], acc[half * 8 + 3]);
+                    o.z = tc05::pack_f16x2(acc[half * 8 + 4], acc[half * 8 + 5]); o.w = tc05::pack_f16x2(acc[half * 8 + 6], acc[half * 8 + 7]);
+                    *reinterpret_cast<uint4*>(dst + c) = o;
+                }
+            }
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<256>(tmem);
+}
+
+inline bool make_map4(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[4], const cuuint64_t (&strides)[3], cuuint32_t box0, cuuint32_t box1) {
+    const cuuint32_t box[4] = {box0, box1, 1u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Producers (all HBM-streaming, one element group per thread, 16-byte stores)
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
@@ -570,6 +762,41 @@ int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float*
         !make_operand_map(&tmW, W, K, N, ldw, batch_inner, sWi, batch_outer, sWo, &w_zi, &w_zo))
         return AC_E_UNSUPPORTED;                         // no silent fallback: the caller sees the failure
     sd_gemm_tma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p, a_zi, a_zo, w_zi, w_zo);
+    return acb::launched();
+}
+
+int ac_sd_flash_attention_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Lq, int Lk, int d, int64_t ld_q,
+                              int64_t ld_k, int64_t ld_vt, int64_t ld_out, float scale, void* stream) {
+    if (!q || !k || !vt || !out || B <= 0 || heads <= 0 || Lq <= 0 || Lk <= 0 || d <= 0 || (d & 7) || d > 128 || !(scale > 0.f)) return AC_E_INVALID_ARG;
+    if ((ld_q & 7) || (ld_k & 7) || (ld_vt & 7) || (ld_out & 7) || ld_vt < Lk || ld_q < (int64_t)heads * d || ld_k < (int64_t)heads * d) return AC_E_INVALID_ARG;
+    if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out) & 15) return AC_E_INVALID_ARG;
+    if (heads > 65535 || B > 65535) return AC_E_INVALID_ARG;
+    const int dn = (d + 15) / 16 * 16, KA = d <= 64 ? 1 : 2;
+    CUtensorMap tmQ, tmK, tmV;
+    {
+        const cuuint64_t dq[4] = {(cuuint64_t)d, (cuuint64_t)Lq, (cuuint64_t)heads, (cuuint64_t)B};
+        const cuuint64_t sq[3] = {(cuuint64_t)ld_q * 2, (cuuint64_t)d * 2, (cuuint64_t)Lq * ld_q * 2};
+        const cuuint64_t dk[4] = {(cuuint64_t)d, (cuuint64_t)Lk, (cuuint64_t)heads, (cuuint64_t)B};
+        const cuuint64_t sk[3] = {(cuuint64_t)ld_k * 2, (cuuint64_t)d * 2, (cuuint64_t)Lk * ld_k * 2};
+        const cuuint64_t dv[4] = {(cuuint64_t)Lk, (cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)B};
+        const cuuint64_t sv[3] = {(cuuint64_t)ld_vt * 2, (cuuint64_t)d * ld_vt * 2, (cuuint64_t)heads * d * ld_vt * 2};
+        if (!make_map4(&tmQ, q, dq, sq, 64, 128) || !make_map4(&tmK, k, dk, sk, 64, 128) || !make_map4(&tmV, vt, dv, sv, 64, (cuuint32_t)dn))
+            return AC_E_UNSUPPORTED;
+    }
+    FlashParams p;
+    p.out = reinterpret_cast<__half*>(out); p.ld_out = ld_out; p.Lq = Lq; p.Lk = Lk; p.d = d; p.dn = dn; p.scale = scale;
+    const size_t smem = (size_t)KA * 16384 * 3 + 4 * (size_t)dn * 128 + 2 * 16384 + 64;
+    dim3 grid((Lq + 127) / 128, heads, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (KA == 1) {
+        static bool a1 = false;
+        if (!a1) { cudaFuncSetAttribute(sd_flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); a1 = true; }
+        sd_flash_attn_kernel<1><<<grid, 128, smem, st>>>(tmQ, tmK, tmV, p);
+    } else {
+        static bool a2 = false;
+        if (!a2) { cudaFuncSetAttribute(sd_flash_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); a2 = true; }
+        sd_flash_attn_kernel<2><<<grid, 128, smem, st>>>(tmQ, tmK, tmV, p);
+    }
     return acb::launched();
 }
 

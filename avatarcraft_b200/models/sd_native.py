@@ -15,6 +15,7 @@ from .. import _lib
 from .sd_blocks import timestep_embedding
 
 _W16 = {}
+FLASH = True          # fused attention kernel; False = Q K^T GEMM -> softmax -> P V GEMM (kept for A/B and head dims > 128)
 
 
 def _check(rc, what):
@@ -145,6 +146,12 @@ def attention(xq16, ctx16, attn, B, Lq, Lk, residual):
     vT = torch.zeros(B, inner, Lp, device=dev, dtype=torch.float16) if Lp != Lk else torch.empty(B, inner, Lp, device=dev, dtype=torch.float16)
     gemm(_w16(attn.to_v.weight, "linear"), ctx16, inner, Lk, Cc, out_f16=True, out=vT, ldc=Lp, batch=(B, 1), sA=(0, 0), sW=(Lk * Cc, 0),
          sC=(inner * Lp, 0))
+    if FLASH and d % 8 == 0 and d <= 128:
+        # fused: scores and probabilities never leave the SM (csrc/sd_ops.cu: sd_flash_attn_kernel)
+        o16 = torch.empty(B * Lq, inner, device=dev, dtype=torch.float16)
+        _check(_lib.lib().ac_sd_flash_attention_f16(_p(q), _p(k), _p(vT), _p(o16), B, heads, Lq, Lk, d, inner, inner, Lp, inner, float(attn.scale),
+                                                    _lib.stream_ptr()), "ac_sd_flash_attention_f16")
+        return linear(o16, attn.to_out[0], B * Lq, residual=residual)
     scores = torch.empty(B, heads, Lq, Lp, device=dev, dtype=torch.float32)
     gemm(q, k, Lq, Lk, d, out=scores, lda=inner, ldw=inner, ldc=Lp, batch=(B, heads), sA=(Lq * inner, d), sW=(Lk * inner, d),
          sC=(heads * Lq * Lp, Lq * Lp))

@@ -298,6 +298,12 @@ int ac_sd_gemm_f16(const void *A, const void *W, const float *bias, const float 
                    const float *residual, void *C, int out_f16, int M, int N, int K, int64_t lda, int64_t ldw,
                    int64_t ldc, int64_t ldr, int batch_outer, int batch_inner, int64_t sAo, int64_t sAi, int64_t sWo,
                    int64_t sWi, int64_t sCo, int64_t sCi, void *stream);
+/* Fused attention: out[b, :, h*d:(h+1)*d] = softmax(scale * Q_bh K_bh^T) V_bh for every (batch, head), the score matrix
+ * never leaves the SM (two passes over the key tiles: statistics, then P V with the accumulator in TMEM).
+ * q [B*Lq, ld_q], k [B*Lk, ld_k] fp16 with head h at columns h*d; vt [B, heads*d, ld_vt] fp16 = V transposed (keys
+ * contiguous, ld_vt >= Lk); out [B*Lq, ld_out] fp16.  d a multiple of 8, d <= 128; every ld a multiple of 8. */
+int ac_sd_flash_attention_f16(const void *q, const void *k, const void *vt, void *out, int B, int heads, int Lq, int Lk,
+                              int d, int64_t ld_q, int64_t ld_k, int64_t ld_vt, int64_t ld_out, float scale, void *stream);
 int ac_sd_group_norm_stats(const float *x, int B, int HW, int C, int G, float eps, double *sums_workspace, float *stats,
                            void *stream);
 int ac_sd_im2col_f16(const float *x, int B, int Hs, int Ws, int C, int ksize, int stride, int pad, int upsample2x,

@@ -48,6 +48,26 @@ def test_batched_strided_gemm_is_per_head_attention():
     assert float((scores[..., :Lk] - ref).abs().max()) < 2e-2
 
 
+@pytest.mark.parametrize("cfg", [(2, 4, 200, 77, 40), (1, 2, 300, 300, 80), (2, 3, 128, 1000, 64), (1, 2, 130, 129, 16), (1, 1, 64, 4096, 40)])
+def test_fused_attention_against_torch(cfg):
+    B, heads, Lq, Lk, d = cfg
+    inner = heads * d
+    g = torch.Generator().manual_seed(Lq + Lk + d)
+    q = torch.randn(B * Lq, inner, generator=g).cuda().half()
+    k = torch.randn(B * Lk, inner, generator=g).cuda().half()
+    v = torch.randn(B, Lk, inner, generator=g).cuda().half()
+    Lp = (Lk + 7) // 8 * 8
+    vt = torch.full((B, inner, Lp), float("nan"), device="cuda", dtype=torch.float16)       # padding must never be read as data
+    vt[:, :, :Lk] = v.transpose(1, 2)
+    out = torch.empty(B * Lq, inner, device="cuda", dtype=torch.float16)
+    scale = d ** -0.5
+    _lib.check(_lib.lib().ac_sd_flash_attention_f16(sd_native._p(q), sd_native._p(k), sd_native._p(vt), sd_native._p(out), B, heads, Lq, Lk, d,
+                                                    inner, inner, Lp, inner, scale, _lib.stream_ptr()), "flash")
+    ref = sd_ops.attention(q.float().reshape(B, Lq, inner), k.float().reshape(B, Lk, inner), v.float(), heads, scale).reshape(B * Lq, inner)
+    assert torch.isfinite(out).all()
+    assert float((out.float() - ref).abs().max()) < 6e-3, float((out.float() - ref).abs().max())      # fp16 P and output
+
+
 def test_producers_against_torch():
     g = torch.Generator().manual_seed(4)
     B, H, W, C, G = 2, 12, 10, 64, 8
