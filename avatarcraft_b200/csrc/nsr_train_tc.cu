@@ -36,7 +36,11 @@ namespace {
 constexpr int kGroupsT = 4;                              // 4-warp groups per CTA (512 threads, one CTA per SM)
 constexpr int kThreadsT = 128 * kGroupsT;
 constexpr int kMlpFloats = OFF_C0;                       // W0 [64][36] | B0 [64] | W1T [64][16] | B1 [16] -- all this kernel reads
-constexpr uint32_t A_BYTES = 128 * 128 * 2, B_BYTES = 64 * 128 * 2;
+// K-major no-swizzle tiles: 16-byte chunk (8 points) c of row r at c*LBO + r*16.  The chunk stride is programmable in the
+// descriptor: 16 bytes of padding per plane (LBO = rows*16 + 16) put the four planes a warp's 32 points touch on distinct
+// bank groups, so the per-point 2-byte column stores are conflict-free (they were 4-way conflicted at LBO = rows*16).
+constexpr uint32_t A_LBO = 128 * 16 + 16, B_LBO = 64 * 16 + 16;
+constexpr uint32_t A_BYTES = 16 * A_LBO, B_BYTES = 16 * B_LBO;
 constexpr size_t T_SW = 0;
 constexpr size_t T_LV = T_SW + kMlpFloats * sizeof(float);
 constexpr size_t T_W0F = (T_LV + kLevels * sizeof(LevelMeta) + 15) / 16 * 16;
@@ -46,9 +50,9 @@ constexpr size_t T_TOTAL = T_BARS + kGroupsT * 8 + 16;
 static_assert(T_TOTAL <= 227 * 1024, "shared memory budget");
 static_assert(kMlpFloats % 4 == 0, "float4 staging");
 
-// element (row r, point k) of a K-major no-swizzle tile with `rows` rows: 16-byte chunk k/8 at (k/8)*rows*16 + r*16
-__device__ __forceinline__ void put(unsigned char* tile, int rows, int r, int k, float v) {
-    *reinterpret_cast<__half*>(tile + (k >> 3) * rows * 16 + r * 16 + (k & 7) * 2) = __float2half_rn(v);
+// element (row r, point k) of a tile with chunk stride `lbo`
+__device__ __forceinline__ void put(unsigned char* tile, uint32_t lbo, int r, int k, float v) {
+    *reinterpret_cast<__half*>(tile + (k >> 3) * lbo + r * 16 + (k & 7) * 2) = __float2half_rn(v);
 }
 
 __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
     }
     if (warp == 0) tc05::tmem_alloc<64 * kGroupsT>(tmem_slot);
     // rows 36..47 of B never change: zero them once (rows 0..35 and 48..63 are rewritten every round)
-    for (int r = 36; r < 48; ++r) put(Bt, 64, r, k, 0.f);
+    for (int r = 36; r < 48; ++r) put(Bt, B_LBO, r, k, 0.f);
     tc05::fence_before_sync();
     __syncthreads();
     tc05::fence_after_sync();
@@ -133,8 +137,8 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
                 dh = fmaf(w4.z, g[4 * q + 2], dh); dh = fmaf(w4.w, g[4 * q + 3], dh);
             }
             const float da = a * 100.0f > 20.0f ? dh : dh * sigmoidf(a * 100.0f);
-            put(At, 128, j, k, valid ? da * s_d : 0.f);
-            put(At, 128, 64 + j, k, valid ? h : 0.f);
+            put(At, A_LBO, j, k, valid ? da * s_d : 0.f);
+            put(At, A_LBO, 64 + j, k, valid ? h : 0.f);
             const float4* __restrict__ wf = reinterpret_cast<const float4*>(w0f + j * 32);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -144,10 +148,10 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
             }
         }
 #pragma unroll
-        for (int q = 0; q < 35; ++q) put(Bt, 64, q, k, in[q]);
-        put(Bt, 64, 35, k, valid ? 1.0f : 0.f);
+        for (int q = 0; q < 35; ++q) put(Bt, B_LBO, q, k, in[q]);
+        put(Bt, B_LBO, 35, k, valid ? 1.0f : 0.f);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) put(Bt, 64, 48 + q, k, g[q] * s_g);
+        for (int q = 0; q < 16; ++q) put(Bt, B_LBO, 48 + q, k, g[q] * s_g);
         // hand the tiles to the tensor core: D += A B^T over this round's 128 points
         tc05::fence_proxy_async_smem();
         tc05::fence_before_sync();
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
             constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
 #pragma unroll
             for (uint32_t s = 0; s < 8; ++s)             // K = 128 points = 8 x (K = 16): chunks 2s, 2s+1
-                tc05::mma_f16(tmem, tc05::smem_desc(a_s + s * 4096u, 2048u, 128u), tc05::smem_desc(b_s + s * 2048u, 1024u, 128u),
+                tc05::mma_f16(tmem, tc05::smem_desc(a_s + s * 2u * A_LBO, A_LBO, 128u), tc05::smem_desc(b_s + s * 2u * B_LBO, B_LBO, 128u),
                               idesc, (base != blockIdx.x * kThreadsT || s != 0) ? 1u : 0u);
             tc05::mma_commit(bars + group);
         }
