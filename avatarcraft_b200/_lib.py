@@ -79,6 +79,8 @@ _SIGNATURES = {
     "ac_nsr_forward_sdf": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V]),
     "ac_nsr_sdf_backward": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V, _V, _V, _V, _V]),
     "ac_nsr_sdf_backward_fused": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V, _V, _V, _V, _V]),
+    "ac_nsr_forward_sdf_stencil": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V]),
+    "ac_nsr_sdf_backward_stencil": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V, _V, _V, _V, _V]),
     "ac_nsr_forward_color": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _U32, _V]),
     "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
     "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),

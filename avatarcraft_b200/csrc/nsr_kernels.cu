@@ -481,7 +481,8 @@ __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __rest
 }  // namespace
 namespace acb {
 int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStream_t st);
-int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st);
+int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st, uint32_t stencil_M = 0,
+                          float eps = 0.f, float* out_fd = nullptr);
 }
 namespace {
 
@@ -533,6 +534,13 @@ int ac_nsr_forward_sdf(const ac_nsr_model* m, const float* x, float* out, uint32
         reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->log2_per_level_scale,
         m->base_resolution, x, out, B, bound);
     return acb::launched();
+}
+
+int ac_nsr_forward_sdf_stencil(const ac_nsr_model* m, const float* P, uint32_t M, float bound, float eps, float* out_centre, float* out_fd,
+                               void* stream) {
+    if (check_model(m) || !P || !out_centre || !out_fd || !(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
+    if (M == 0) return AC_OK;
+    return acb::launch_forward_sdf_tc(m, P, out_centre, 7u * M, bound, (cudaStream_t)stream, M, eps, out_fd);
 }
 
 int ac_nsr_sdf_backward(const ac_nsr_model* m, const float* x, const float* grad_out, uint32_t B, float bound,

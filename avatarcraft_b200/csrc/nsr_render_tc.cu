@@ -573,7 +573,11 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
 // Staging is the render kernel's prologue restricted to what the SDF network needs.
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
                                                                           const float* __restrict__ blob, float S, uint32_t H,
-                                                                          const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound) {
+                                                                          const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound,
+                                                                          const uint32_t stencil_M, const float eps, float* __restrict__ out_fd) {
+    // stencil_M > 0: x holds M section points and the B = 7 M evaluated points are generated here -- block 0 the points
+    // themselves (16 outputs -> out [M,16]), blocks 1..6 their +-eps neighbours along x, y, z re-clamped to the bound
+    // (signed distance only -> out_fd [6,M]): the finite-difference stencil of NeRFNetwork.gradient (:683-704).
     extern __shared__ __align__(1024) unsigned char smem[];
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
     unsigned char* bt = smem + SM_B;
@@ -612,13 +616,39 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const 
         const uint32_t b = base + threadIdx.x;
         const bool valid = b < B;
         const uint32_t bb = valid ? b : B - 1;           // padding threads re-evaluate the last point (every thread joins the MMA round)
-        const float px = x[3 * (size_t)bb], py = x[3 * (size_t)bb + 1], pz = x[3 * (size_t)bb + 2];
-        float o16[16];
-        group_sdf_eval<true>(g, table, lv, bound, px, py, pz, o16);
-        if (valid) {
-            float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)b);
+        float px, py, pz;
+        uint32_t blk = 0, smp = bb;
+        if (stencil_M) {
+            blk = bb / stencil_M; smp = bb - blk * stencil_M;
+            px = x[3 * (size_t)smp]; py = x[3 * (size_t)smp + 1]; pz = x[3 * (size_t)smp + 2];
+            if (blk) {
+                const float e = (blk & 1) ? eps : -eps;  // blocks 1,3,5 = +eps, 2,4,6 = -eps
+                const uint32_t ax = (blk - 1) >> 1;
+                if (ax == 0) px = clampf(px + e, -bound, bound);
+                else if (ax == 1) py = clampf(py + e, -bound, bound);
+                else pz = clampf(pz + e, -bound, bound);
+            }
+        } else {
+            px = x[3 * (size_t)bb]; py = x[3 * (size_t)bb + 1]; pz = x[3 * (size_t)bb + 2];
+        }
+        // the group's 128 threads take the same branch: all 16 outputs when the group's first point is a section point
+        const uint32_t g_first = base + (uint32_t)(group * 128);
+        if (!stencil_M || g_first < stencil_M) {
+            float o16[16];
+            group_sdf_eval<true>(g, table, lv, bound, px, py, pz, o16);
+            if (valid) {
+                if (blk == 0) {
+                    float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)smp);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+                } else {
+                    out_fd[(size_t)(blk - 1) * stencil_M + smp] = o16[0];
+                }
+            }
+        } else {
+            float o1[1];
+            group_sdf_eval<false>(g, table, lv, bound, px, py, pz, o1);
+            if (valid) out_fd[(size_t)(blk - 1) * stencil_M + smp] = o1[0];
         }
     }
     tc05::fence_before_sync();
@@ -691,7 +721,8 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
 }  // namespace acb
 
 namespace acb {
-int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st) {
+int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st, uint32_t stencil_M,
+                          float eps, float* out_fd) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(forward_sdf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); attr = true; }
     if (cudaMemcpyToSymbolAsync(c_w, m->mlp_blob + OFF_EPI, EPI_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -700,7 +731,7 @@ int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uin
     const uint32_t want = (B + per_cta - 1) / per_cta;
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
     forward_sdf_tc_kernel<<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob,
-                                                                  m->log2_per_level_scale, m->base_resolution, x, out, B, bound);
+                                                                  m->log2_per_level_scale, m->base_resolution, x, out, B, bound, stencil_M, eps, out_fd);
     return acb::launched();
 }
 }  // namespace acb

@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
                                                                        const float* __restrict__ blob, float S, uint32_t H,
                                                                        const float* __restrict__ x, const float* __restrict__ gout, uint32_t B,
                                                                        float bound, const float* __restrict__ scales, float* __restrict__ grad_table,
-                                                                       float* __restrict__ grad_w0b, float* __restrict__ grad_w1) {
+                                                                       float* __restrict__ grad_w0b, float* __restrict__ grad_w1, const uint32_t stencil_M,
+                                                                       const float eps, const float* __restrict__ gout_fd) {
+    // stencil_M > 0: x holds M section points, gout [M,16] their upstream gradients and gout_fd [6,M] the gradients of the
+    // six finite-difference neighbours' signed distances; the B = 7 M points are generated here (see forward_sdf_tc_kernel).
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sw = reinterpret_cast<float*>(smem + T_SW);
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + T_LV);
@@ -96,12 +99,27 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
         float g[16];
         float px = 0.f, py = 0.f, pz = 0.f;
         if (valid) {
-            px = x[3 * (size_t)b]; py = x[3 * (size_t)b + 1]; pz = x[3 * (size_t)b + 2];
+            uint32_t blk = 0, smp = b;
+            if (stencil_M) { blk = b / stencil_M; smp = b - blk * stencil_M; }
+            px = x[3 * (size_t)smp]; py = x[3 * (size_t)smp + 1]; pz = x[3 * (size_t)smp + 2];
+            if (blk) {
+                const float e = (blk & 1) ? eps : -eps;
+                const uint32_t ax = (blk - 1) >> 1;
+                if (ax == 0) px = clampf(px + e, -bound, bound);
+                else if (ax == 1) py = clampf(py + e, -bound, bound);
+                else pz = clampf(pz + e, -bound, bound);
+            }
             encode_point(table, lv, bound, px, py, pz, in);
+            if (blk == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 v = *reinterpret_cast<const float4*>(gout + 16 * (size_t)b + 4 * q);
-                g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(gout + 16 * (size_t)smp + 4 * q);
+                    g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+                }
+            } else {
+                g[0] = gout_fd[(size_t)(blk - 1) * stencil_M + smp];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) g[q] = 0.f;
             }
         } else {
 #pragma unroll
@@ -226,6 +244,24 @@ extern "C" int ac_nsr_sdf_backward_fused(const ac_nsr_model* m, const float* x, 
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
     sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, grad_out, B,
-        bound, scales, grad_table, grad_w0b, grad_w1);
+        bound, scales, grad_table, grad_w0b, grad_w1, 0u, 0.f, nullptr);
+    return acb::launched();
+}
+
+extern "C" int ac_nsr_sdf_backward_stencil(const ac_nsr_model* m, const float* P, uint32_t M, float bound, float eps, const float* grad_centre,
+                                           const float* grad_fd, const float* scales, float* grad_table, float* grad_w0b, float* grad_w1,
+                                           void* stream) {
+    if (!m || !m->embeddings || !m->offsets || !m->mlp_blob || !P || !grad_centre || !grad_fd || !scales || !grad_table || !grad_w0b || !grad_w1)
+        return AC_E_INVALID_ARG;
+    if (!(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
+    if (M == 0) return AC_OK;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sdf_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_TOTAL); attr = true; }
+    const uint32_t B = 7u * M;
+    const uint32_t want = (B + kThreadsT - 1) / kThreadsT;
+    const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
+    sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, P, grad_centre, B,
+        bound, scales, grad_table, grad_w0b, grad_w1, M, eps, grad_fd);
     return acb::launched();
 }

@@ -76,12 +76,7 @@ class _SdfQuery(torch.autograd.Function):
             # the persistent loop): no per-point layer terms (2.4 GB per patch) and no GEMM launches.  The power-of-two
             # scales keep delta / grad_out inside the fp16 range whatever the loss scale (stylize.py:190 multiplies one term
             # by 1e5); they are device scalars, so nothing synchronises.
-            w1 = torch._weight_norm(net.sdf_net[1].weight_v.detach(), net.sdf_net[1].weight_g.detach(), 0)
-            gmax = gout.abs().amax().clamp_min(1e-30)
-            c1 = w1.abs().sum(0).amax().clamp_min(1e-30)
-            e_g = torch.floor(torch.log2(30000.0 / gmax)).clamp(-100.0, 100.0)
-            e_d = torch.floor(torch.log2(30000.0 / (gmax * c1))).clamp(-100.0, 100.0)
-            scales = torch.exp2(torch.stack([e_d, e_g])).float().contiguous()
+            scales = _fp16_scales(gout.abs().amax(), net)
             acc0 = torch.zeros(64, 36, **f32); acc1 = torch.zeros(16, 64, **f32)
             _lib.check(_lib.lib().ac_nsr_sdf_backward_fused(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound, _lib.ptr(scales),
                                                             _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.stream_ptr()),
@@ -90,6 +85,57 @@ class _SdfQuery(torch.autograd.Function):
             gw1 = acc1 / scales[1]
         gw0, gb0 = gw0b[:, :35].contiguous(), gw0b[:, 35].contiguous()
         return None, grad_table, gw0, gb0, gw1, gout.sum(0), None, None
+
+
+def _fp16_scales(gmax, net):
+    """Device-side power-of-two factors (s_d, s_g) that bring delta / grad_out into the fp16 range of the tensor-core
+    operands of the fused backward (include/avatarcraft_b200.h); no host synchronisation."""
+    w1 = torch._weight_norm(net.sdf_net[1].weight_v.detach(), net.sdf_net[1].weight_g.detach(), 0)
+    gmax = gmax.clamp_min(1e-30)
+    c1 = w1.abs().sum(0).amax().clamp_min(1e-30)
+    e_g = torch.floor(torch.log2(30000.0 / gmax)).clamp(-100.0, 100.0)
+    e_d = torch.floor(torch.log2(30000.0 / (gmax * c1))).clamp(-100.0, 100.0)
+    return torch.exp2(torch.stack([e_d, e_g])).float().contiguous()
+
+
+class _SdfStencil(torch.autograd.Function):
+    """forward_sdf at M section points and at their six +-eps neighbours (the finite-difference stencil of the training
+    path) as ONE op: forward = ac_nsr_forward_sdf_stencil -> (centre [M,16], fd [6,M]); backward =
+    ac_nsr_sdf_backward_stencil (weight gradients reduced in-kernel).  Neighbour points, their 15 unused outputs and the
+    [7M,16] gradient tensor are never materialised."""
+
+    @staticmethod
+    def forward(ctx, P, embeddings, w0, b0, w1, b1, net, bound, eps):
+        P = P.detach().reshape(-1, 3).float().contiguous()
+        M = P.shape[0]
+        centre = torch.empty(M, 16, device=P.device, dtype=torch.float32)
+        fd = torch.empty(6, M, device=P.device, dtype=torch.float32)
+        m = net._device_model()
+        _lib.check(_lib.lib().ac_nsr_forward_sdf_stencil(ctypes.byref(m), _lib.ptr(P), M, float(bound), float(eps), _lib.ptr(centre), _lib.ptr(fd),
+                                                         _lib.stream_ptr()), "ac_nsr_forward_sdf_stencil")
+        ctx.save_for_backward(P)
+        ctx.net, ctx.bound, ctx.eps, ctx.emb_shape = net, float(bound), float(eps), embeddings.shape
+        return centre, fd
+
+    @staticmethod
+    def backward(ctx, g_centre, g_fd):
+        (P,) = ctx.saved_tensors
+        net, M, dev = ctx.net, P.shape[0], P.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        g_centre = (torch.zeros(M, 16, **f32) if g_centre is None else g_centre.contiguous().float())
+        g_fd = (torch.zeros(6, M, **f32) if g_fd is None else g_fd.contiguous().float())
+        grad_table = torch.zeros(ctx.emb_shape, **f32)
+        scales = _fp16_scales(torch.maximum(g_centre.abs().amax(), g_fd.abs().amax()), net)
+        acc0 = torch.zeros(64, 36, **f32); acc1 = torch.zeros(16, 64, **f32)
+        m = net._device_model()
+        _lib.check(_lib.lib().ac_nsr_sdf_backward_stencil(ctypes.byref(m), _lib.ptr(P), M, ctx.bound, ctx.eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
+                                                          _lib.ptr(scales), _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.stream_ptr()),
+                   "ac_nsr_sdf_backward_stencil")
+        gw0b = acc0 / scales[0]
+        gw1 = acc1 / scales[1]
+        gb1 = g_centre.sum(0)
+        gb1[0] = gb1[0] + g_fd.sum()
+        return None, grad_table, gw0b[:, :35].contiguous(), gw0b[:, 35].contiguous(), gw1, gb1, None, None, None
 
 
 class SingleVarianceNetwork(nn.Module):
@@ -265,9 +311,10 @@ class NeRFRenderer(nn.Module):
         """Training-mode `run` (autograd enabled).  As in the reference, sample placement carries no
         gradient (`with torch.no_grad()`, models/instant_nsr.py:175-185): the depths come from the fused
         kernel.  The differentiable part (:186-299) evaluates the 7 x N x T SDF points with the fused
-        `_SdfQuery` op (one launch forward, one fused backward + table scatter); the light per-sample
-        algebra (normals, alpha, compositing, eikonal) and the colour MLP are torch ops here -- a fused
-        backward kernel for them is the next step."""
+        `_SdfStencil` op (one tensor-core launch forward that generates the six +-eps neighbours of every
+        section point itself; one fused backward: table scatter + weight gradients reduced in TMEM); the
+        per-sample algebra (normals, alpha, compositing, eikonal) and the colour MLP are torch ops here -- a
+        fused backward kernel for them is the next step."""
         B, N = rays_o.shape[:2]
         o = rays_o.reshape(-1, 3).float().contiguous()
         d = rays_d.reshape(-1, 3).float().contiguous()
@@ -285,20 +332,13 @@ class NeRFRenderer(nn.Module):
             z_mid = torch.cat([z[:, :-1] + 0.5 * gaps[:, :-1], z[:, -1:]], -1)
             P = (o[:, None, :] + d[:, None, :] * z_mid[..., None]).clamp(-bound, bound).reshape(-1, 3)
             eps = 0.005 * (1.0 - normal_epsilon_ratio)
-            shifted = [P]
-            for axis in range(3):
-                for sign in (1.0, -1.0):
-                    q = P.clone()
-                    q[:, axis] = (q[:, axis] + sign * eps).clamp(-bound, bound)
-                    shifted.append(q)
-            pts = torch.cat(shifted, 0)
         M = P.shape[0]
         sdf_w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in self.sdf_net]
         col_w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in self.color_net]
-        out = _SdfQuery.apply(pts, self.encoder.embeddings, sdf_w[0], self.sdf_net[0].bias, sdf_w[1], self.sdf_net[1].bias,
-                              self, bound)
-        sdf, feat = out[:M, :1], out[:M, 1:]
-        f = out[M:, 0].reshape(3, 2, M)
+        centre, fd = _SdfStencil.apply(P, self.encoder.embeddings, sdf_w[0], self.sdf_net[0].bias, sdf_w[1], self.sdf_net[1].bias,
+                                       self, bound, eps)
+        sdf, feat = centre[:, :1], centre[:, 1:]
+        f = fd.reshape(3, 2, M)
         grad = (0.5 * (f[:, 0] - f[:, 1]) / eps).t()
         gnorm = torch.linalg.norm(grad, ord=2, dim=-1, keepdim=True)
         normal = grad / (1e-5 + gnorm)

@@ -123,6 +123,16 @@ int ac_nsr_sdf_backward(const ac_nsr_model *model, const float *x, const float *
  * max_j sum_o |W1[o][j]|) and s_g <= 30000 / max|grad_out|; the caller divides the results by them. */
 int ac_nsr_sdf_backward_fused(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B, float bound,
                               const float *scales, float *grad_table, float *grad_w0b, float *grad_w1, void *stream);
+/* The training path's finite-difference stencil in one call each way (models/instant_nsr.py:210-215 + :683-704): P [M,3]
+ * section points (already clamped to the bound).  Forward: out_centre [M,16] = forward_sdf(P), out_fd [6,M] = the signed
+ * distance at clamp(P +- eps e_k) in the order (+x, -x, +y, -y, +z, -z); the 7 M points are generated inside the kernel
+ * (no [7M,3] point list, no 15 unused outputs per neighbour).  Backward: grad_centre [M,16], grad_fd [6,M] -> the same
+ * outputs as ac_nsr_sdf_backward_fused. */
+int ac_nsr_forward_sdf_stencil(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
+                               float *out_centre, float *out_fd, void *stream);
+int ac_nsr_sdf_backward_stencil(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
+                                const float *grad_centre, const float *grad_fd, const float *scales, float *grad_table,
+                                float *grad_w0b, float *grad_w1, void *stream);
 /* NeRFNetwork.forward_color (models/instant_nsr.py:644-663, use_viewdirs=False):
  * x [B,3], normal [B,3], geo_feat [B,15] -> rgb [B,3]. */
 int ac_nsr_forward_color(const ac_nsr_model *model, const float *x, const float *normal,
