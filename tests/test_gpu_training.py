@@ -200,3 +200,43 @@ def test_fused_backward_equals_layer_term_backward():
         assert rel_l2(gt_b.cpu().numpy(), gt_a.cpu().numpy()) < 1e-5
     assert L.ac_nsr_sdf_backward_fused(ctypes.byref(m), None, _lib.ptr(gout), B, 1.6, _lib.ptr(scales), _lib.ptr(gt_b), _lib.ptr(acc0),
                                        _lib.ptr(acc1), _lib.stream_ptr()) == _lib.AC_E_INVALID_ARG
+
+
+def test_stencil_ops_equal_flat_point_ops():
+    """ac_nsr_forward_sdf_stencil / ac_nsr_sdf_backward_stencil (neighbours generated in-kernel) against the flat-point
+    entry points fed the explicit 7 M point list, as models/instant_nsr.py:683-704 builds it (+-eps, re-clamped)."""
+    import ctypes
+    from avatarcraft_b200 import _lib
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    gen = torch.Generator().manual_seed(12)
+    M, bound, eps = 20011, 1.6, 0.005                      # not a multiple of 128: groups straddle the block boundaries
+    P = ((torch.rand(M, 3, generator=gen) * 2 - 1) * 1.6).cuda()
+    P[:50] = P[:50].sign() * 1.6                           # on the bound: the neighbour is clamped back
+    pts = [P]
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            q = P.clone(); q[:, axis] = (q[:, axis] + sign * eps).clamp(-bound, bound); pts.append(q)
+    flat = torch.cat(pts, 0).contiguous()
+    m = net._device_model()
+    L = _lib.lib()
+    centre = torch.empty(M, 16, device="cuda"); fd = torch.empty(6, M, device="cuda")
+    _lib.check(L.ac_nsr_forward_sdf_stencil(ctypes.byref(m), _lib.ptr(P), M, bound, eps, _lib.ptr(centre), _lib.ptr(fd), _lib.stream_ptr()), "stencil fwd")
+    ref = net.forward_sdf(flat, bound)
+    assert torch.equal(centre, ref[:M]) and torch.equal(fd.reshape(-1), ref[M:, 0])
+    g_c = torch.randn(M, 16, generator=gen).cuda(); g_f = torch.randn(6, M, generator=gen).cuda()
+    gout = torch.zeros(7 * M, 16, device="cuda"); gout[:M] = g_c; gout[M:, 0] = g_f.reshape(-1)
+    scales = torch.tensor([256.0, 1024.0], device="cuda")
+    outs = []
+    for stencil in (True, False):
+        gt = torch.zeros_like(net.encoder.embeddings); a0 = torch.zeros(64, 36, device="cuda"); a1 = torch.zeros(16, 64, device="cuda")
+        if stencil:
+            rc = L.ac_nsr_sdf_backward_stencil(ctypes.byref(m), _lib.ptr(P), M, bound, eps, _lib.ptr(g_c), _lib.ptr(g_f), _lib.ptr(scales), _lib.ptr(gt),
+                                               _lib.ptr(a0), _lib.ptr(a1), _lib.stream_ptr())
+        else:
+            rc = L.ac_nsr_sdf_backward_fused(ctypes.byref(m), _lib.ptr(flat), _lib.ptr(gout), 7 * M, bound, _lib.ptr(scales), _lib.ptr(gt), _lib.ptr(a0),
+                                             _lib.ptr(a1), _lib.stream_ptr())
+        _lib.check(rc, "backward")
+        outs.append((gt, a0, a1))
+    for a, b in zip(outs[0], outs[1]):                       # same arithmetic, only the order of the fp32 reductions differs
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
