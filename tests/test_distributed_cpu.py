@@ -108,3 +108,39 @@ def test_cfg_pair_split_over_two_ranks_equals_single_process():
     for p in ps:
         p.join(timeout=60)
     assert torch.equal(got[0], got[1]) and torch.allclose(got[0], want, atol=1e-7) and float(want.abs().max()) > 0
+
+
+def _shard_render_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from avatarcraft_b200.utils.distributed import render_rays_sharded
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = torch.arange(24.0).reshape(8, 3); d = torch.ones(8, 3)
+    calls = []
+
+    def fake_render(a, b):                      # a "render" whose pixel depends only on its own ray
+        calls.append(a.shape[0])
+        return a * 2.0 + b
+
+    full = render_rays_sharded(fake_render, o, d, rank, world)
+    q.put((rank, full, calls))
+    dist.destroy_process_group()
+
+
+def test_pass1_ray_sharding_reassembles_the_whole_image():
+    """Pass 1 of a multi-GPU step: each rank renders n/world rays, ONE all-gather gives every rank the full image."""
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_shard_render_worker, args=(r, 2, 29573, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = {r: (img, calls) for r, img, calls in (q.get(timeout=120) for _ in range(2))}
+    for p in ps:
+        p.join(timeout=60)
+    want = torch.arange(24.0).reshape(8, 3) * 2.0 + 1.0
+    for r in range(2):
+        assert torch.equal(got[r][0], want) and got[r][1] == [4]       # half of the rays rendered locally, whole image held
