@@ -218,6 +218,16 @@ __device__ __forceinline__ float softplus100_mufu(float x) {
     return fmaf(l, 0.006931471805599453f, fmaxf(x, 0.0f));
 }
 
+// sigmoid(t) with two MUFU ops (ex2.approx, rcp.approx): relative error ~2e-7.  Used for softplus'(a) = sigmoid(100 a) in
+// the training backward, where it multiplies an upstream gradient (the libdevice expf + IEEE divide it replaces cost ~20
+// instructions per hidden unit).
+__device__ __forceinline__ float sigmoid_mufu(float t) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+
 // Hash-encode a point given in world units (HashEncoder.forward, hashgrid.py:126-142):
 // x01 = (x + bound) / (2*bound); out-of-range -> all-zero features (hashencoder.cu:94-119).
 // Fills in[0..35] = {x, y, z, 32 features, 0} -- the SDF network's input row
