@@ -131,3 +131,27 @@ def test_entry_scripts_run_end_to_end(tmp_path):
     ref = state_dict("trained", 43)
     assert set(sd.keys()) == set(ref.keys())
     assert float((sd["encoder.embeddings"] - ref["encoder.embeddings"]).abs().max()) > 0
+
+
+def test_stylize_with_sds_guidance_and_resume(tmp_path):
+    """stylize.py --guidance sds (SD-1.5-shaped networks, random weights: the HF checkpoints are not available offline)
+    for one view, then a second run resumed from its checkpoint: optimiser moments and the step counter come back."""
+    import os, subprocess, sys
+    from tests.util import ROOT
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    run = lambda *a: subprocess.run([sys.executable, os.path.join(ROOT, "stylize.py"), "--synthetic", "--exp_name", "g", "--render_h", "64",
+                                     "--render_w", "64", "--n_views", "1", "--fine_epochs", "0", "--subsample_scale", "1", "--batch_size", "4096",
+                                     "--guidance", "sds", *a], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    r = run("--coarse_epochs", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    ck = tmp_path / "style" / "canonical_360" / "g" / "g.pth.tar"
+    res = torch.load(str(ck)[:-len(".pth.tar")] + ".resume.pt", map_location="cpu", weights_only=False)
+    assert res["step"] == 1 and res["optimizer"]["step"] == 1 and float(res["optimizer"]["exp_avg"].abs().max()) > 0
+    first = torch.load(ck, map_location="cpu")
+    r = run("--coarse_epochs", "2", "--resume", str(ck))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "resumed from" in r.stdout and "optimizer state restored" in r.stdout
+    res2 = torch.load(str(ck)[:-len(".pth.tar")] + ".resume.pt", map_location="cpu", weights_only=False)
+    assert res2["step"] == 2 and res2["optimizer"]["step"] == 2
+    second = torch.load(ck, map_location="cpu")
+    assert float((second["encoder.embeddings"] - first["encoder.embeddings"]).abs().max()) > 0
