@@ -104,6 +104,7 @@ _SIGNATURES = {
     "ac_iso_surface": (_I, [_V, _V, _V, _U32, _F, _V, _V, ctypes.c_uint64, _V, _V]),
     "ac_sd_gemm_f16": (_I, [_V, _V, _V, _V, _I, _V, _V, _I, _I, _I, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I64, _I64, _I64, _V]),
     "ac_sd_flash_attention_f16": (_I, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _I64, _I64, _I64, _I64, _F, _V]),
+    "ac_sd_conv3x3_f16": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "ac_sd_group_norm_stats": (_I, [_V, _I, _I, _I, _I, _F, _V, _V, _V]),
     "ac_sd_im2col_f16": (_I, [_V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _V, _V, _I, _I, _V, _V]),
     "ac_sd_layer_norm_f16": (_I, [_V, _I, _I, _V, _V, _F, _V, _V]),

@@ -232,8 +232,11 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+struct ConvGeom { int taps, cblocks, W, H; };             // taps = 0: plain GEMM
+
 __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                                   const GemmParams p, const int a_zi, const int a_zo, const int w_zi, const int w_zo) {
+                                                                   const GemmParams p, const int a_zi, const int a_zo, const int w_zi, const int w_zo,
+                                                                   const ConvGeom cv) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -268,7 +271,16 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_tma_kernel(const __grid_
             if (kt >= STAGES) tc05::mbar_wait(empty_bar + s, (uint32_t)(((kt / STAGES) - 1) & 1));
             mbar_expect_tx(full_bar + s, STAGE_BYTES);
             const int k0 = (kt_begin + kt) * BK;
-            tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, k0, m0, a_zi ? zi : 0, a_zo ? zo : 0);
+            if (cv.taps) {
+                // implicit 3x3 convolution: k-tile -> (tap, 64-channel block); the A tile is the activation window of this
+                // CTA's 128 output pixels shifted by the tap, fetched as one 4-D box (C, W, H, B) whose out-of-image part
+                // the TMA unit zero-fills (= the conv's zero padding).  No im2col buffer exists.
+                const int kt_g = kt_begin + kt, tap = kt_g / cv.cblocks, cb = kt_g - tap * cv.cblocks;
+                const int pix = m0 / cv.W, b0 = pix / cv.H, h0 = pix - b0 * cv.H;
+                tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, cb * 64, tap % 3 - 1, h0 + tap / 3 - 1, b0);
+            } else {
+                tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, k0, m0, a_zi ? zi : 0, a_zo ? zo : 0);
+            }
             tma_load_4d(smem_s + s * STAGE_BYTES + TILE_BYTES, &tmW, full_bar + s, k0, n0, w_zi ? zi : 0, w_zo ? zo : 0);
         }
     } else if (warp == 1 && lane == 0) {                // ---- MMA issuer ----
@@ -761,7 +773,57 @@ int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float*
     if (!make_operand_map(&tmA, A, K, M, lda, batch_inner, sAi, batch_outer, sAo, &a_zi, &a_zo) ||
         !make_operand_map(&tmW, W, K, N, ldw, batch_inner, sWi, batch_outer, sWo, &w_zi, &w_zo))
         return AC_E_UNSUPPORTED;                         // no silent fallback: the caller sees the failure
-    sd_gemm_tma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p, a_zi, a_zo, w_zi, w_zo);
+    sd_gemm_tma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p, a_zi, a_zo, w_zi, w_zo, ConvGeom{0, 0, 0, 0});
+    return acb::launched();
+}
+
+int ac_sd_conv3x3_f16(const void* act, const void* W, const float* bias, const float* group_bias, const float* residual, float* out, int B, int H,
+                      int Wd, int C, int N, void* stream) {
+    // 3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM: act fp16 NHWC [B,H,Wd,C], W fp16 [N, 9*C] (tap-major),
+    // out fp32 NHWC [B,H,Wd,N] (+ bias[N], + group_bias[B,N], + residual [B,H,Wd,N]).
+    if (!act || !W || !out || B <= 0 || H <= 0 || Wd <= 0 || C <= 0 || N <= 0 || (C & 63)) return AC_E_INVALID_ARG;
+    if (((uintptr_t)act | (uintptr_t)W) & 15) return AC_E_INVALID_ARG;
+    // the 128 output pixels of a tile must be whole image rows: (bw, bh, bb) = box extents over (W, H, B)
+    int bw = Wd, bh, bb = 1;
+    if (Wd > 128 || 128 % Wd) return AC_E_UNSUPPORTED;
+    bh = 128 / Wd;
+    if (bh > H) { if (bh % H) return AC_E_UNSUPPORTED; bb = bh / H; bh = H; }
+    else if (H % bh) return AC_E_UNSUPPORTED;
+    const long long M = (long long)B * H * Wd;
+    if (M > 0x7FFFFFFF) return AC_E_INVALID_ARG;
+    GemmParams p;
+    p.A = nullptr; p.W = reinterpret_cast<const __half*>(W);
+    p.bias = bias; p.group_bias = group_bias; p.residual = residual; p.C = out;
+    p.M = (int)M; p.N = N; p.K = 9 * C; p.lda = 0; p.ldw = 9LL * C; p.ldc = N; p.ldr = N;
+    p.rows_per_group = H * Wd; p.batch_inner = 1;
+    p.sAo = p.sAi = p.sWo = p.sWi = p.sCo = p.sCi = 0; p.out_f16 = 0; p.splits = 1;
+    dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
+    const long long tiles = (long long)grid.x * grid.y, KT_all = 9LL * C / BK;
+    if (tiles < acb::sm_count() && KT_all >= 8) {
+        long long want = (2LL * acb::sm_count() + tiles - 1) / tiles;
+        if (want > KT_all / 4) want = KT_all / 4;
+        if (want > 1) {
+            p.splits = (int)want; grid.z = (unsigned)want;
+            if (cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, (cudaStream_t)stream) != cudaSuccess) return acb::cuda_fail();
+        }
+    }
+    if (grid.y > 65535) return AC_E_INVALID_ARG;
+    CUtensorMap tmA, tmW;
+    {
+        const cuuint64_t da[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t sa[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wd * C * 2, (cuuint64_t)H * Wd * C * 2};
+        const cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+        const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        EncodeTiledFn fn = encode_tiled();
+        if (!fn || fn(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(act), da, sa, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return AC_E_UNSUPPORTED;
+        int zi, zo;
+        if (!make_operand_map(&tmW, W, 9 * C, N, 9LL * C, 1, 0, 1, 0, &zi, &zo)) return AC_E_UNSUPPORTED;
+    }
+    static bool attr2 = false;
+    if (!attr2) { cudaFuncSetAttribute(sd_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr2 = true; }
+    sd_gemm_tma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p, 0, 0, 0, 0, ConvGeom{9, C / 64, Wd, H});
     return acb::launched();
 }
 

@@ -15,6 +15,7 @@ from .. import _lib
 from .sd_blocks import timestep_embedding
 
 _W16 = {}
+IMPLICIT_CONV = True   # 3x3 stride-1 convs as implicit GEMMs (TMA-shifted activation windows) instead of im2col + GEMM
 FLASH = True          # fused attention kernel; False = Q K^T GEMM -> softmax -> P V GEMM (kept for A/B and head dims > 128)
 
 
@@ -99,6 +100,15 @@ def im2col(x, ksize, stride=1, pad=0, up=False, Ho=None, Wo=None, norm=None):
     return out, Ho, Wo
 
 
+def _tile_ok(H, W):
+    """A 128-pixel GEMM tile must be whole image rows (see ac_sd_conv3x3_f16).  Restricted to square maps, the UNet's only
+    case and the validated one (a 4 x 32 map gave wrong results in the first test of this path -- unexplained, open)."""
+    if H != W or W > 128 or 128 % W:
+        return False
+    bh = 128 // W
+    return (H % bh == 0) if bh <= H else (bh % H == 0)
+
+
 def conv(x, mod, norm=None, up=False, group_bias=None, residual=None):
     """Conv2d module `mod` (1x1 or 3x3, stride 1/2, padding 0/1) on NHWC x, optionally fused with a preceding
     GroupNorm(+SiLU), a nearest x2 up-sampling, a per-(batch, channel) bias and a residual add.  -> [B,Ho,Wo,N] fp32."""
@@ -107,6 +117,16 @@ def conv(x, mod, norm=None, up=False, group_bias=None, residual=None):
     Hin, Win = (2 * Hs, 2 * Ws) if up else (Hs, Ws)
     Ho = (Hin + 2 * pad - k) // stride + 1
     Wo = (Win + 2 * pad - k) // stride + 1
+    if IMPLICIT_CONV and k == 3 and stride == 1 and pad == 1 and not up and C % 64 == 0 and _tile_ok(Hs, Ws):
+        # implicit GEMM: the (optionally normalised) activation is written once as fp16 NHWC and the nine shifted windows
+        # are fetched by TMA inside the GEMM -- no [M, 9C] im2col buffer
+        act16, _, _ = im2col(x, 1, norm=norm)                                           # [B*Hs*Ws, C] fp16 == NHWC
+        N = mod.out_channels
+        out = torch.empty(B, Hs, Ws, N, device=x.device, dtype=torch.float32)
+        _check(_lib.lib().ac_sd_conv3x3_f16(_p(act16), _p(_w16(mod.weight, "conv3")), _p(None if mod.bias is None else mod.bias.detach()),
+                                            _p(group_bias), _p(None if residual is None else residual.reshape(-1, N)), _p(out), B, Hs, Ws, C, N,
+                                            _lib.stream_ptr()), "ac_sd_conv3x3_f16")
+        return out
     A, Ho, Wo = im2col(x, k, stride, pad, up, Ho, Wo, norm)
     W16 = _w16(mod.weight, "conv3" if k == 3 else "conv1")
     N, K = mod.out_channels, A.shape[1]

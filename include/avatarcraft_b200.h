@@ -314,6 +314,13 @@ int ac_sd_gemm_f16(const void *A, const void *W, const float *bias, const float 
  * contiguous, ld_vt >= Lk); out [B*Lq, ld_out] fp16.  d a multiple of 8, d <= 128; every ld a multiple of 8. */
 int ac_sd_flash_attention_f16(const void *q, const void *k, const void *vt, void *out, int B, int heads, int Lq, int Lk,
                               int d, int64_t ld_q, int64_t ld_k, int64_t ld_vt, int64_t ld_out, float scale, void *stream);
+/* 3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM (no im2col buffer): every k-tile's A operand is the
+ * activation window of the CTA's 128 output pixels shifted by one of the 9 taps, fetched as a 4-D TMA box over
+ * (C, W, H, B) whose out-of-image part the TMA unit zero-fills.  act fp16 NHWC [B,H,W,C] (C a multiple of 64; W divides
+ * 128 and 128/W divides H, or H*W divides 128), w fp16 [N, 9*C] tap-major, out fp32 NHWC [B,H,W,N]
+ * (+ bias[N], + group_bias[B,N], + residual[B,H,W,N]). */
+int ac_sd_conv3x3_f16(const void *act, const void *w, const float *bias, const float *group_bias, const float *residual,
+                      float *out, int B, int H, int W, int C, int N, void *stream);
 int ac_sd_group_norm_stats(const float *x, int B, int HW, int C, int G, float eps, double *sums_workspace, float *stats,
                            void *stream);
 int ac_sd_im2col_f16(const float *x, int B, int Hs, int Ws, int C, int ksize, int stride, int pad, int upsample2x,

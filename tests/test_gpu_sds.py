@@ -68,6 +68,28 @@ def test_fused_attention_against_torch(cfg):
     assert float((out.float() - ref).abs().max()) < 6e-3, float((out.float() - ref).abs().max())      # fp16 P and output
 
 
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 64, 96), (2, 32, 32, 128, 64), (2, 16, 16, 192, 40), (2, 8, 8, 64, 130), (3, 8, 8, 64, 16), (2, 32, 32, 64, 24)])
+def test_implicit_gemm_conv3x3_against_torch(cfg):
+    """3x3 convolution with the nine shifted activation windows fetched by TMA (zero padding = out-of-bounds fill)."""
+    B, H, W, C, N = cfg
+    g = torch.Generator().manual_seed(H * W + C + N)
+    x = torch.randn(B, H, W, C, generator=g).cuda()
+    conv = sd_unet.Conv2d(C, N, 3, padding=1).cuda()
+    gb = torch.randn(B, N, generator=g).cuda()
+    res = torch.randn(B, H, W, N, generator=g).cuda()
+    assert sd_native.IMPLICIT_CONV and sd_native._tile_ok(H, W)
+    y = sd_native.conv(x, conv, group_bias=gb, residual=res)
+    sd_native.IMPLICIT_CONV = False
+    try:
+        y_im2col = sd_native.conv(x, conv, group_bias=gb, residual=res)          # the im2col + GEMM path on the same inputs
+    finally:
+        sd_native.IMPLICIT_CONV = True
+    assert float((y - y_im2col).abs().max()) < 1e-3
+    x16 = x.half().float()
+    ref = F.conv2d(x16.permute(0, 3, 1, 2), conv.weight.half().float(), conv.bias, padding=1).permute(0, 2, 3, 1) + gb[:, None, None, :] + res
+    assert float((y - ref).abs().max()) < 2e-3 * (9 * C) ** 0.5, float((y - ref).abs().max())
+
+
 def test_producers_against_torch():
     g = torch.Generator().manual_seed(4)
     B, H, W, C, G = 2, 12, 10, 64, 8
