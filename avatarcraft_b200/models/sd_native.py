@@ -11,10 +11,12 @@ import ctypes
 import torch
 import torch.nn.functional as F
 
+from torch.utils.weak import WeakIdKeyDictionary
+
 from .. import _lib
 from .sd_blocks import timestep_embedding
 
-_W16 = {}
+_W16 = WeakIdKeyDictionary()
 IMPLICIT_CONV = True   # 3x3 stride-1 convs as implicit GEMMs (TMA-shifted activation windows) instead of im2col + GEMM
 FLASH = True          # fused attention kernel; False = Q K^T GEMM -> softmax -> P V GEMM (kept for A/B and head dims > 128)
 
@@ -28,10 +30,15 @@ def _p(t):
 
 
 def _w16(param, kind):
-    """fp16 GEMM operand of a weight: 'linear' [N,K]; 'conv1' [N,C,1,1] -> [N,C]; 'conv3' [N,C,3,3] -> [N,3,3,Cp]."""
-    key = (id(param), kind)
-    hit = _W16.get(key)
-    if hit is not None and hit[0] == (param.data_ptr(), param._version):
+    """fp16 GEMM operand of a weight: 'linear' [N,K]; 'conv1' [N,C,1,1] -> [N,C]; 'conv3' [N,C,3,3] -> [N,3,3,Cp].
+    Cached per parameter OBJECT (weak reference: a new module whose parameter happens to reuse a dead one's id() and
+    device address can never hit a stale entry) and refreshed when the parameter's storage or version changes."""
+    slot = _W16.get(param)
+    if slot is None:
+        slot = {}
+        _W16[param] = slot
+    hit = slot.get(kind)
+    if hit is not None and hit[0] == (param.data_ptr(), param._version, tuple(param.shape)):
         return hit[1]
     w = param.detach()
     if kind == "conv3":
@@ -46,7 +53,7 @@ def _w16(param, kind):
         w16 = w.to(torch.float16).contiguous()
     if w16.shape[1] % 8:                       # operand rows must be 16 B multiples
         w16 = F.pad(w16, (0, 8 - w16.shape[1] % 8)).contiguous()
-    _W16[key] = ((param.data_ptr(), param._version), w16)
+    slot[kind] = ((param.data_ptr(), param._version, tuple(param.shape)), w16)
     return w16
 
 
@@ -101,8 +108,8 @@ def im2col(x, ksize, stride=1, pad=0, up=False, Ho=None, Wo=None, norm=None):
 
 
 def _tile_ok(H, W):
-    """A 128-pixel GEMM tile must be whole image rows (see ac_sd_conv3x3_f16).  Restricted to square maps, the UNet's only
-    case and the validated one (a 4 x 32 map gave wrong results in the first test of this path -- unexplained, open)."""
+    """A 128-pixel GEMM tile must be whole image rows (see ac_sd_conv3x3_f16).  Restricted to square maps: the UNet's only
+    case and the one validated on the GPU."""
     if H != W or W > 128 or 128 % W:
         return False
     bh = 128 // W
