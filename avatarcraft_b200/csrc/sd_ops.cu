@@ -5,14 +5,18 @@
 // fp16 and every contraction runs on the 5th-generation tensor cores:
 //
 //   ac_sd_gemm_f16      C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ group_bias[m / rows_per_group, N]) (+ residual[M,N])
-//                       tcgen05.mma kind::f16, M128 x N128 x K16, fp32 accumulators in TMEM (128 columns), operands
-//                       staged by cp.async (16 B, zero-filled past M / N / K) straight into the K-major no-swizzle
-//                       core-matrix layout, 3-stage ring released by tcgen05.commit -> mbarrier; batched through
-//                       blockIdx.z with a two-level (outer, inner) stride so per-head slices of [B, L, heads*d] need
-//                       no copies.  Linear layers, 1x1 convs, 3x3 convs (after im2col), Q K^T and P V all use it.
+//                       tcgen05.mma kind::f16, M128 x N128 x K16, fp32 accumulators in TMEM (128 columns).  Default main
+//                       loop: operands by TMA (cp.async.bulk.tensor 4-D tiles, SWIZZLE_128B, zero-filled past M / N / K),
+//                       full/empty mbarrier ring, one elected producer thread and one elected MMA thread; batched through
+//                       blockIdx.z with a two-level (outer, inner) stride folded into the tensor map, so per-head slices of
+//                       [B, L, heads*d] need no copies; split-K for weight-streaming shapes.  The first version (cp.async
+//                       into the no-swizzle layout, one __syncthreads per k-tile) is kept behind AC_SD_GEMM=cpasync.
+//   ac_sd_conv3x3_f16   the same kernel as an implicit GEMM: the A tile of k-tile (tap, channel block) is the activation
+//                       window of the CTA's 128 output pixels shifted by the tap, one 4-D TMA box; no im2col buffer.
+//   ac_sd_flash_attention_f16   softmax(scale Q K^T) V per (batch, head, 128 queries) with the scores kept on the SM.
 //   producers           write the fp16 A operand of the next GEMM: GroupNorm(+SiLU) applied on the fly inside the
-//                       im2col of a 3x3 conv (stride 1/2, optional nearest x2 up-sampling of the source),
-//                       GroupNorm -> fp16, LayerNorm -> fp16, GEGLU -> fp16, softmax -> fp16, plain cast.
+//                       normalise-and-cast / im2col producer (3x3 stride 2, nearest x2 up-sampling), LayerNorm -> fp16,
+//                       GEGLU -> fp16, softmax -> fp16 (unfused attention path, head dims > 128), plain cast.
 //
 // HBM traffic is irrelevant at these sizes (the largest activation is 10 MB); the GEMMs are L2-bandwidth / tensor bound.
 #include <cuda.h>

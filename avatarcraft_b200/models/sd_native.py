@@ -1,6 +1,6 @@
 """Native (sm_100a) forward of the Stable-Diffusion UNet for the SDS step: walks a `UNet2DConditionModel`'s parameters
-and evaluates it with the kernels of csrc/sd_ops.cu -- tcgen05 GEMMs fed by fused GroupNorm/SiLU/im2col, LayerNorm,
-GEGLU, softmax producers.  Same arithmetic graph as `UNet2DConditionModel.forward` (the autograd / torch-op path),
+and evaluates it with the kernels of csrc/sd_ops.cu -- TMA-fed tcgen05 GEMMs, implicit-GEMM 3x3 convolutions, a fused
+attention kernel, and GroupNorm/SiLU, LayerNorm, GEGLU producers of the fp16 operands.  Same arithmetic graph as `UNet2DConditionModel.forward` (the autograd / torch-op path),
 with fp16 GEMM operands and fp32 accumulation; tests/test_gpu_sds.py compares the two on identical weights.
 
 Layout: activations are contiguous fp32 [B, H, W, C] (== the [B*H*W, C] token matrix); fp16 copies of the weights
@@ -160,8 +160,9 @@ def layer_norm16(x, mod):
 
 def attention(xq16, ctx16, attn, B, Lq, Lk, residual):
     """Multi-head attention of module `attn` (to_q/to_k/to_v/to_out.0): xq16 [B*Lq, Cq] fp16, ctx16 [B*Lk, Cc] fp16
-    -> to_out(softmax(q k^T * scale) v) + residual, fp32 [B*Lq, Cq].  Two batched GEMMs around the softmax kernel; V is
-    produced already transposed ([B, inner, Lk]) by swapping the GEMM operands, so P V needs no transpose."""
+    -> to_out(softmax(q k^T * scale) v) + residual, fp32 [B*Lq, Cq].  V is produced already transposed ([B, inner, Lk]) by
+    swapping the value projection's GEMM operands; head dims <= 128 go through the fused attention kernel (scores stay
+    on the SM), larger ones through two batched GEMMs around the softmax kernel."""
     dev = xq16.device
     heads = attn.heads
     inner = attn.to_q.out_features
