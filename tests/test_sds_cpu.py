@@ -117,3 +117,25 @@ def test_text_embeds_are_uncond_then_text():
     e = sd.get_text_embeds("a photo of a knight")
     assert e.shape == (2, 77, 32)
     assert torch.equal(e[:1], sd.get_text_embeds("something else")[:1]) and not torch.equal(e[0], e[1])
+
+
+def test_fp16_weight_cache_follows_the_parameter_object():
+    """The native path caches fp16 GEMM operands per parameter: keyed by weak reference (a new parameter that reuses a
+    dead one's id() / address must not see its copy), refreshed on in-place updates, conv kernels permuted tap-major."""
+    import gc
+    from avatarcraft_b200.models import sd_native
+    n0 = len(sd_native._W16)
+    p = torch.nn.Parameter(torch.randn(8, 16))
+    a = sd_native._w16(p, "linear")
+    assert a.dtype == torch.float16 and sd_native._w16(p, "linear") is a and len(sd_native._W16) == n0 + 1
+    with torch.no_grad():
+        p.add_(1.0)
+    b = sd_native._w16(p, "linear")
+    assert b is not a and torch.allclose(b.float(), p.detach(), atol=1e-2)
+    w = torch.nn.Parameter(torch.randn(5, 4, 3, 3))
+    c = sd_native._w16(w, "conv3")                                   # [N, ky, kx, Cp] with Cp = 8, zero padded
+    assert c.shape == (5, 72) and torch.equal(c.reshape(5, 3, 3, 8)[..., 4:], torch.zeros(5, 3, 3, 4, dtype=torch.float16))
+    assert torch.allclose(c.reshape(5, 3, 3, 8)[..., :4].float(), w.detach().permute(0, 2, 3, 1), atol=1e-2)
+    del p, w, a, b, c
+    gc.collect()
+    assert len(sd_native._W16) == n0
