@@ -24,6 +24,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <mutex>
 
 #include "../../include/avatarcraft_b200.h"
 #include "launch_util.cuh"
@@ -59,9 +62,18 @@ constexpr uint32_t kTmemCols = 512;             // one 128x64 fp32 accumulator p
 // fp32 weights of the register epilogues live in the constant bank: every lane reads the same element, the
 // index is a compile-time constant after unrolling, so they fold into FFMA operands (c[bank][offset]) and cost
 // neither a load instruction nor MIO-queue bandwidth.  Refreshed from the blob's OFF_EPI block by a 6 KB D2D
-// copy on the launch stream before every render launch.
-__constant__ float c_w[EPI_FLOATS];
+// copy on the launch stream before every launch.
+// Re-entrancy: the bank holds kSlots copies and every kernel is instantiated once per slot (the slot must be a
+// compile-time constant for the operand folding).  A launch leases the next slot round-robin, makes its stream
+// wait for the event of the slot's previous user, copies, launches and records the slot's event (SlotLease at the
+// end of this file): launches of different models on different streams never share a copy.
+#ifndef AC_CW_SLOTS
+#define AC_CW_SLOTS 4
+#endif
+constexpr int kSlots = AC_CW_SLOTS;
+__constant__ float c_w[kSlots][EPI_FLOATS];
 constexpr int W_XB = EPI_XB, W_W1T = EPI_W1T, W_B1 = EPI_B1, W_C2T = EPI_C2T;
+#define CW(i) c_w[SLOT][(i)]
 
 // dynamic shared memory map (bytes)
 constexpr size_t SM_LEVELS = 0;
@@ -87,7 +99,7 @@ struct RenderParamsTC {
 struct Group {
     unsigned char* a;     // this group's A region (generic pointer)
     uint32_t a_s;         // ... and its shared-space address
-    uint32_t b_s;         // shared-space address of the weight tiles
+    uint32_t b_s;         // shared-space address of the weight tiles (layout B_*: W0 | C0 | C1, each hi then lo)
     uint64_t* bar;
     uint32_t phase;
     uint32_t tmem;        // accumulator address of this thread's row (lane field set), column 0 of the group
@@ -175,10 +187,10 @@ __device__ __noinline__ void encode_to_tile(unsigned char* arow, const float2* _
 
 // Epilogue of the SDF network for this thread's accumulator row: + raw-xyz columns + bias (exact fp32),
 // softplus, second layer 64 -> {1, 16}.
-template <bool FULL>
+template <int SLOT, bool FULL>
 __device__ __forceinline__ void sdf_tail(uint32_t tmem_row, float x, float y, float z, float (&out)[FULL ? 16 : 1]) {
 #pragma unroll
-    for (int o = 0; o < (FULL ? 16 : 1); ++o) out[o] = c_w[W_B1 + o];
+    for (int o = 0; o < (FULL ? 16 : 1); ++o) out[o] = CW(W_B1 + o);
 #pragma unroll
     for (int qtr = 0; qtr < 4; ++qtr) {
         float acc[16];
@@ -186,26 +198,27 @@ __device__ __forceinline__ void sdf_tail(uint32_t tmem_row, float x, float y, fl
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
             const int j = qtr * 16 + jj;
-            const float lin = fmaf(c_w[W_XB + 4 * j], x, fmaf(c_w[W_XB + 4 * j + 1], y, fmaf(c_w[W_XB + 4 * j + 2], z, c_w[W_XB + 4 * j + 3])));
+            const float lin = fmaf(CW(W_XB + 4 * j), x, fmaf(CW(W_XB + 4 * j + 1), y, fmaf(CW(W_XB + 4 * j + 2), z, CW(W_XB + 4 * j + 3))));
             const float h = softplus100_mufu(acc[jj] + lin);
             if (FULL) {
 #pragma unroll
-                for (int o = 0; o < 16; ++o) out[o] = fmaf(c_w[W_W1T + j * 16 + o], h, out[o]);
+                for (int o = 0; o < 16; ++o) out[o] = fmaf(CW(W_W1T + j * 16 + o), h, out[o]);
             } else {
-                out[0] = fmaf(c_w[W_W1T + j * 16], h, out[0]);
+                out[0] = fmaf(CW(W_W1T + j * 16), h, out[0]);
             }
         }
     }
 }
+template <int SLOT>
 __device__ __noinline__ float sdf_tail_scalar(uint32_t tmem_row, float x, float y, float z) {
     float o[1];
-    sdf_tail<false>(tmem_row, x, y, z, o);
+    sdf_tail<SLOT, false>(tmem_row, x, y, z, o);
     return o[0];
 }
 
 // Encode -> A tile -> tcgen05.mma -> epilogue.  Must be called by all 128 threads of the group, the same
 // number of times.
-template <bool FULL>
+template <int SLOT, bool FULL>
 __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restrict__ table, const LevelMeta* __restrict__ lv,
                                                float bound, float x, float y, float z, float (&out)[FULL ? 16 : 1]) {
     encode_to_tile(g.a + g.row * 16, table, lv, bound, x, y, z, g.std_layout);
@@ -213,13 +226,13 @@ __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restric
     if constexpr (FULL) {
 #if AC_FULL_TAIL_LOOP
 #pragma unroll
-        for (int o = 0; o < 16; ++o) out[o] = c_w[W_B1 + o];
+        for (int o = 0; o < 16; ++o) out[o] = CW(W_B1 + o);
 #pragma unroll 1
         for (int qtr = 0; qtr < 4; ++qtr) {
             float acc[16];
             tc05::tmem_ld16(g.tmem + qtr * 16, acc);
-            const float* __restrict__ xb = c_w + W_XB + 64 * qtr;
-            const float* __restrict__ w1 = c_w + W_W1T + 256 * qtr;
+            const float* __restrict__ xb = c_w[SLOT] + W_XB + 64 * qtr;
+            const float* __restrict__ w1 = c_w[SLOT] + W_W1T + 256 * qtr;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const float lin = fmaf(xb[4 * jj], x, fmaf(xb[4 * jj + 1], y, fmaf(xb[4 * jj + 2], z, xb[4 * jj + 3])));
@@ -229,32 +242,17 @@ __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restric
             }
         }
 #else
-        sdf_tail<true>(g.tmem, x, y, z, out);
+        sdf_tail<SLOT, true>(g.tmem, x, y, z, out);
 #endif
     } else {
-        out[0] = sdf_tail_scalar(g.tmem, x, y, z);
+        out[0] = sdf_tail_scalar<SLOT>(g.tmem, x, y, z);
     }
 }
 
-// Colour MLP 21 -> 64 -> 64 -> 3 (models/instant_nsr.py:644-663) for the group's 128 samples.
-// cin = (x, y, z, nx, ny, nz, 15 geometry features); all 128 threads of the group call it together.
-__device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24], float (&rgb)[3]) {
-    // layer 0: K = 32 (21 inputs + zero pad), fp16x3
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4 hi, lo;
-        if (c < 3) {
-            tc05::split_f16x2(cin[8 * c + 0], cin[8 * c + 1], hi.x, lo.x);
-            tc05::split_f16x2(cin[8 * c + 2], cin[8 * c + 3], hi.y, lo.y);
-            tc05::split_f16x2(cin[8 * c + 4], cin[8 * c + 5], hi.z, lo.z);
-            tc05::split_f16x2(cin[8 * c + 6], cin[8 * c + 7], hi.w, lo.w);
-        } else {
-            hi = make_uint4(0u, 0u, 0u, 0u); lo = hi;
-        }
-        *reinterpret_cast<uint4*>(g.a + c * 2048 + g.row * 16) = hi;
-        *reinterpret_cast<uint4*>(g.a + 8192 + c * 2048 + g.row * 16) = lo;
-    }
-    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_C0_HI, g.b_s + B_C0_LO); });
+// Colour MLP 21 -> 64 -> 64 -> 3 (models/instant_nsr.py:644-663) for the group's 128 samples, after layer 0's MMA has
+// been committed: relu -> layer 1 (fp16 activations x (hi, lo) weights) -> relu -> 64 -> 3 head -> sigmoid.
+template <int SLOT>
+__device__ __forceinline__ void group_color_rest(Group& g, float (&rgb)[3]) {
     // relu -> fp16 -> A tile of layer 1 (K = 64 = 8 chunks, fills the whole 16 KB region)
 #pragma unroll
     for (int qtr = 0; qtr < 4; ++qtr) {
@@ -290,10 +288,32 @@ __device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24
         for (int jj = 0; jj < 16; ++jj) {
             const float h2 = fmaxf(acc[jj], 0.f);
             const int j = qtr * 16 + jj;
-            o0 = fmaf(c_w[W_C2T + 4 * j], h2, o0); o1 = fmaf(c_w[W_C2T + 4 * j + 1], h2, o1); o2 = fmaf(c_w[W_C2T + 4 * j + 2], h2, o2);
+            o0 = fmaf(CW(W_C2T + 4 * j), h2, o0); o1 = fmaf(CW(W_C2T + 4 * j + 1), h2, o1); o2 = fmaf(CW(W_C2T + 4 * j + 2), h2, o2);
         }
     }
     rgb[0] = sigmoidf(o0); rgb[1] = sigmoidf(o1); rgb[2] = sigmoidf(o2);
+}
+
+// cin = (x, y, z, nx, ny, nz, 15 geometry features); all 128 threads of the group call it together.
+template <int SLOT>
+__device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24], float (&rgb)[3]) {
+    // layer 0: K = 32 (21 inputs + zero pad), fp16x3
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 hi, lo;
+        if (c < 3) {
+            tc05::split_f16x2(cin[8 * c + 0], cin[8 * c + 1], hi.x, lo.x);
+            tc05::split_f16x2(cin[8 * c + 2], cin[8 * c + 3], hi.y, lo.y);
+            tc05::split_f16x2(cin[8 * c + 4], cin[8 * c + 5], hi.z, lo.z);
+            tc05::split_f16x2(cin[8 * c + 6], cin[8 * c + 7], hi.w, lo.w);
+        } else {
+            hi = make_uint4(0u, 0u, 0u, 0u); lo = hi;
+        }
+        *reinterpret_cast<uint4*>(g.a + c * 2048 + g.row * 16) = hi;
+        *reinterpret_cast<uint4*>(g.a + 8192 + c * 2048 + g.row * 16) = lo;
+    }
+    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_C0_HI, g.b_s + B_C0_LO); });
+    group_color_rest<SLOT>(g, rgb);
 }
 
 // Weight W[n][k] (n < 64) -> fp16 (hi, lo) tiles in the UMMA K-major layout: chunk k/8, row n, element k%8.
@@ -305,6 +325,7 @@ __device__ __forceinline__ void stage_b_tile(unsigned char* bhi, unsigned char* 
     *reinterpret_cast<__half*>(blo + at) = l;
 }
 
+template <int SLOT>
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const RenderParamsTC p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 float x, y, zz;
                 ray_point(r, z, x, y, zz);
                 float o[1];
-                group_sdf_eval<false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
+                group_sdf_eval<SLOT, false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
                                       clampf(zz, -bound, bound), o);
                 sdfs[k] = o[0];
             }
@@ -416,7 +437,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 float x, y, zz;
                 ray_point(r, zq, x, y, zz);
                 float o[1];
-                group_sdf_eval<false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
+                group_sdf_eval<SLOT, false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
                                       clampf(zz, -bound, bound), o);
                 s_new = o[0];
             }
@@ -476,7 +497,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 const float qy = ax == 1 ? clampf(py + e, -bound, bound) : py;
                 const float qz = ax == 2 ? clampf(pz + e, -bound, bound) : pz;
                 float o[1];
-                group_sdf_eval<false>(g, table, lv, bound, qx, qy, qz, o);
+                group_sdf_eval<SLOT, false>(g, table, lv, bound, qx, qy, qz, o);
                 if (q0 + lane < 6 * nS) fd[q] = o[0];
             }
             __syncwarp();
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             float cin[24], sdf0, gn;
             {
                 float o16[16];
-                group_sdf_eval<true>(g, table, lv, bound, px, py, pz, o16);
+                group_sdf_eval<SLOT, true>(g, table, lv, bound, px, py, pz, o16);
                 sdf0 = o16[0];
 #pragma unroll
                 for (int q = 0; q < 15; ++q) cin[6 + q] = o16[1 + q];
@@ -512,7 +533,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             cin[21] = cin[22] = cin[23] = 0.f;
             __syncwarp();                                // fd[] consumed before the next block overwrites it
             float col[3];
-            group_color_eval(g, cin, col);
+            group_color_eval<SLOT>(g, cin, col);
             const float nx = cin[3], ny = cin[4], nz = cin[5];
             const float cosv = r.dx * nx + r.dy * ny + r.dz * nz;
             const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);
@@ -571,6 +592,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
 // NeRFNetwork.forward_sdf on a flat point list with the same tensor-core group machinery as the render kernel
 // (thread = point, four warps = one 128-row MMA tile): 3.7 M points per training patch, 2x the SIMT kernel's rate.
 // Staging is the render kernel's prologue restricted to what the SDF network needs.
+template <int SLOT>
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
                                                                           const float* __restrict__ blob, float S, uint32_t H,
                                                                           const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound,
@@ -635,7 +657,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const 
         const uint32_t g_first = base + (uint32_t)(group * 128);
         if (!stencil_M || g_first < stencil_M) {
             float o16[16];
-            group_sdf_eval<true>(g, table, lv, bound, px, py, pz, o16);
+            group_sdf_eval<SLOT, true>(g, table, lv, bound, px, py, pz, o16);
             if (valid) {
                 if (blk == 0) {
                     float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)smp);
@@ -647,7 +669,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const 
             }
         } else {
             float o1[1];
-            group_sdf_eval<false>(g, table, lv, bound, px, py, pz, o1);
+            group_sdf_eval<SLOT, false>(g, table, lv, bound, px, py, pz, o1);
             if (valid) out_fd[(size_t)(blk - 1) * stencil_M + smp] = o1[0];
         }
     }
@@ -700,6 +722,65 @@ __global__ void __launch_bounds__(128, 1) debug_tc_layer_kernel(const float* __r
 
 }  // namespace
 
+#include "nsr_render_st.cuh"
+
+namespace {
+// ---- constant-bank slot leases -------------------------------------------------------------------------------
+struct SlotTable {
+    cudaEvent_t ev[kSlots] = {};
+    bool has_ev[kSlots] = {};
+    unsigned next = 0;
+};
+SlotTable g_slots[64];
+std::mutex g_slot_mu;
+
+// Holds the mutex from lease to event record: the three host calls (copy, launch, record) of one launch are not
+// interleaved with another thread's, so "the slot's event" always covers the slot's latest user.
+struct SlotLease {
+    std::lock_guard<std::mutex> lock;
+    cudaStream_t st;
+    SlotTable* tab = nullptr;
+    int slot = 0;
+    bool capturing = false;
+    int rc = AC_OK;
+    SlotLease(const float* blob, cudaStream_t stream) : lock(g_slot_mu), st(stream) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { rc = acb::cuda_fail(); return; }
+        tab = &g_slots[dev];
+        slot = (int)(tab->next++ % kSlots);
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        capturing = cs != cudaStreamCaptureStatusNone;       // inside a capture the graph's own edges order the slot's users
+        if (!capturing && tab->has_ev[slot] && cudaStreamWaitEvent(st, tab->ev[slot], 0) != cudaSuccess) { rc = acb::cuda_fail(); return; }
+        if (cudaMemcpyToSymbolAsync(c_w, blob + OFF_EPI, EPI_FLOATS * sizeof(float), (size_t)slot * EPI_FLOATS * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            rc = acb::cuda_fail();
+    }
+    void launched() {
+        if (capturing || !tab) return;
+        if (!tab->has_ev[slot]) {
+            if (cudaEventCreateWithFlags(&tab->ev[slot], cudaEventDisableTiming) != cudaSuccess) return;
+            tab->has_ev[slot] = true;
+        }
+        cudaEventRecord(tab->ev[slot], st);
+    }
+};
+
+#if AC_CW_SLOTS == 4
+#define AC_SLOT_SWITCH(slot, CALL)        \
+    switch (slot) {                       \
+        case 0: { CALL(0); } break;       \
+        case 1: { CALL(1); } break;       \
+        case 2: { CALL(2); } break;       \
+        default: { CALL(3); } break;      \
+    }
+#elif AC_CW_SLOTS == 1                    /* development builds: one instantiation, 4x faster to compile */
+#define AC_SLOT_SWITCH(slot, CALL) { CALL(0); }
+#else
+#error "AC_CW_SLOTS must be 1 or 4"
+#endif
+}  // namespace
+
 namespace acb {
 int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStream_t st) {
     RenderParamsTC p;
@@ -708,31 +789,52 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
     p.S = m->log2_per_level_scale; p.H = m->base_resolution;
     p.a = *a;
     p.eik_partial = reinterpret_cast<float*>(a->workspace);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(nsr_render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); attr = true; }
-    if (cudaMemcpyToSymbolAsync(c_w, m->mlp_blob + OFF_EPI, EPI_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        return acb::cuda_fail();
+    // AC_RENDER_IMPL=tc5: the round-1 kernel (one point per lane, no stencil sharing), kept for A/B tests.
+    const char* impl = getenv("AC_RENDER_IMPL");          // read per launch so that one process can compare both kernels
+    const bool use_v5 = !(impl && impl[0] == 's' && impl[1] == 't');      // WIP: the stencil kernel is opt-in (AC_RENDER_IMPL=st) until it is the faster one
     const uint32_t n_quads = (a->n_rays + 3) / 4;
-    const uint32_t want = (n_quads + kGroups - 1) / kGroups;
-    const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
-    nsr_render_tc_kernel<<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p);
-    return acb::launched();
+    const uint32_t sms = (uint32_t)acb::sm_count();
+    SlotLease lease(m->mlp_blob, st);
+    if (lease.rc) return lease.rc;
+    if (use_v5) {
+        const uint32_t want = (n_quads + kGroups - 1) / kGroups;
+        const uint32_t grid = want < sms ? want : sms;
+#define AC_CALL(S)                                                                \
+    ACB_SET_MAX_SMEM(nsr_render_tc_kernel<S>, SM_TOTAL);                          \
+    nsr_render_tc_kernel<S><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
+        AC_SLOT_SWITCH(lease.slot, AC_CALL)
+#undef AC_CALL
+    } else {
+        // one 4-ray quad per group; quads are dealt to CTAs first, so a small launch (a 512-ray shard of a training
+        // patch) spreads over all SMs with one busy group each instead of filling 1/4 of the SMs
+        const uint32_t grid = n_quads < sms ? n_quads : sms;
+#define AC_CALL(S)                                                                \
+    ACB_SET_MAX_SMEM(nsr_render_st_kernel<S>, SS_TOTAL);                          \
+    nsr_render_st_kernel<S><<<grid, kWarpsS * 32, SS_TOTAL, st>>>(p)
+        AC_SLOT_SWITCH(lease.slot, AC_CALL)
+#undef AC_CALL
+    }
+    const int rc = acb::launched();
+    lease.launched();
+    return rc;
 }
-}  // namespace acb
 
-namespace acb {
 int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st, uint32_t stencil_M,
                           float eps, float* out_fd) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(forward_sdf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); attr = true; }
-    if (cudaMemcpyToSymbolAsync(c_w, m->mlp_blob + OFF_EPI, EPI_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        return acb::cuda_fail();
     const uint32_t per_cta = kGroups * 128;
     const uint32_t want = (B + per_cta - 1) / per_cta;
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
-    forward_sdf_tc_kernel<<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob,
-                                                                  m->log2_per_level_scale, m->base_resolution, x, out, B, bound, stencil_M, eps, out_fd);
-    return acb::launched();
+    SlotLease lease(m->mlp_blob, st);
+    if (lease.rc) return lease.rc;
+#define AC_CALL(S)                                                                                                              \
+    ACB_SET_MAX_SMEM(forward_sdf_tc_kernel<S>, SM_TOTAL);                                                                       \
+    forward_sdf_tc_kernel<S><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(reinterpret_cast<const float2*>(m->embeddings), m->offsets, \
+        m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, out, B, bound, stencil_M, eps, out_fd)
+    AC_SLOT_SWITCH(lease.slot, AC_CALL)
+#undef AC_CALL
+    const int rc = acb::launched();
+    lease.launched();
+    return rc;
 }
 }  // namespace acb
 
