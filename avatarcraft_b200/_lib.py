@@ -29,17 +29,31 @@ def build_variant(path: str, defines) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a with nvcc (cross-compiles without a GPU)."""
+    """Compile every CUDA source for sm_100a with nvcc (cross-compiles without a GPU): one object per translation unit
+    (in parallel, only the stale ones), then one link."""
     if os.environ.get("AC_LIB_PATH"):
         return LIB_PATH
-    srcs = [os.path.join(_PKG, "csrc", s) for s in SOURCES]
-    deps = srcs + [os.path.join(_PKG, "csrc", h) for h in os.listdir(os.path.join(_PKG, "csrc")) if h.endswith(".cuh")]
-    deps.append(os.path.join(_ROOT, "include", "avatarcraft_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    csrc = os.path.join(_PKG, "csrc")
+    hdrs = [os.path.join(csrc, h) for h in os.listdir(csrc) if h.endswith(".cuh")] + [os.path.join(_ROOT, "include", "avatarcraft_b200.h")]
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    objdir = os.path.join(_PKG, "_build")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-    subprocess.check_call(cmd)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(name):
+        src, obj = os.path.join(csrc, name), os.path.join(objdir, name[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            subprocess.check_call([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+            return obj, True
+        return obj, False
+
+    with ThreadPoolExecutor(max(1, min(len(SOURCES), os.cpu_count() or 1))) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in res]
+    if any(c for _, c in res) or not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(o) for o in objs):
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 

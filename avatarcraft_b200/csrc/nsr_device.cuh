@@ -30,6 +30,13 @@ constexpr int EPI_FLOATS = EPI_C2T + 64 * 4;  // 1552
 constexpr int BLOB_FLOATS = OFF_EPI + EPI_FLOATS;
 static_assert(BLOB_FLOATS == 10848, "blob size is part of the C ABI");
 
+// Experiment hook (scripts/build_variants.py): AC_TEX_MIN_SCALE routes the gathers of hashed levels with scale above the
+// threshold through the texture pipe (tex1Dfetch on a linear float2 texture of the table: the same bits, another path
+// through l1tex).  Measured (profiles/r02_gather_experiments.md): 1-2 % slower than ld.global.nc at every threshold.
+#if defined(AC_TEX_MIN_SCALE)
+__constant__ cudaTextureObject_t c_table_tex;
+#endif
+
 struct LevelMeta {
     uint32_t offset;   // first table entry of the level
     uint32_t size;     // entries in the level ("hashmap_size")
@@ -104,6 +111,12 @@ __device__ __forceinline__ float2 grid_level_3d_k(const float2* __restrict__ tab
     if (HASHED && m.scale > AC_PROBE_SKIP) {      // TIMING PROBE ONLY: fine levels cost nothing
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = make_float2(px, py);
+    } else
+#endif
+#if defined(AC_TEX_MIN_SCALE)
+    if (HASHED && m.scale > AC_TEX_MIN_SCALE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tex1Dfetch<float2>(c_table_tex, (int)(m.offset + s[k]));
     } else
 #endif
     {

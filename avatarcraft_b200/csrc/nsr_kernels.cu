@@ -590,8 +590,9 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
     if (a->n_rays == 0) return AC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t seg = a->eikonal_segment ? a->eikonal_segment : a->n_rays;
-    static const bool use_simt = [] { const char* e = getenv("AC_RENDER_IMPL"); return e && e[0] == 's'; }();
-    if (!use_simt) {   // tensor-core kernel (default); AC_RENDER_IMPL=simt keeps the SIMT kernel for A/B debugging
+    const char* impl_env = getenv("AC_RENDER_IMPL");
+    const bool use_simt = impl_env && impl_env[0] == 's' && impl_env[1] == 'i';
+    if (!use_simt) {   // tensor-core kernels (default); AC_RENDER_IMPL=simt keeps the SIMT kernel for A/B debugging
         int rc = acb::launch_render_tc(m, a, st);
         if (rc || sample_only) return rc;
         eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(reinterpret_cast<float*>(a->workspace), a->n_rays, seg, a->eikonal);

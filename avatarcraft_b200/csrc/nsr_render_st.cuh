@@ -41,12 +41,20 @@ constexpr int kWarpsS = 4 * kGroupsS;
 
 // dynamic shared memory map (bytes)
 constexpr size_t SS_LEVELS = 0;
-constexpr size_t SS_B = (SS_LEVELS + kLevels * sizeof(LevelMeta) + 127) / 128 * 128;
+constexpr size_t SS_EPI = (SS_LEVELS + kLevels * sizeof(LevelMeta) + 127) / 128 * 128;
+// fp32 epilogue weights, read with broadcast LDS by rolled loops (the hot code of 16 warps in 4 different phases has to
+// fit the instruction cache: constant-bank folding needs fully unrolled 64-unit bodies, ~30 KB per tail variant)
+constexpr int E_XB8 = 0;                        // [64][8]: wx, wy, wz, b0, W1[0][j], 0, 0, 0
+constexpr int E_W1T = E_XB8 + 64 * 8;           // [64][16]: W1 transposed
+constexpr int E_C2T = E_W1T + 64 * 16;          // [64][4]: colour head transposed
+constexpr int E_B1 = E_C2T + 64 * 4;            // [16]
+constexpr int E_FLOATS = E_B1 + 16;
+constexpr size_t SS_B = (SS_EPI + E_FLOATS * 4 + 127) / 128 * 128;
 constexpr uint32_t B_W0P_HI = B_BYTES, B_W0P_LO = B_BYTES + 4096, BS_BYTES = B_BYTES + 8192;   // W0 with permuted K columns
 constexpr size_t SS_A = SS_B + BS_BYTES;                                    // per group 32 KB: two tiles of (hi 8 KB | lo 8 KB)
-constexpr size_t SS_F = SS_A + (size_t)kGroupsS * 32768;                    // per group 8 KB: the centre's 15 geometry features as colour-MLP
-                                                                            // A chunks (hi c0 c1 | lo c0 c1), written by the 16-output tail
-constexpr size_t SS_ROWS = SS_F + (size_t)kGroupsS * 8192;                  // per warp: depths, sdf, scratch (3 x 128 floats)
+constexpr size_t SS_F = SS_A + (size_t)kGroupsS * 32768;                    // per group 4 KB: the centre's 15 geometry features as fp16
+                                                                            // colour-MLP A chunks (c0 | c1), written by the 16-output tail
+constexpr size_t SS_ROWS = SS_F + (size_t)kGroupsS * 4096;                  // per warp: depths, sdf, scratch (3 x 128 floats)
 constexpr size_t SS_RAYS = SS_ROWS + (size_t)kWarpsS * 3 * kMaxT * 4;       // per warp: origin, direction, near, span (8 floats)
 constexpr size_t SS_BARS = SS_RAYS + (size_t)kWarpsS * 32;
 constexpr size_t SS_TOTAL = SS_BARS + kGroupsS * 8 + 16;
@@ -74,145 +82,255 @@ __device__ __forceinline__ void floor_pos(float p, float& fl, uint32_t& ci) {
 #endif
 }
 
-struct Cell {            // the centre point's cell on one level
-    float q[3], f[3];    // 1 - frac, frac
-    uint32_t c[3];       // cell coordinates
-    uint32_t t[3];       // slot terms of the low corner: x, y * m1, z * m2  (dense: strides, hashed: primes)
-    uint32_t mul[3];     // 1, m1, m2
-    uint32_t mask;
-};
+// Four 8-byte gathers under one predicate (no divergent branch); lanes with pred == false keep the zeros.
+__device__ __forceinline__ void ldg4_if(bool pred, const float2* p0, const float2* p1, const float2* p2, const float2* p3, float2 (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = make_float2(0.f, 0.f);
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %12, 0;\n\t"
+        "@q ld.global.nc.v2.f32 {%0, %1}, [%8];\n\t"
+        "@q ld.global.nc.v2.f32 {%2, %3}, [%9];\n\t"
+        "@q ld.global.nc.v2.f32 {%4, %5}, [%10];\n\t"
+        "@q ld.global.nc.v2.f32 {%6, %7}, [%11];\n\t}"
+        : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x), "+f"(v[3].y)
+        : "l"(p0), "l"(p1), "l"(p2), "l"(p3), "r"((uint32_t)pred));
+}
 
 template <bool HASHED>
 __device__ __forceinline__ uint32_t slot_of(uint32_t x, uint32_t y, uint32_t z, uint32_t mask) {
     return HASHED ? ((x ^ y ^ z) & mask) : (x + y + z);
 }
 
-// Stencil neighbour along axis A (sign PLUS) on a level where it can leave the centre cell by at most one cell.
-// C = the centre cell's corners (index = xbit + 2 ybit + 4 zbit); un = the neighbour's normalised coordinate on A.
-template <bool HASHED, int A, bool PLUS>
-__device__ __forceinline__ float2 neighbour_shared(const float2* __restrict__ t, const Cell& ce, const float2 (&C)[8], float un, float scale) {
-    const float pa = fmaf(un, scale, 0.5f);
-    float fl; uint32_t ni;
-    floor_pos(pa, fl, ni);
-    const float fa = pa - fl, qa = 1.0f - fa;
-    const bool cross = ni != ce.c[A];
-    // the one face the centre cell does not have: cell coordinate c+2 (PLUS) or c-1 along A
-    const uint32_t ta = PLUS ? ce.t[A] + 2u * ce.mul[A] : ce.t[A] - ce.mul[A];
-    constexpr int B0 = A == 0 ? 1 : 0, B1 = A == 2 ? 1 : 2;         // the two other axes, lower first
-    float2 L[4];
+// One level of the 7-point stencil on a level where a neighbour leaves the centre cell by at most one cell
+// (eps * scale / (2 bound) < 1).  out[0] = centre: the reference's 8-corner blend, bit for bit (hashencoder.cu:121-172).
+// out[1..6] = +x, -x, +y, -y, +z, -z: the same trilinear interpolant evaluated face-wise -- the centre cell's two faces
+// across the neighbour's axis are blended once per axis (G_lo, G_hi) and shared by both signs; a neighbour that steps
+// into the adjacent cell gathers the one new face (4 corners) and blends (G_hi, G_new) resp. (G_new, G_lo).  Same
+// corner values and weights as an independent evaluation, summed in a different order: <= 2 ulp on a feature.
+template <bool HASHED>
+__device__ __forceinline__ void stencil_level_shared(const float2* __restrict__ table, const LevelMeta m, const float (&uc)[3],
+                                                     const float (&un)[6], float2 (&out)[7]) {
+    const float2* __restrict__ t = table + m.offset;
+    float q[3], f[3];
+    uint32_t c[3], tm[3], mul[3];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        uint32_t term[3];
-        term[A] = ta;
-        term[B0] = ce.t[B0] + ((k & 1) ? ce.mul[B0] : 0u);
-        term[B1] = ce.t[B1] + ((k & 2) ? ce.mul[B1] : 0u);
-        L[k] = make_float2(0.f, 0.f);
-        if (cross) L[k] = __ldg(t + slot_of<HASHED>(term[0], term[1], term[2], ce.mask));
+    for (int d = 0; d < 3; ++d) {
+        const float p = fmaf(uc[d], m.scale, 0.5f);
+        float fl;
+        floor_pos(p, fl, c[d]);
+        f[d] = p - fl;
+        q[d] = 1.0f - f[d];
     }
-    // weights of the three faces along A, in ascending cell order: PLUS (old-low, old-high, new), MINUS (new, old-low, old-high)
-    float w3[3];
-    if (PLUS) { w3[0] = cross ? 0.f : qa; w3[1] = cross ? qa : fa; w3[2] = cross ? fa : 0.f; }
-    else      { w3[0] = cross ? qa : 0.f; w3[1] = cross ? fa : qa; w3[2] = cross ? 0.f : fa; }
-    float2 r = make_float2(0.f, 0.f);
+    mul[0] = 1u;
+    mul[1] = HASHED ? 2654435761u : m.res1;
+    mul[2] = HASHED ? 805459861u : m.res1 * m.res1;
+    tm[0] = c[0]; tm[1] = c[1] * mul[1]; tm[2] = c[2] * mul[2];
+    const uint32_t mask = m.size - 1u;
+    float2 C[8];
 #pragma unroll
-    for (int iz = 0; iz < (A == 2 ? 3 : 2); ++iz)
-#pragma unroll
-        for (int iy = 0; iy < (A == 1 ? 3 : 2); ++iy)
-#pragma unroll
-            for (int ix = 0; ix < (A == 0 ? 3 : 2); ++ix) {
-                const int i3[3] = {ix, iy, iz};
-                const float wx = A == 0 ? w3[ix] : (ix ? ce.f[0] : ce.q[0]);
-                const float wy = A == 1 ? w3[iy] : (iy ? ce.f[1] : ce.q[1]);
-                const float wz = A == 2 ? w3[iz] : (iz ? ce.f[2] : ce.q[2]);
-                const float w = (wx * wy) * wz;                        // the reference's product order (hashencoder.cu:141-153)
-                const int pa3 = i3[A];
-                const bool is_new = PLUS ? pa3 == 2 : pa3 == 0;
-                const int abit = PLUS ? pa3 : pa3 - 1;
-                float2 v;
-                if (is_new) v = L[i3[B0] + 2 * i3[B1]];
-                else {
-                    int bits[3] = {ix, iy, iz};
-                    bits[A] = abit;
-                    v = C[bits[0] + 2 * bits[1] + 4 * bits[2]];
-                }
-                ffma2(r, w, v);
-            }
-    return r;
-}
-
-// One level of the stencil: out[0] = centre, out[1..6] = +x, -x, +y, -y, +z, -z.  uc = centre (normalised), un[n] = the
-// moved coordinate of neighbour n (normalised).  SHARED: neighbours can leave the centre cell by at most one cell.
-template <bool HASHED, bool SHARED>
-__device__ __forceinline__ void stencil_level(const float2* __restrict__ table, const LevelMeta m, const float (&uc)[3], const float (&un)[6],
-                                              float2 (&out)[7]) {
-    if constexpr (!SHARED) {
-        out[0] = grid_level_3d_k<HASHED>(table, m, uc[0], uc[1], uc[2]);
-#pragma unroll
-        for (int n = 0; n < 6; ++n) {
-            const int a = n >> 1;
-            out[1 + n] = grid_level_3d_k<HASHED>(table, m, a == 0 ? un[n] : uc[0], a == 1 ? un[n] : uc[1], a == 2 ? un[n] : uc[2]);
-        }
-    } else {
-        Cell ce;
-        const float2* __restrict__ t = table + m.offset;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const float p = fmaf(uc[d], m.scale, 0.5f);
-            float fl;
-            floor_pos(p, fl, ce.c[d]);
-            ce.f[d] = p - fl;
-            ce.q[d] = 1.0f - ce.f[d];
-        }
-        ce.mul[0] = 1u;
-        ce.mul[1] = HASHED ? 2654435761u : m.res1;
-        ce.mul[2] = HASHED ? 805459861u : m.res1 * m.res1;
-        ce.t[0] = ce.c[0]; ce.t[1] = ce.c[1] * ce.mul[1]; ce.t[2] = ce.c[2] * ce.mul[2];
-        ce.mask = m.size - 1u;
-        float2 C[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            C[k] = __ldg(t + slot_of<HASHED>(ce.t[0] + (k & 1), ce.t[1] + ((k & 2) ? ce.mul[1] : 0u), ce.t[2] + ((k & 4) ? ce.mul[2] : 0u), ce.mask));
+    for (int k = 0; k < 8; ++k)
+        C[k] = __ldg(t + slot_of<HASHED>(tm[0] + (k & 1), tm[1] + ((k & 2) ? mul[1] : 0u), tm[2] + ((k & 4) ? mul[2] : 0u), mask));
+    {
         float2 r = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float w = (((k & 1) ? ce.f[0] : ce.q[0]) * ((k & 2) ? ce.f[1] : ce.q[1])) * ((k & 4) ? ce.f[2] : ce.q[2]);
+            const float w = (((k & 1) ? f[0] : q[0]) * ((k & 2) ? f[1] : q[1])) * ((k & 4) ? f[2] : q[2]);
             ffma2(r, w, C[k]);
         }
         out[0] = r;
-        out[1] = neighbour_shared<HASHED, 0, true>(t, ce, C, un[0], m.scale);
-        out[2] = neighbour_shared<HASHED, 0, false>(t, ce, C, un[1], m.scale);
-        out[3] = neighbour_shared<HASHED, 1, true>(t, ce, C, un[2], m.scale);
-        out[4] = neighbour_shared<HASHED, 1, false>(t, ce, C, un[3], m.scale);
-        out[5] = neighbour_shared<HASHED, 2, true>(t, ce, C, un[4], m.scale);
-        out[6] = neighbour_shared<HASHED, 2, false>(t, ce, C, un[5], m.scale);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int b0 = a == 0 ? 1 : 0, b1 = a == 2 ? 1 : 2;         // the two other axes, lower first
+        float pw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pw[k] = ((k & 1) ? f[b0] : q[b0]) * ((k & 2) ? f[b1] : q[b1]);
+        float2 G[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            G[h] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int bits[3];
+                bits[a] = h; bits[b0] = k & 1; bits[b1] = k >> 1;
+                ffma2(G[h], pw[k], C[bits[0] + 2 * bits[1] + 4 * bits[2]]);
+            }
+        }
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {                         // 0: +eps, 1: -eps
+            const float pa = fmaf(un[2 * a + sgn], m.scale, 0.5f);
+            float fl; uint32_t ni;
+            floor_pos(pa, fl, ni);
+            const float fa = pa - fl, qa = 1.0f - fa;
+            const bool cross = ni != c[a];
+            float2 Gn = make_float2(0.f, 0.f);
+            if (__any_sync(0xffffffffu, cross)) {                   // warp-uniform: coarse levels mostly skip it
+                // the one face the centre cell does not have: cell coordinate c+2 (+eps) or c-1 (-eps) along a
+                uint32_t term[3];
+                term[a] = sgn == 0 ? tm[a] + 2u * mul[a] : tm[a] - mul[a];
+                const float2* ptr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    term[b0] = tm[b0] + ((k & 1) ? mul[b0] : 0u);
+                    term[b1] = tm[b1] + ((k & 2) ? mul[b1] : 0u);
+                    ptr[k] = t + slot_of<HASHED>(term[0], term[1], term[2], mask);
+                }
+                float2 L[4];
+                ldg4_if(cross, ptr[0], ptr[1], ptr[2], ptr[3], L);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ffma2(Gn, pw[k], L[k]);
+            }
+            // faces in ascending cell order: +eps (G_lo, G_hi, G_new), -eps (G_new, G_lo, G_hi); the face outside the
+            // neighbour's cell gets weight 0
+            float2 r = make_float2(0.f, 0.f);
+            if (sgn == 0) {
+                ffma2(r, cross ? 0.f : qa, G[0]); ffma2(r, cross ? qa : fa, G[1]); ffma2(r, cross ? fa : 0.f, Gn);
+            } else {
+                ffma2(r, cross ? qa : 0.f, Gn); ffma2(r, cross ? fa : qa, G[0]); ffma2(r, cross ? 0.f : fa, G[1]);
+            }
+            out[1 + 2 * a + sgn] = r;
+        }
     }
 }
 
-// Any level kind (cold path: non-power-of-two hashed levels, huge resolutions): seven independent evaluations.
-__device__ __noinline__ void stencil_level_generic(const float2* __restrict__ table, const LevelMeta* __restrict__ lvp, const float (&uc)[3],
-                                                   const float (&un)[6], float2 (&out)[7]) {
-    const LevelMeta m = *lvp;
-    out[0] = grid_level_3d(table, m, uc[0], uc[1], uc[2]);
+// A-row address of stencil point pt (0 = centre, 1..6 = +x, -x, +y, -y, +z, -z) in the pass of the group's ray j: the
+// centre sits in slot j of tile 0, slot j of tile 1 stays empty, the neighbours fill the other slots in order
+// (slot = 32 rows; tile = 4 slots).  Returns the byte offset of the row inside the group's A region (hi half).
+__device__ __forceinline__ uint32_t stencil_row_offset(int pt, int j, int lane) {
+    int sl;
+    if (pt == 0) sl = j;
+    else {
+        const int n = pt - 1, h = n >= 3 ? 1 : 0, r = n - 3 * h;
+        sl = 4 * h + r + (r >= j ? 1 : 0);
+    }
+    return (uint32_t)((sl >> 2) * 16384 + ((sl & 3) * 32 + lane) * 16);
+}
+
+// SDF-network tails for TWO accumulator rows of this thread (tile 0 and tile 1): + raw-xyz columns + bias (exact fp32, the
+// round-1 arithmetic and summation order), softplus, 64 -> 1.  Rolled over the four 16-unit quarters; weights by
+// broadcast LDS.
+__device__ __forceinline__ void sdf_tail2(const float* __restrict__ epi, uint32_t tmem0, uint32_t tmem1, const float (&p0)[3],
+                                          const float (&p1)[3], float& s0, float& s1) {
+    s0 = epi[E_B1]; s1 = s0;
 #pragma unroll 1
-    for (int n = 0; n < 6; ++n) {
-        const int a = n >> 1;
-        out[1 + n] = grid_level_3d(table, m, a == 0 ? un[n] : uc[0], a == 1 ? un[n] : uc[1], a == 2 ? un[n] : uc[2]);
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float a0[16], a1[16];
+        tc05::tmem_ld16(tmem0 + qtr * 16, a0);
+        tc05::tmem_ld16(tmem1 + qtr * 16, a1);
+        const float4* __restrict__ xb = reinterpret_cast<const float4*>(epi + E_XB8 + qtr * 16 * 8);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const float4 w = xb[2 * jj];
+            const float w1 = epi[E_XB8 + (qtr * 16 + jj) * 8 + 4];
+            const float l0 = fmaf(w.x, p0[0], fmaf(w.y, p0[1], fmaf(w.z, p0[2], w.w)));
+            const float l1 = fmaf(w.x, p1[0], fmaf(w.y, p1[1], fmaf(w.z, p1[2], w.w)));
+            s0 = fmaf(w1, softplus100_mufu(a0[jj] + l0), s0);
+            s1 = fmaf(w1, softplus100_mufu(a1[jj] + l1), s1);
+        }
     }
 }
 
-// Slot (0..7: tile = slot / 4, rows 32 * (slot % 4) ..) of stencil point pt (0 = centre, 1..6 = neighbours) in the pass
-// of the group's ray j: the centre sits in slot j of tile 0, slot j of tile 1 stays empty, the neighbours fill the rest
-// in order.
-__device__ __forceinline__ int stencil_slot(int pt, int j) {
-    if (pt == 0) return j;
-    const int n = pt - 1, h = n >= 3 ? 1 : 0, r = n - 3 * h;
-    return 4 * h + r + (r >= j ? 1 : 0);
+// One-row variant (coarse samples and importance rounds: lane = point, as in the round-1 kernel).  __noinline__: one copy.
+__device__ __noinline__ float sdf_tail1(const float* __restrict__ epi, uint32_t tmem0, float x, float y, float z) {
+    float s0 = epi[E_B1];
+#pragma unroll 1
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float a0[16];
+        tc05::tmem_ld16(tmem0 + qtr * 16, a0);
+        const float4* __restrict__ xb = reinterpret_cast<const float4*>(epi + E_XB8 + qtr * 16 * 8);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const float4 w = xb[2 * jj];
+            const float w1 = epi[E_XB8 + (qtr * 16 + jj) * 8 + 4];
+            s0 = fmaf(w1, softplus100_mufu(a0[jj] + fmaf(w.x, x, fmaf(w.y, y, fmaf(w.z, z, w.w)))), s0);
+        }
+    }
+    return s0;
 }
 
-template <int SLOT>
+// Encode -> A tile (natural K order) -> tcgen05.mma -> scalar tail: the SDF of one point per lane.  All 128 threads of the
+// group call it together.
+__device__ __forceinline__ float sample_sdf(Group& g, const float* __restrict__ epi, const float2* __restrict__ table,
+                                            const LevelMeta* __restrict__ lv, float bound, float x, float y, float z) {
+    encode_to_tile(g.a + g.row * 16, table, lv, bound, x, y, z, g.std_layout);
+    group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_W0_HI, g.b_s + B_W0_LO); });
+    return sdf_tail1(epi, g.tmem, x, y, z);
+}
+
+// 16-output tail (signed distance + 15 geometry features) for this thread's row of tile 0.
+__device__ __forceinline__ void sdf_tail_full(const float* __restrict__ epi, uint32_t tmem0, const float (&p)[3], float (&out)[16]) {
+    float2 o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o2[i] = make_float2(epi[E_B1 + 2 * i], epi[E_B1 + 2 * i + 1]);
+#pragma unroll 1
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float a0[16];
+        tc05::tmem_ld16(tmem0 + qtr * 16, a0);
+        const float4* __restrict__ xb = reinterpret_cast<const float4*>(epi + E_XB8 + qtr * 16 * 8);
+        const float4* __restrict__ w1 = reinterpret_cast<const float4*>(epi + E_W1T + qtr * 16 * 16);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const float4 w = xb[2 * jj];
+            const float h = softplus100_mufu(a0[jj] + fmaf(w.x, p[0], fmaf(w.y, p[1], fmaf(w.z, p[2], w.w))));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 r = w1[4 * jj + i];
+                ffma2(o2[2 * i], h, make_float2(r.x, r.y));
+                ffma2(o2[2 * i + 1], h, make_float2(r.z, r.w));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { out[2 * i] = o2[i].x; out[2 * i + 1] = o2[i].y; }
+}
+
+// Colour MLP after layer 0's MMA: relu -> layer 1 (fp16 activations x (hi, lo) weights) -> relu -> 64 -> 3 head -> sigmoid,
+// head weights by broadcast LDS (rolled).
+__device__ __forceinline__ void color_rest_smem(Group& g, const float* __restrict__ epi, float (&rgb)[3]) {
+#pragma unroll 1
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float acc[16];
+        tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint4 pk;
+            pk.x = tc05::pack_f16x2(fmaxf(acc[8 * half + 0], 0.f), fmaxf(acc[8 * half + 1], 0.f));
+            pk.y = tc05::pack_f16x2(fmaxf(acc[8 * half + 2], 0.f), fmaxf(acc[8 * half + 3], 0.f));
+            pk.z = tc05::pack_f16x2(fmaxf(acc[8 * half + 4], 0.f), fmaxf(acc[8 * half + 5], 0.f));
+            pk.w = tc05::pack_f16x2(fmaxf(acc[8 * half + 6], 0.f), fmaxf(acc[8 * half + 7], 0.f));
+            *reinterpret_cast<uint4*>(g.a + (2 * qtr + half) * 2048 + g.row * 16) = pk;
+        }
+    }
+    group_mma_round(g, [&] {
+        constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
+#pragma unroll
+        for (uint32_t s = 0; s < 4; ++s) {           // K = 64 = 4 x (K=16)
+            const uint64_t ad = tc05::smem_desc(g.a_s + s * 4096u, 2048u, 128u);
+            const uint64_t bh = tc05::smem_desc(g.b_s + B_C1_HI + s * 2048u, 1024u, 128u);
+            const uint64_t bl = tc05::smem_desc(g.b_s + B_C1_LO + s * 2048u, 1024u, 128u);
+            tc05::mma_f16(g.tmem & 0xFFFFu, ad, bh, idesc, s);
+            tc05::mma_f16(g.tmem & 0xFFFFu, ad, bl, idesc, 1u);
+        }
+    });
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+    for (int qtr = 0; qtr < 4; ++qtr) {
+        float acc[16];
+        tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+        const float4* __restrict__ c2 = reinterpret_cast<const float4*>(epi + E_C2T + qtr * 16 * 4);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const float h2 = fmaxf(acc[jj], 0.f);
+            const float4 w = c2[jj];
+            o0 = fmaf(w.x, h2, o0); o1 = fmaf(w.y, h2, o1); o2 = fmaf(w.z, h2, o2);
+        }
+    }
+    rgb[0] = sigmoidf(o0); rgb[1] = sigmoidf(o1); rgb[2] = sigmoidf(o2);
+}
+
 __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const RenderParamsTC p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SS_LEVELS);
+    float* epi = reinterpret_cast<float*>(smem + SS_EPI);
     unsigned char* bt = smem + SS_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SS_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroupsS);
@@ -224,6 +342,16 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
     {
         const float* blob = p.blob;
         if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(p.offsets, threadIdx.x, p.S, p.H, 3);
+        {   // fp32 epilogue weights (the blob's OFF_EPI block: XB[64][4] | W1T[64][16] | B1[16] | C2T[64][4])
+            const float* e = blob + OFF_EPI;
+            for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+                const int j = i >> 3, c = i & 7;
+                epi[E_XB8 + i] = c < 4 ? __ldg(e + EPI_XB + 4 * j + c) : (c == 4 ? __ldg(e + EPI_W1T + 16 * j) : 0.f);
+            }
+            for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) epi[E_W1T + i] = __ldg(e + EPI_W1T + i);
+            for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) epi[E_C2T + i] = __ldg(e + EPI_C2T + i);
+            if (threadIdx.x < 16) epi[E_B1 + threadIdx.x] = __ldg(e + EPI_B1 + threadIdx.x);
+        }
         for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
             const int n = i >> 5, k = i & 31;
             stage_b_tile(bt + B_W0_HI, bt + B_W0_LO, n, k, __ldg(blob + OFF_W0 + n * kSdfInPad + 3 + k));
@@ -239,7 +367,7 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
             stage_b_tile(bt + B_C1_HI, bt + B_C1_LO, n, k, __ldg(blob + OFF_C1 + n * kHidden + k));
         }
         // tile 1's empty slot is multiplied by the tensor core as well: keep it finite
-        for (int i = threadIdx.x; i < kGroupsS * 32768 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + SS_A)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < (int)((SS_ROWS - SS_A) / 16); i += blockDim.x) reinterpret_cast<uint4*>(smem + SS_A)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) {
             for (int gI = 0; gI < kGroupsS; ++gI) tc05::mbar_init(bars + gI, 1);
             tc05::fence_mbar_init();
@@ -261,13 +389,9 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
     g.row = wq * 32 + lane;
     g.tmem = tmem_base + (uint32_t)group * 128u + ((uint32_t)(wq * 32) << 16);
     g.bar_id = 1 + group;
-    bool std_levels = true;         // every level dense or power-of-two hashed, resolution inside the magic-floor range
     {
         bool ok = true;
-        for (int l = 0; l < kLevels; ++l) {
-            ok = ok && (lv[l].hashed == (l < 5 ? 0u : 1u));
-            std_levels = std_levels && lv[l].hashed < 2u && lv[l].scale < 2.0e6f;
-        }
+        for (int l = 0; l < kLevels; ++l) ok = ok && (lv[l].hashed == (l < 5 ? 0u : 1u));
         g.std_layout = ok;
     }
 
@@ -319,10 +443,7 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
             if (rounds > 0) {
                 float x, y, zz;
                 ray_point(r, z, x, y, zz);
-                float o[1];
-                group_sdf_eval<SLOT, false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
-                                            clampf(zz, -bound, bound), o);
-                sdfs[k] = o[0];
+                sdfs[k] = sample_sdf(g, epi, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound), clampf(zz, -bound, bound));
             }
             zs[k] = z;          // duplicate lanes write identical values
         }
@@ -338,10 +459,7 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
                 const float zq = __shfl_sync(0xffffffffu, z_new, lane & 15);     // lanes 16..31 mirror 0..15
                 float x, y, zz;
                 ray_point(r, zq, x, y, zz);
-                float o[1];
-                group_sdf_eval<SLOT, false>(g, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound),
-                                            clampf(zz, -bound, bound), o);
-                s_new = o[0];
+                s_new = sample_sdf(g, epi, table, lv, bound, clampf(x, -bound, bound), clampf(y, -bound, bound), clampf(zz, -bound, bound));
             }
             int pos_old[4], pos_new;
             merge_positions(zs, T, z_new, lane, pos_old, pos_new);
@@ -377,7 +495,7 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
         float carry = 1.0f;
         float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_nx = 0.f, acc_ny = 0.f, acc_nz = 0.f;
         float acc_w = 0.f, acc_d = 0.f, eik_num = 0.f, eik_den = 0.f;
-        unsigned char* fsm = smem + SS_F + (size_t)group * 8192;           // colour A chunks 0, 1 of the group's 128 samples
+        unsigned char* fsm = smem + SS_F + (size_t)group * 4096;           // colour A chunks 0, 1 (fp16) of the group's 128 samples
         for (int k0 = 0; k0 < Ttot; k0 += 32) {
             float sdf0 = 0.f;                           // centre SDF of this warp's own sample (written in pass j == wq)
 
@@ -411,38 +529,44 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
                         un[2 * d] = (clampf(pc[d] + eps, -bound, bound) + bound) / two_b;
                         un[2 * d + 1] = (clampf(pc[d] - eps, -bound, bound) + bound) / two_b;
                     }
-                    // this warp's K chunk of the 7 rows: levels wq, wq+4 (first 8 bytes of the chunk), then wq+8, wq+12
+                    // this warp's K chunk of the 7 rows: levels wq, wq+4, wq+8, wq+12 -> 4 bytes (hi) + 4 bytes (lo) each
+                    unsigned char* achunk = g.a + wq * 2048;
 #pragma unroll 1
-                    for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t hi[7][2], lo[7][2];
-#pragma unroll 1
-                        for (int i2 = 0; i2 < 2; ++i2) {
-                            const int l = wq + 4 * (2 * hf + i2);
-                            const LevelMeta m = lv[l];
+                    for (int i = 0; i < 4; ++i) {
+                        const int l = wq + 4 * i;
+                        const LevelMeta m = lv[l];
+                        // shared: a neighbour leaves the centre cell by <= 1 cell, slots are plain sums / power-of-two hashes
+                        const bool shared = shift_per_scale * m.scale + 1e-3f < 1.0f && m.hashed < 2u && m.scale < 2.0e6f;
+                        if (shared) {
                             float2 f7[7];
-                            const bool shared = shift_per_scale * m.scale + 1e-3f < 1.0f;   // a neighbour leaves the centre cell by <= 1 cell
-                            if (!std_levels) stencil_level_generic(table, lv + l, uc, un, f7);
-                            else if (m.hashed == 0u) {
-                                if (shared) stencil_level<false, true>(table, m, uc, un, f7);
-                                else stencil_level<false, false>(table, m, uc, un, f7);
-                            } else {
-                                if (shared) stencil_level<true, true>(table, m, uc, un, f7);
-                                else stencil_level<true, false>(table, m, uc, un, f7);
-                            }
+                            if (m.hashed == 0u) stencil_level_shared<false>(table, m, uc, un, f7);
+                            else stencil_level_shared<true>(table, m, uc, un, f7);
 #pragma unroll
                             for (int pt = 0; pt < 7; ++pt) {
                                 uint32_t h, lw;
                                 tc05::split_f16x2(f7[pt].x, f7[pt].y, h, lw);
-                                if (i2 == 0) { hi[pt][0] = h; lo[pt][0] = lw; }      // rolled loop: select, do not index registers
-                                else { hi[pt][1] = h; lo[pt][1] = lw; }
+                                unsigned char* arow = achunk + stencil_row_offset(pt, j, lane) + 4 * i;
+                                *reinterpret_cast<uint32_t*>(arow) = h;
+                                *reinterpret_cast<uint32_t*>(arow + 8192) = lw;
                             }
-                        }
-#pragma unroll
-                        for (int pt = 0; pt < 7; ++pt) {
-                            const int sl = stencil_slot(pt, j);
-                            unsigned char* arow = g.a + (sl >> 2) * 16384 + wq * 2048 + ((sl & 3) * 32 + lane) * 16 + hf * 8;
-                            *reinterpret_cast<uint2*>(arow) = make_uint2(hi[pt][0], hi[pt][1]);
-                            *reinterpret_cast<uint2*>(arow + 8192) = make_uint2(lo[pt][0], lo[pt][1]);
+                        } else {
+                            // the stencil spans several cells (levels 12..15 for eps = 0.005, bound = 1.6): seven independent
+                            // evaluations; rolled -- one copy of the level body in the instruction cache
+#pragma unroll 1
+                            for (int pt = 0; pt < 7; ++pt) {
+                                float x = uc[0], y = uc[1], z = uc[2];
+                                if (pt > 0) {
+                                    const int n = pt - 1;
+                                    const float mv = n == 0 ? un[0] : n == 1 ? un[1] : n == 2 ? un[2] : n == 3 ? un[3] : n == 4 ? un[4] : un[5];
+                                    if (n < 2) x = mv; else if (n < 4) y = mv; else z = mv;
+                                }
+                                const float2 fv = grid_level_3d(table, m, x, y, z);
+                                uint32_t h, lw;
+                                tc05::split_f16x2(fv.x, fv.y, h, lw);
+                                unsigned char* arow = achunk + stencil_row_offset(pt, j, lane) + 4 * i;
+                                *reinterpret_cast<uint32_t*>(arow) = h;
+                                *reinterpret_cast<uint32_t*>(arow + 8192) = lw;
+                            }
                         }
                     }
                 }
@@ -453,31 +577,37 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
                 // tails: slot wq of tile 0 and of tile 1
                 if (wq == j) {
                     float o16[16];
-                    sdf_tail<SLOT, true>(g.tmem, pc[0], pc[1], pc[2], o16);
+                    sdf_tail_full(epi, g.tmem, pc, o16);
                     sdf0 = o16[0];
-                    // geometry features -> colour layer 0's A chunks 0 and 1 (K 0..14, K 15 = 0), own row
-                    uint4 h4, l4;
-                    tc05::split_f16x2(o16[1], o16[2], h4.x, l4.x); tc05::split_f16x2(o16[3], o16[4], h4.y, l4.y);
-                    tc05::split_f16x2(o16[5], o16[6], h4.z, l4.z); tc05::split_f16x2(o16[7], o16[8], h4.w, l4.w);
+                    // geometry features -> colour layer 0's A chunks 0 and 1 (K 0..14, K 15 = 0) as fp16, own row
+                    uint4 h4;
+                    h4.x = tc05::pack_f16x2(o16[1], o16[2]); h4.y = tc05::pack_f16x2(o16[3], o16[4]);
+                    h4.z = tc05::pack_f16x2(o16[5], o16[6]); h4.w = tc05::pack_f16x2(o16[7], o16[8]);
                     *reinterpret_cast<uint4*>(fsm + g.row * 16) = h4;
-                    *reinterpret_cast<uint4*>(fsm + 4096 + g.row * 16) = l4;
-                    tc05::split_f16x2(o16[9], o16[10], h4.x, l4.x); tc05::split_f16x2(o16[11], o16[12], h4.y, l4.y);
-                    tc05::split_f16x2(o16[13], o16[14], h4.z, l4.z); tc05::split_f16x2(o16[15], 0.f, h4.w, l4.w);
+                    h4.x = tc05::pack_f16x2(o16[9], o16[10]); h4.y = tc05::pack_f16x2(o16[11], o16[12]);
+                    h4.z = tc05::pack_f16x2(o16[13], o16[14]); h4.w = tc05::pack_f16x2(o16[15], 0.f);
                     *reinterpret_cast<uint4*>(fsm + 2048 + g.row * 16) = h4;
-                    *reinterpret_cast<uint4*>(fsm + 4096 + 2048 + g.row * 16) = l4;
                 } else {
                     const int r0 = wq - (wq > j ? 1 : 0);            // neighbour index of tile 0's slot wq; tile 1's is r0 + 3
-#pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {
-                        const int n = r0 + 3 * h;
-                        const int a = n >> 1;
+                    float q0[3] = {pc[0], pc[1], pc[2]}, q1[3] = {pc[0], pc[1], pc[2]};
+                    {
+                        const int n = r0, a = n >> 1;
                         const float e = (n & 1) ? -eps : eps;
-                        float q3[3] = {pc[0], pc[1], pc[2]};
-                        if (a == 0) q3[0] = clampf(pc[0] + e, -bound, bound);
-                        else if (a == 1) q3[1] = clampf(pc[1] + e, -bound, bound);
-                        else q3[2] = clampf(pc[2] + e, -bound, bound);
-                        fdj[n * 32 + lane] = sdf_tail_scalar<SLOT>(g.tmem + 64u * h, q3[0], q3[1], q3[2]);
+                        if (a == 0) q0[0] = clampf(pc[0] + e, -bound, bound);
+                        else if (a == 1) q0[1] = clampf(pc[1] + e, -bound, bound);
+                        else q0[2] = clampf(pc[2] + e, -bound, bound);
                     }
+                    {
+                        const int n = r0 + 3, a = n >> 1;
+                        const float e = (n & 1) ? -eps : eps;
+                        if (a == 0) q1[0] = clampf(pc[0] + e, -bound, bound);
+                        else if (a == 1) q1[1] = clampf(pc[1] + e, -bound, bound);
+                        else q1[2] = clampf(pc[2] + e, -bound, bound);
+                    }
+                    float s0, s1;
+                    sdf_tail2(epi, g.tmem, g.tmem + 64u, q0, q1, s0, s1);
+                    fdj[r0 * 32 + lane] = s0;
+                    fdj[(r0 + 3) * 32 + lane] = s1;
                 }
             }
             tc05::fence_before_sync();
@@ -527,10 +657,10 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
                 constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
                 const uint32_t d = g.tmem & 0xFFFFu;
                 const uint32_t bh_s = g.b_s + B_C0_HI, bl_s = g.b_s + B_C0_LO;
-                {   // K 0..15: feature chunks
-                    const uint64_t ah = tc05::smem_desc(f_s, 2048u, 128u), al = tc05::smem_desc(f_s + 4096u, 2048u, 128u);
+                {   // K 0..15: geometry features, fp16 (2^-11 relative, like the activations of colour layer 1) x (hi, lo) weights
+                    const uint64_t ah = tc05::smem_desc(f_s, 2048u, 128u);
                     const uint64_t bh = tc05::smem_desc(bh_s, 1024u, 128u), bl = tc05::smem_desc(bl_s, 1024u, 128u);
-                    tc05::mma_f16(d, ah, bh, idesc, 0u); tc05::mma_f16(d, al, bh, idesc, 1u); tc05::mma_f16(d, ah, bl, idesc, 1u);
+                    tc05::mma_f16(d, ah, bh, idesc, 0u); tc05::mma_f16(d, ah, bl, idesc, 1u);
                 }
                 {   // K 16..31: position / normal chunk + zero chunk
                     const uint64_t ah = tc05::smem_desc(g.a_s + 4096u, 2048u, 128u), al = tc05::smem_desc(g.a_s + 8192u + 4096u, 2048u, 128u);
@@ -539,7 +669,7 @@ __global__ void __launch_bounds__(kWarpsS * 32, 1) nsr_render_st_kernel(const Re
                 }
             });
             float col[3];
-            group_color_rest<SLOT>(g, col);
+            color_rest_smem(g, epi, col);
             const float cosv = rr.dx * nx + rr.dy * ny + rr.dz * nz;
             const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);
             const float hs = it * delta * 0.5f;

@@ -392,7 +392,11 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
     const uint32_t n_quads = (p.a.n_rays + 3) / 4;
     const bool staged = p.a.z_in != nullptr;       // sampling done by the host pipeline (warp path)
 
-    for (uint32_t quad = blockIdx.x * kGroups + group; quad < n_quads; quad += gridDim.x * kGroups) {
+    // A full launch gives a CTA kGroups adjacent quads per iteration; a small one deals quads to CTAs first, so that a
+    // 512-ray shard of a training patch runs on 128 SMs with one busy group each instead of on 19 full CTAs.
+    const bool dense_map = n_quads >= gridDim.x * kGroups;
+    for (uint32_t quad = dense_map ? blockIdx.x * kGroups + group : blockIdx.x + gridDim.x * group; quad < n_quads;
+         quad += gridDim.x * kGroups) {
         const uint32_t ray_raw = quad * 4 + (warp & 3);
         const bool ray_ok = ray_raw < p.a.n_rays;
         const uint32_t ray = ray_ok ? ray_raw : p.a.n_rays - 1;       // padding warps recompute the last ray
@@ -794,26 +798,36 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
     const bool use_v5 = !(impl && impl[0] == 's' && impl[1] == 't');      // WIP: the stencil kernel is opt-in (AC_RENDER_IMPL=st) until it is the faster one
     const uint32_t n_quads = (a->n_rays + 3) / 4;
     const uint32_t sms = (uint32_t)acb::sm_count();
+    if (!use_v5) {
+        // The stencil kernel keeps its epilogue weights in shared memory: no constant-bank slot, nothing shared between
+        // launches.  One 4-ray quad per group; quads are dealt to CTAs first, so a small launch (a 512-ray shard of a
+        // training patch) spreads over all SMs with one busy group each instead of filling 1/4 of the SMs.
+        const uint32_t grid = n_quads < sms ? n_quads : sms;
+        ACB_SET_MAX_SMEM(nsr_render_st_kernel, SS_TOTAL);
+        nsr_render_st_kernel<<<grid, kWarpsS * 32, SS_TOTAL, st>>>(p);
+        return acb::launched();
+    }
+#if defined(AC_TEX_MIN_SCALE)
+    {   // experiment: linear float2 texture over the table (standard 16-level layout: 6 119 857 entries)
+        static cudaTextureObject_t tex = 0; static const void* tex_ptr = nullptr;
+        if (tex_ptr != m->embeddings) {
+            cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = const_cast<float*>(m->embeddings);
+            rd.res.linear.desc = cudaCreateChannelDesc<float2>(); rd.res.linear.sizeInBytes = (size_t)6119857 * 8;
+            cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) return acb::cuda_fail();
+            tex_ptr = m->embeddings;
+        }
+        if (cudaMemcpyToSymbolAsync(c_table_tex, &tex, sizeof(tex), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return acb::cuda_fail();
+    }
+#endif
     SlotLease lease(m->mlp_blob, st);
     if (lease.rc) return lease.rc;
-    if (use_v5) {
-        const uint32_t want = (n_quads + kGroups - 1) / kGroups;
-        const uint32_t grid = want < sms ? want : sms;
+    const uint32_t grid = n_quads < sms ? n_quads : sms;
 #define AC_CALL(S)                                                                \
     ACB_SET_MAX_SMEM(nsr_render_tc_kernel<S>, SM_TOTAL);                          \
     nsr_render_tc_kernel<S><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
-        AC_SLOT_SWITCH(lease.slot, AC_CALL)
+    AC_SLOT_SWITCH(lease.slot, AC_CALL)
 #undef AC_CALL
-    } else {
-        // one 4-ray quad per group; quads are dealt to CTAs first, so a small launch (a 512-ray shard of a training
-        // patch) spreads over all SMs with one busy group each instead of filling 1/4 of the SMs
-        const uint32_t grid = n_quads < sms ? n_quads : sms;
-#define AC_CALL(S)                                                                \
-    ACB_SET_MAX_SMEM(nsr_render_st_kernel<S>, SS_TOTAL);                          \
-    nsr_render_st_kernel<S><<<grid, kWarpsS * 32, SS_TOTAL, st>>>(p)
-        AC_SLOT_SWITCH(lease.slot, AC_CALL)
-#undef AC_CALL
-    }
     const int rc = acb::launched();
     lease.launched();
     return rc;
