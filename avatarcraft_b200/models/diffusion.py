@@ -99,7 +99,11 @@ class StableDiffusion(nn.Module):
             self.unet = unet if unet is not None else UNet2DConditionModel(cfg)
             self.text_encoder = text_encoder if text_encoder is not None else HashTextEncoder(cfg.cross_attention_dim)
         self.tokenizer = tokenizer
-        self.cfg_parallel = True                             # multi-GPU: split the classifier-free-guidance pair over ranks
+        # multi-GPU: split the classifier-free-guidance pair over ranks.  Only valid when every rank holds bit-identical
+        # (latents, t, noise): the trainer guarantees that through pixel_gradient(seed=...) on the all-gathered pass-1 image
+        # and switches it on; anywhere else the ranks draw their own randoms, so it is off by default.
+        self.cfg_parallel = False
+        self._user_text_encoder = text_encoder is not None
         if weights_dir is not None:
             self._load_diffusers_dir(weights_dir)
         self.to(self.device)
@@ -109,12 +113,30 @@ class StableDiffusion(nn.Module):
         self.alphas = self.scheduler.alphas_cumprod.to(self.device)
 
     def _load_diffusers_dir(self, root):
-        """diffusers layout: <root>/unet/diffusion_pytorch_model.bin, <root>/vae/diffusion_pytorch_model.bin."""
-        for sub, mod in (("unet", self.unet), ("vae", self.vae)):
+        """diffusers layout: <root>/{unet,vae}/diffusion_pytorch_model.{safetensors,bin} and the text side
+        <root>/text_encoder + <root>/tokenizer (models/diffusion.py:53-60 loads all four from one model id).  The prompt
+        conditions the UNet through the text encoder: real UNet weights with the random stand-in encoder would make
+        SDS silently ignore the prompt, so a missing text side is an error unless the caller passed its own modules."""
+        def load_state(sub):
+            st = os.path.join(root, sub, "diffusion_pytorch_model.safetensors")
+            if os.path.exists(st):
+                from safetensors.torch import load_file
+                return load_file(st, device="cpu")
             f = os.path.join(root, sub, "diffusion_pytorch_model.bin")
             if not os.path.exists(f):
-                raise FileNotFoundError(f)
-            mod.load_state_dict(torch.load(f, map_location="cpu"))
+                raise FileNotFoundError(f"{st} (or .bin)")
+            return torch.load(f, map_location="cpu")
+        self.unet.load_state_dict(load_state("unet"))
+        self.vae.load_state_dict(load_state("vae"))
+        if self._user_text_encoder and self.tokenizer is not None:
+            return
+        te, tk = os.path.join(root, "text_encoder"), os.path.join(root, "tokenizer")
+        if not (os.path.isdir(te) and os.path.isdir(tk)):
+            raise FileNotFoundError(f"{te} and {tk}: the checkpoint's CLIP text encoder and tokenizer are required with real "
+                                    "UNet weights (or pass text_encoder= and tokenizer=)")
+        from transformers import CLIPTextModel, CLIPTokenizer
+        self.tokenizer = CLIPTokenizer.from_pretrained(tk)
+        self.text_encoder = CLIPTextModel.from_pretrained(te)
 
     # ---- text ----------------------------------------------------------------------------------------------------
     def get_text_embeds(self, prompt):
@@ -190,6 +212,9 @@ class StableDiffusion(nn.Module):
         rank of a multi-GPU job, so replicated VAE work agrees bit for bit and no broadcast is needed."""
         if seed is not None:
             torch.manual_seed(int(seed))
+        elif self.cfg_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            raise RuntimeError("cfg_parallel needs identical (t, noise) on every rank: pass seed= (or set cfg_parallel = False)")
         img = rgb_rows.detach().reshape(1, h, w, 3).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
         with torch.enable_grad():
             self.mannual_backward(text_embeddings, img, guidance_scale)

@@ -364,6 +364,7 @@ class NeRFRenderer(nn.Module):
         relax = (torch.linalg.norm(P, ord=2, dim=-1).reshape(n, T) < 1.2).float()
         gerr = (gnorm.reshape(n, T) - 1.0) ** 2
         eik = (relax * gerr).sum() / (relax.sum() + 1e-5)
+        self.last_eikonal_count = relax.sum().detach()          # samples inside the eikonal mask (split-patch weighting)
         bg = 1 if bg_color is None else torch.as_tensor(bg_color, dtype=torch.float32, device=dev)
         image = image + (1 - wsum) * bg
         return depth.reshape(B, N), weights, wsum, image.reshape(B, N, 3), nmap, eik, 0.0, color, alpha, z

@@ -66,10 +66,24 @@ def render_rays_sharded(render_fn, rays_o, rays_d, rank: int, world: int, group=
     n = rays_o.shape[0]
     if world <= 1 or not (dist.is_available() and dist.is_initialized()):
         return render_fn(rays_o, rays_d)
-    if n % world:
-        raise ValueError("render_rays_sharded needs n_rays divisible by the world size")
-    s, e = shard_rays(n, rank, world)
-    mine = render_fn(rays_o[s:e], rays_d[s:e]).contiguous()
-    full = torch.empty(n, mine.shape[1], device=mine.device, dtype=mine.dtype)
+    pad = (-n) % world                  # a ray count that does not divide: repeat the last ray, drop the copies after the gather
+    if pad:
+        rays_o = torch.cat([rays_o, rays_o[-1:].expand(pad, -1)])
+        rays_d = torch.cat([rays_d, rays_d[-1:].expand(pad, -1)])
+    s, e = shard_rays(n + pad, rank, world)
+    mine = render_fn(rays_o[s:e].contiguous(), rays_d[s:e].contiguous()).contiguous()
+    full = torch.empty(n + pad, mine.shape[1], device=mine.device, dtype=mine.dtype)
     dist.all_gather_into_tensor(full, mine, group=group)
-    return full
+    return full[:n]
+
+
+def masked_mean_share(local_count: torch.Tensor, group=None) -> torch.Tensor:
+    """Weight that turns this rank's masked mean (sum_local / (count_local + 1e-5), the eikonal term of
+    models/instant_nsr.py:266-272) into its share of the whole patch's masked mean when ONE patch is split over ranks:
+    (count_local + 1e-5) / (count_global + 1e-5), with count_global from one scalar all-reduce.  The sum over ranks of
+    share * local_mean is sum_global / (count_global + 1e-5) -- what a single process computes.  (Scaling by
+    local_rays / patch_rays is only right for plain means: the mask count differs per rank.)"""
+    total = local_count.detach().clone().float()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return (local_count.detach().float() + 1e-5) / (total + 1e-5)

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from .constant import NSR_BOUND, WHITE_BKG
-from .distributed import allreduce_gradients, shard_patches
+from .distributed import allreduce_gradients, masked_mean_share, shard_patches
 from .optim import FlatAdam
 from .render_utils import render_instantnsr_naive
 
@@ -31,8 +31,11 @@ def stylize_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad,
                                                   bound=NSR_BOUND)
         loss = (rgb * pixel_grad[s:e]).sum()                       # == rgb.backward(gradient=pixel_grad)
         if w_eikonal > 0.0:
-            loss = loss + eik * (w_eikonal * scale)
-            stats["eikonal"].append(eik.detach())
+            # a split patch: the eikonal term is a MASKED mean (|p| < 1.2), so each rank's share is its mask count over the
+            # patch's, not its ray count (one scalar all-reduce); whole patches keep weight 1
+            share = masked_mean_share(net_style.last_eikonal_count) if scale != 1.0 else 1.0
+            loss = loss + eik * (w_eikonal * share)
+            stats["eikonal"].append(eik.detach() * share)
         if use_opacity and net_gt is not None:
             with torch.no_grad():
                 _, _, extra_gt = render_instantnsr_naive(net_gt, o, d, requires_grad=False, bkg_key=bkg_key, return_torch=True,

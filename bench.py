@@ -323,6 +323,7 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
     if sd_guidance:       # the real guidance: SD-1.5-shaped UNet (native tcgen05 forward) + VAE encoder with gradient, random weights
         from avatarcraft_b200.models.diffusion import StableDiffusion
         sd = StableDiffusion(dev, "1.5")
+        sd.cfg_parallel = world > 1          # every rank seeds the step identically (pixel_gradient(seed=...)): the CFG pair may be split
         emb = sd.get_text_embeds("a 3D rendering of a knight in bronze armour")
     count = [0]
 

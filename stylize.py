@@ -59,6 +59,9 @@ def main():
     ap.add_argument("--guidance_scale", type=float, default=100.0)
     ap.add_argument("--i_save", type=int, default=1000)
     ap.add_argument("--lr", type=float, default=5e-3)
+    ap.add_argument("--lr_decay", action="store_true",
+                    help="halve the LR after half of the epochs.  Off by default: the reference builds a StepLR but never steps it "
+                         "(`# scheduler.step()`, stylize.py:214), so its LR stays at 5e-3 for the whole run")
     ap.add_argument("--resume", type=str, default=None, help="a *.pth.tar written by this script (its .resume.pt is picked up)")
     opt = ap.parse_args()
 
@@ -72,33 +75,41 @@ def main():
     net_style, net_gt = net_style.cuda().train(), net_gt.cuda().eval()        # net_style is never .eval()ed (stylize.py:336)
     for p in net_gt.parameters():
         p.requires_grad_(False)
-    # Adam(lr 5e-3) + StepLR(epochs//2, 0.5) (stylize.py:355-363) on flat buffers: one all-reduce + one update launch
+    # Adam(lr 5e-3) (stylize.py:355-363; its StepLR is never stepped, :214) on flat buffers: one all-reduce + one update launch
     optimizer = FlatAdam(net_style.parameters(), lr=opt.lr)
     sd_guide = text_emb = None
     if opt.guidance == "sds":                                                  # stylize.py:340-352 setup_loss + :100 text embeds
         from avatarcraft_b200.models.diffusion import StableDiffusion
         sd_guide = StableDiffusion("cuda", opt.sd_version, weights_dir=opt.sd_weights)
+        sd_guide.cfg_parallel = world > 1       # every rank draws (t, noise) from the per-step seed below, so the pair may be split
         text_emb = sd_guide.get_text_embeds(opt.prompt)
     out_dir = os.path.join("style", "canonical_360", opt.exp_name)
     os.makedirs(out_dir, exist_ok=True)
-    H, W, step, first_epoch = opt.render_h, opt.render_w, 0, 0
+    H, W, step, first_epoch, first_view = opt.render_h, opt.render_w, 0, 0, 0
     n_epochs = opt.coarse_epochs + opt.fine_epochs
     if opt.resume:                                                             # weights + optimizer moments + counters + RNG
         info = load_checkpoint(opt.resume, net_style, optimizer)
         step, first_epoch = info["step"], info["epoch"]
-        print(f"resumed from {opt.resume}: step {step}, epoch {first_epoch}, optimizer state {'restored' if info['resumed'] else 'fresh'}")
+        first_view = int(info["extra"].get("view_pos", 0))                     # position inside the epoch's view permutation
+        print(f"resumed from {opt.resume}: step {step}, epoch {first_epoch}, view {first_view}, "
+              f"optimizer state {'restored' if info['resumed'] else 'fresh'}")
+        if first_epoch >= n_epochs:
+            print("the checkpoint is from a finished run: nothing left to train")
     for epoch in range(first_epoch, n_epochs):
-        optimizer.param_groups[0]["lr"] = opt.lr * (0.5 ** (epoch // max(n_epochs // 2, 1)))
+        lr = opt.lr * (0.5 ** (epoch // max(n_epochs // 2, 1))) if opt.lr_decay else opt.lr
+        optimizer.param_groups[0]["lr"] = lr
         stride = opt.subsample_scale if epoch < opt.coarse_epochs else min(1, opt.subsample_scale // 2) or 1
         poses = default_360_path((0.0, 0.0, 0.0), CANONICAL_CAMERA_DIST_TRAIN, opt.n_views)
-        perm = torch.randperm(opt.n_views, generator=torch.Generator().manual_seed(epoch))      # same order on every rank
-        for vi in perm.tolist():
+        perm = torch.randperm(opt.n_views, generator=torch.Generator().manual_seed(epoch)).tolist()      # same order on every rank
+        start = first_view if epoch == first_epoch else 0                      # a resumed epoch continues where it stopped
+        for vpos in range(start, len(perm)):
+            vi = perm[vpos]
             o, d = rays_for_pose(poses[vi], W, H, "cuda")
             o, d = o.reshape(H, W, 3)[::stride, ::stride].reshape(-1, 3).contiguous(), d.reshape(H, W, 3)[::stride, ::stride].reshape(-1, 3).contiguous()
             h, w = H // stride, W // stride
             with torch.no_grad():                                                                # pass 1 (stylize.py:115), ray-sharded
                 fn = lambda a, b: render_utils.render_instantnsr_naive(net_style, a, b, opt.batch_size, render_can=True, perturb=True)[0]
-                rgb = render_rays_sharded(fn, o, d, rank, world) if o.shape[0] % world == 0 else fn(o, d)
+                rgb = render_rays_sharded(fn, o, d, rank, world)                                 # pads a ray count that does not divide
             if sd_guide is not None:                                                             # SDS (models/diffusion.py:92-149)
                 pixel_grad = sd_guide.pixel_gradient(text_emb, rgb, h, w, opt.guidance_scale, seed=1_000_003 * (epoch + 1) + step)
             else:
@@ -109,10 +120,14 @@ def main():
             step += 1
             if rank == 0 and step % 10 == 0:
                 print(f"epoch {epoch} step {step} eikonal {float(stats['eikonal'] or 0):.4f}")
-            if rank == 0 and step % opt.i_save == 0:
-                save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}_{step:06d}.pth.tar"), net_style, optimizer, step, epoch)
+            if rank == 0 and step % opt.i_save == 0:                           # reference name: <exp>_<step+1 (0-based), 4 digits> (stylize.py:206,256)
+                nxt = (epoch, vpos + 1) if vpos + 1 < len(perm) else (epoch + 1, 0)
+                save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}_{step:04d}.pth.tar"), net_style, optimizer, step, nxt[0],
+                                extra={"view_pos": nxt[1]})
     if rank == 0:
-        save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}.pth.tar"), net_style, optimizer, step, n_epochs)
+        # the reference's final log_model(global_step) (stylize.py:216) + a fixed name for the render scripts
+        save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}_{step + 1:04d}.pth.tar"), net_style, optimizer, step, n_epochs, extra={"view_pos": 0})
+        save_checkpoint(os.path.join(out_dir, f"{opt.exp_name}.pth.tar"), net_style, optimizer, step, n_epochs, extra={"view_pos": 0})
         print("saved", os.path.join(out_dir, f"{opt.exp_name}.pth.tar"))
     if world > 1:
         dist.destroy_process_group()

@@ -80,8 +80,16 @@ def _cfg_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
     sd = diffusion.StableDiffusion("cpu", "1.5", unet=_StubUNet(), vae=sd_vae.AutoencoderKL.tiny(), text_encoder=diffusion.HashTextEncoder(32))
+    assert sd.cfg_parallel is False                 # off unless the caller guarantees identical (t, noise) on every rank
+    sd.cfg_parallel = True                          # ... which the shared per-step seed does (stylize.py)
     emb = torch.stack([torch.full((77, 32), 0.2), torch.full((77, 32), 0.5)])
     rgb = torch.rand(16 * 16, 3, generator=torch.Generator().manual_seed(5))
+    try:
+        sd.pixel_gradient(emb, rgb, 16, 16, guidance_scale=100)           # no seed: the ranks would draw different noise
+        refused = False
+    except RuntimeError:
+        refused = True
+    assert refused
     g = sd.pixel_gradient(emb, rgb, 16, 16, guidance_scale=100, seed=11)
     q.put((rank, g))
     dist.destroy_process_group()
@@ -125,7 +133,9 @@ def _shard_render_worker(rank, world, port, q):
         return a * 2.0 + b
 
     full = render_rays_sharded(fake_render, o, d, rank, world)
-    q.put((rank, full, calls))
+    odd = render_rays_sharded(fake_render, o[:7], d[:7], rank, world)        # 7 rays on 2 ranks: padded, gathered, trimmed
+    assert torch.equal(odd, o[:7] * 2.0 + 1.0)
+    q.put((rank, full, calls[:1]))
     dist.destroy_process_group()
 
 
@@ -144,3 +154,48 @@ def test_pass1_ray_sharding_reassembles_the_whole_image():
     want = torch.arange(24.0).reshape(8, 3) * 2.0 + 1.0
     for r in range(2):
         assert torch.equal(got[r][0], want) and got[r][1] == [4]       # half of the rays rendered locally, whole image held
+
+
+def _masked_mean_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from avatarcraft_b200.utils.distributed import masked_mean_share, shard_patches
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gen = torch.Generator().manual_seed(3)
+    w = torch.rand(600, 8, generator=gen).requires_grad_(True)                 # stands in for the parameters
+    pts = torch.rand(600, 8, generator=gen) * 2.0                               # |p| decides the eikonal mask
+    (s, e, scale), = shard_patches(600, 600, rank, world)                       # ONE patch split over both ranks
+    assert scale == 0.5
+    relax = (pts[s:e] < 1.2).float()
+    err = (w[s:e] * 3.0 - 1.0) ** 2
+    eik = (relax * err).sum() / (relax.sum() + 1e-5)                            # this rank's masked mean (models/instant_nsr.py:266-272)
+    (eik * masked_mean_share(relax.sum())).backward()
+    g = w.grad.clone()
+    dist.all_reduce(g)
+    q.put((rank, g, float(relax.sum())))
+    dist.destroy_process_group()
+
+
+def test_split_patch_masked_eikonal_equals_single_process():
+    """the eikonal term is a masked mean whose mask count differs per rank; weighting each rank by its ray
+    share (1/2) is wrong, weighting by its share of the mask count reproduces the single-process gradient."""
+    import torch
+    import torch.multiprocessing as mp
+    gen = torch.Generator().manual_seed(3)
+    w = torch.rand(600, 8, generator=gen).requires_grad_(True)
+    pts = torch.rand(600, 8, generator=gen) * 2.0
+    relax = (pts < 1.2).float()
+    ((relax * (w * 3.0 - 1.0) ** 2).sum() / (relax.sum() + 1e-5)).backward()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_masked_mean_worker, args=(r, 2, 29577, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = {r: (g, c) for r, g, c in (q.get(timeout=120) for _ in range(2))}
+    for p in ps:
+        p.join(timeout=60)
+    assert got[0][1] != got[1][1]                                               # the two halves do have different mask counts
+    for r in range(2):
+        assert float((got[r][0] - w.grad).abs().max()) <= 1e-6 * float(w.grad.abs().max())

@@ -155,3 +155,36 @@ def test_stylize_with_sds_guidance_and_resume(tmp_path):
     assert res2["step"] == 2 and res2["optimizer"]["step"] == 2
     second = torch.load(ck, map_location="cpu")
     assert float((second["encoder.embeddings"] - first["encoder.embeddings"]).abs().max()) > 0
+
+
+def test_stylize_resume_is_step_accurate_inside_an_epoch(tmp_path):
+    """A periodic checkpoint taken in the middle of an epoch records the position inside the epoch's view permutation: the
+    resumed run trains the remaining views only (same total step count as the uninterrupted run, reference file names
+    <exp>_<step+1, 0-based: 4 digits>.pth.tar) and ends at (nearly) the same weights -- the hash-table gradient is summed
+    with atomics, so not bit for bit."""
+    import os, subprocess, sys
+    from tests.util import ROOT
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    def run(cwd, *a):
+        os.makedirs(cwd, exist_ok=True)
+        return subprocess.run([sys.executable, os.path.join(ROOT, "stylize.py"), "--synthetic", "--exp_name", "r", "--render_h", "32", "--render_w", "32",
+                               "--n_views", "3", "--coarse_epochs", "1", "--fine_epochs", "0", "--subsample_scale", "1", "--batch_size", "1024",
+                               "--guidance", "target", "--i_save", "2", *a], cwd=cwd, env=env, capture_output=True, text=True, timeout=600)
+    a, b = tmp_path / "a", tmp_path / "b"
+    r = run(a)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out_a = a / "style" / "canonical_360" / "r"
+    assert (out_a / "r_0002.pth.tar").exists() and (out_a / "r_0004.pth.tar").exists()          # periodic (step 2) and final (3 + 1)
+    mid = torch.load(out_a / "r_0002.resume.pt", map_location="cpu", weights_only=False)
+    assert mid["step"] == 2 and mid["epoch"] == 0 and mid["extra"]["view_pos"] == 2
+    r = run(b, "--resume", str(out_a / "r_0002.pth.tar"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "view 2" in r.stdout
+    out_b = b / "style" / "canonical_360" / "r"
+    end_b = torch.load(out_b / "r.resume.pt", map_location="cpu", weights_only=False)
+    assert end_b["step"] == 3 and end_b["optimizer"]["step"] == 3                                 # one more step, not a replayed epoch
+    wa, wb = torch.load(out_a / "r.pth.tar", map_location="cpu"), torch.load(out_b / "r.pth.tar", map_location="cpu")
+    for k in wa:
+        assert float((wa[k].float() - wb[k].float()).abs().max()) <= 2e-3, k
+    # constant learning rate by default: the reference never steps its StepLR (stylize.py:214)
+    assert end_b["optimizer"]["lr"] == 5e-3
