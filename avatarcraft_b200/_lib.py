@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("AC_LIB_PATH") or os.path.join(_PKG, "libavatarcraft_b200.so")   # AC_LIB_PATH: tuning variants
-SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu", "raymarch_ops.cu", "frame_ops.cu", "sd_ops.cu", "nsr_train_tc.cu"]
+SOURCES = ["api_common.cu", "encoder_ops.cu", "nsr_kernels.cu", "nsr_render_tc.cu", "warp_ops.cu", "sh_ops.cu", "raymarch_ops.cu", "frame_ops.cu", "sd_ops.cu", "nsr_train_tc.cu", "nsr_shade_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -77,6 +77,26 @@ class NsrRenderArgs(ctypes.Structure):
                 ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64)]
 
 
+class NsrShadeArgs(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("rays_o", "rays_d", "z_vals", "points", "centre", "fd", "bg_color")] + \
+               [("n_rays", ctypes.c_uint32), ("n_samples", ctypes.c_uint32), ("num_steps", ctypes.c_uint32),
+                ("bound", ctypes.c_float), ("eps", ctypes.c_float), ("cos_anneal_ratio", ctypes.c_float)] + \
+               [(k, ctypes.c_void_p) for k in ("rgb", "depth", "weight_sum", "normal", "eik_partial", "weights", "pts_color", "pts_alpha")]
+
+
+class NsrShadeGrads(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("g_rgb", "g_weight_sum", "g_normal", "g_depth", "g_eikonal", "wsum_gt")] + \
+               [("opacity_weight", ctypes.c_float)] + \
+               [(k, ctypes.c_void_p) for k in ("eik_out", "scale", "g_centre", "g_fd", "g_variance", "terms_a", "terms_b", "g_b1", "opacity_loss")] + \
+               [("terms_ld", ctypes.c_uint64)]
+
+
+class WeightNormLayer(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("dW", "v", "g", "dv", "dg")] + \
+               [("rows", ctypes.c_int), ("cols", ctypes.c_int), ("ldw", ctypes.c_int), ("scale", ctypes.c_void_p), ("db", ctypes.c_void_p),
+                ("db_col", ctypes.c_int)]
+
+
 _V, _U32, _F, _I, _D, _I64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_double, ctypes.c_int64
 _SIGNATURES = {
     "ac_version": (ctypes.c_char_p, []),
@@ -95,6 +115,14 @@ _SIGNATURES = {
     "ac_nsr_sdf_backward_fused": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V, _V, _V, _V, _V]),
     "ac_nsr_forward_sdf_stencil": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V]),
     "ac_nsr_sdf_backward_stencil": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V, _V, _V, _V, _V]),
+    "ac_nsr_shade_forward": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrShadeArgs), _V, _V]),
+    "ac_nsr_shade_backward": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrShadeArgs), ctypes.POINTER(NsrShadeGrads), _V]),
+    "ac_absmax_scale": (_I, [_V, _U32, _F, _V, _V]),
+    "ac_nsr_sdf_backward_scales": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _V, _V]),
+    "ac_fill_uniform": (_I, [_V, ctypes.c_uint64, ctypes.c_uint64, _V]),
+    "ac_zero": (_I, [_V, ctypes.c_uint64, _V]),
+    "ac_nsr_section_points": (_I, [_V, _V, _V, _U32, _U32, _F, _V, _V]),
+    "ac_nsr_weight_norm_backward": (_I, [ctypes.POINTER(WeightNormLayer), _U32, _V]),
     "ac_nsr_forward_color": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _U32, _V]),
     "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
     "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),

@@ -23,11 +23,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/avatarcraft_b200.h"
 #include "launch_util.cuh"
 #include "nsr_device.cuh"
 #include "tc05.cuh"
+#include "nsr_tc_group.cuh"
 
 using namespace acb;
 
@@ -231,6 +233,303 @@ __global__ void __launch_bounds__(kThreadsT, 1) sdf_backward_tc_kernel(const flo
     if (warp == 0) tc05::tmem_dealloc<64 * kGroupsT>(*tmem_slot);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Second version (default): the per-point MLP recompute and back-propagation run on the tensor cores as well, with row =
+// point tiles (the layout the render / forward kernels write), so the CUDA cores are left with the hash gathers, the
+// activations and the table reductions.  Per 128 points (one 4-warp group, thread = point = tile row):
+//
+//   IN  [128 pts x 64]  fp16  cols 0..31 hash features (hi; lo in a second tile), 32..34 x y z, 35 = 1, 36..47 = 0,
+//                             48..63 grad_out * s_g
+//   round 1   a   [128 x 64] = IN_feat(hi,lo) W0f(hi,lo)^T                       6 x tcgen05.mma M128 N64 K16 (fp16x3)
+//   epilogue  a += W0[:, xyz] p + b0 (fp32) ; h = softplus100(a) ; dh = W1^T grad_out (fp32: one product per unit for the six
+//             finite-difference neighbours, whose 15 feature gradients are zero) ; delta = dh * sigmoid(100 a)
+//   DH  [128 pts x 128] fp16  cols 0..63 delta * s_d (hi; lo in a second tile), 64..127 h
+//   round 2   din [128 x 32] = DELTA(hi,lo) W0f(hi,lo)                           12 x tcgen05.mma M128 N32 K16 (fp16x3)
+//             D   [128 x 64] += DH^T IN : the weight gradients, K = the 128 points  8 x tcgen05.mma M128 N64 K16
+//   scatter   din / s_d into the eight corners of the sixteen levels (red.global.add.v2.f32)
+//
+// The weight-gradient product reads the SAME tiles transposed: a K-major [point][column] tile, seen as an MN-major operand,
+// is [column][point] (core matrices of 8 points x 8 columns; SBO = the 2 KB column-chunk stride, LBO = the 128 B between
+// 8-point groups), so nothing is written twice.  D[0..63][0..35] = s_d [dW0 (features, xyz) | db0], D[64..127][48..63] =
+// s_g dW1^T, accumulated in TMEM over the persistent loop and flushed once per group.
+// Three groups per CTA: each group needs 64 KB of tiles (IN 16, DH 32, lo 16) and 128 TMEM columns.
+constexpr int kGroupsB = 3;
+constexpr int kThreadsB = 128 * kGroupsB;
+constexpr size_t M_XB = 0;                                        // float4 [64]: W0[j][x y z], b0[j]
+constexpr size_t M_W1T = M_XB + 64 * 16;                          // float [64][16]
+constexpr size_t M_LV = M_W1T + 64 * 16 * 4;
+constexpr size_t M_WT = (M_LV + kLevels * sizeof(LevelMeta) + 1023) / 1024 * 1024;
+constexpr uint32_t WT_W0_HI = 0, WT_W0_LO = 4096;                 // W0f  [n = 64 units][k = 32 features], chunk stride 1024
+constexpr uint32_t WT_W0T_HI = 8192, WT_W0T_LO = 12288;           // W0f^T [n = 32 features][k = 64 units], chunk stride 512
+constexpr uint32_t WT_BYTES = 16384;
+constexpr size_t M_TILES = M_WT + WT_BYTES;
+constexpr uint32_t G_IN = 0, G_DH = 16384, G_LO = 49152, G_BYTES = 65536;
+constexpr size_t M_BARS = M_TILES + (size_t)kGroupsB * G_BYTES;
+constexpr size_t M_TOTAL = M_BARS + kGroupsB * 8 + 16;
+static_assert(M_TOTAL <= 227 * 1024, "shared memory budget");
+
+// kind::f16, fp32 accumulate, A and B both MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t idesc_f16_mn(uint32_t M, uint32_t N) { return tc05::idesc_f16(M, N) | (1u << 15) | (1u << 16); }
+
+__global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                                        const float* __restrict__ blob, float S, uint32_t H,
+                                                                        const float* __restrict__ x, const float* __restrict__ gout, uint32_t B,
+                                                                        float bound, const float* __restrict__ scales, float* __restrict__ grad_table,
+                                                                        float* __restrict__ grad_w0b, float* __restrict__ grad_w1, const uint32_t stencil_M,
+                                                                        const float eps, const float* __restrict__ gout_fd) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float4* xb = reinterpret_cast<float4*>(smem + M_XB);
+    float* w1t = reinterpret_cast<float*>(smem + M_W1T);
+    LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + M_LV);
+    unsigned char* wt = smem + M_WT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M_BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroupsB);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, group = warp >> 2;
+
+    for (int j = tid; j < 64; j += blockDim.x)
+        xb[j] = make_float4(__ldg(blob + OFF_W0 + j * kSdfInPad), __ldg(blob + OFF_W0 + j * kSdfInPad + 1), __ldg(blob + OFF_W0 + j * kSdfInPad + 2),
+                            __ldg(blob + OFF_B0 + j));
+    for (int i = tid; i < 64 * 16; i += blockDim.x) w1t[i] = __ldg(blob + OFF_W1T + i);
+    if (tid < kLevels) lv[tid] = make_level_meta(offsets, tid, S, H, 3);
+    for (int i = tid; i < 64 * 32; i += blockDim.x) {
+        const int j = i >> 5, f = i & 31;
+        const float w = __ldg(blob + OFF_W0 + j * kSdfInPad + 3 + f);
+        stage_b_tile(wt + WT_W0_HI, wt + WT_W0_LO, j, f, w);
+        const __half h = __float2half_rn(w), l = __float2half_rn(w - __half2float(h));
+        const int at = (j >> 3) * 512 + f * 16 + (j & 7) * 2;
+        *reinterpret_cast<__half*>(wt + WT_W0T_HI + at) = h;
+        *reinterpret_cast<__half*>(wt + WT_W0T_LO + at) = l;
+    }
+    if (tid == 0) {
+        for (int g = 0; g < kGroupsB; ++g) tc05::mbar_init(bars + g, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc<512>(tmem_slot);
+    tc05::fence_proxy_async_smem();
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    Group g;
+    g.a = smem + M_TILES + (size_t)group * G_BYTES;
+    g.a_s = tc05::smem_u32(g.a);
+    g.b_s = tc05::smem_u32(wt);
+    g.bar = bars + group;
+    g.phase = 0;
+    g.row = (warp & 3) * 32 + lane;
+    g.tmem = tmem_base + (uint32_t)group * 128u + ((uint32_t)((warp & 3) * 32) << 16);
+    g.bar_id = 1 + group;
+    {
+        bool ok = true;
+        for (int l = 0; l < kLevels; ++l) ok = ok && (lv[l].hashed == (l < 5 ? 0u : 1u));
+        g.std_layout = ok;
+    }
+    const uint32_t tmem_acc = (g.tmem & 0xFFFFu) + 64u;                  // weight-gradient accumulator columns of this group
+    const float s_d = scales[0], s_g = scales[1], inv_s_d = 1.0f / s_d;
+    unsigned char* row_ptr = g.a + g.row * 16;
+
+    for (uint32_t base = blockIdx.x * kThreadsB; base < B; base += gridDim.x * kThreadsB) {     // uniform trip count per CTA
+        const uint32_t b = base + tid;
+        const bool valid = b < B;
+        float px = 3.0f * bound + 1.0f, py = px, pz = px;                 // padding threads: out of range -> zero features, no scatter
+        uint32_t blk = 0, smp = 0;
+        float gq[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) gq[q] = 0.f;
+        if (valid) {
+            smp = b;
+            if (stencil_M) { blk = b / stencil_M; smp = b - blk * stencil_M; }
+            px = x[3 * (size_t)smp]; py = x[3 * (size_t)smp + 1]; pz = x[3 * (size_t)smp + 2];
+            if (blk) {
+                const float e = (blk & 1) ? eps : -eps;
+                const uint32_t ax = (blk - 1) >> 1;
+                if (ax == 0) px = clampf(px + e, -bound, bound);
+                else if (ax == 1) py = clampf(py + e, -bound, bound);
+                else pz = clampf(pz + e, -bound, bound);
+                gq[0] = gout_fd[(size_t)(blk - 1) * stencil_M + smp];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(gout + 16 * (size_t)smp + 4 * q);
+                    gq[4 * q] = v.x; gq[4 * q + 1] = v.y; gq[4 * q + 2] = v.z; gq[4 * q + 3] = v.w;
+                }
+            }
+        }
+        const bool sd_only = __all_sync(0xffffffffu, blk != 0u || !valid);   // warp-uniform: only d/d(signed distance) is non-zero
+        // ---- IN tile: features (hi | lo), then (x y z 1 0 0 0 0), zeros, grad_out * s_g ----
+        encode_to_tile<G_LO>(row_ptr + G_IN, table, lv, bound, px, py, pz, g.std_layout);
+        {
+            uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) { c4.x = tc05::pack_f16x2(px, py); c4.y = tc05::pack_f16x2(pz, 1.0f); }
+            *reinterpret_cast<uint4*>(row_ptr + G_IN + 4 * 2048) = c4;
+            *reinterpret_cast<uint4*>(row_ptr + G_IN + 5 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+            uint4 g0, g1;
+            g0.x = tc05::pack_f16x2(gq[0] * s_g, gq[1] * s_g); g0.y = tc05::pack_f16x2(gq[2] * s_g, gq[3] * s_g);
+            g0.z = tc05::pack_f16x2(gq[4] * s_g, gq[5] * s_g); g0.w = tc05::pack_f16x2(gq[6] * s_g, gq[7] * s_g);
+            g1.x = tc05::pack_f16x2(gq[8] * s_g, gq[9] * s_g); g1.y = tc05::pack_f16x2(gq[10] * s_g, gq[11] * s_g);
+            g1.z = tc05::pack_f16x2(gq[12] * s_g, gq[13] * s_g); g1.w = tc05::pack_f16x2(gq[14] * s_g, gq[15] * s_g);
+            *reinterpret_cast<uint4*>(row_ptr + G_IN + 6 * 2048) = g0;
+            *reinterpret_cast<uint4*>(row_ptr + G_IN + 7 * 2048) = g1;
+        }
+        // ---- round 1: pre-activation of the hidden layer (feature part) ----
+        group_mma_round(g, [&] {
+            constexpr uint32_t idesc = tc05::idesc_f16(128, 64);
+#pragma unroll
+            for (uint32_t s = 0; s < 2; ++s) {
+                const uint64_t ah = tc05::smem_desc(g.a_s + G_IN + s * 4096u, 2048u, 128u);
+                const uint64_t al = tc05::smem_desc(g.a_s + G_LO + s * 4096u, 2048u, 128u);
+                const uint64_t bh = tc05::smem_desc(g.b_s + WT_W0_HI + s * 2048u, 1024u, 128u);
+                const uint64_t bl = tc05::smem_desc(g.b_s + WT_W0_LO + s * 2048u, 1024u, 128u);
+                tc05::mma_f16(g.tmem & 0xFFFFu, ah, bh, idesc, s);
+                tc05::mma_f16(g.tmem & 0xFFFFu, al, bh, idesc, 1u);
+                tc05::mma_f16(g.tmem & 0xFFFFu, ah, bl, idesc, 1u);
+            }
+        });
+        // ---- epilogue: activation, its derivative, dL/d(pre-activation) -> DH tile ----
+#pragma unroll 1
+        for (int qtr = 0; qtr < 4; ++qtr) {
+            float acc[16];
+            tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+            float dl[16], hh[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int j = qtr * 16 + jj;
+                const float4 w = xb[j];
+                const float a = acc[jj] + fmaf(w.x, px, fmaf(w.y, py, fmaf(w.z, pz, w.w)));
+                hh[jj] = softplus100_mufu(a);
+                float dh;
+                if (sd_only) {
+                    dh = w1t[j * 16] * gq[0];
+                } else {
+                    const float4* __restrict__ w1 = reinterpret_cast<const float4*>(w1t + j * 16);
+                    dh = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w4 = w1[q];
+                        dh = fmaf(w4.x, gq[4 * q], dh); dh = fmaf(w4.y, gq[4 * q + 1], dh);
+                        dh = fmaf(w4.z, gq[4 * q + 2], dh); dh = fmaf(w4.w, gq[4 * q + 3], dh);
+                    }
+                }
+                const float da = a * 100.0f > 20.0f ? dh : dh * sigmoid_mufu(a * 100.0f);
+                dl[jj] = da * s_d;
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint4 hi, lo, hd;
+                tc05::split_f16x2(dl[8 * half + 0], dl[8 * half + 1], hi.x, lo.x); tc05::split_f16x2(dl[8 * half + 2], dl[8 * half + 3], hi.y, lo.y);
+                tc05::split_f16x2(dl[8 * half + 4], dl[8 * half + 5], hi.z, lo.z); tc05::split_f16x2(dl[8 * half + 6], dl[8 * half + 7], hi.w, lo.w);
+                hd.x = tc05::pack_f16x2(hh[8 * half + 0], hh[8 * half + 1]); hd.y = tc05::pack_f16x2(hh[8 * half + 2], hh[8 * half + 3]);
+                hd.z = tc05::pack_f16x2(hh[8 * half + 4], hh[8 * half + 5]); hd.w = tc05::pack_f16x2(hh[8 * half + 6], hh[8 * half + 7]);
+                const int c = 2 * qtr + half;
+                *reinterpret_cast<uint4*>(row_ptr + G_DH + c * 2048) = hi;
+                *reinterpret_cast<uint4*>(row_ptr + G_LO + c * 2048) = lo;
+                *reinterpret_cast<uint4*>(row_ptr + G_DH + (8 + c) * 2048) = hd;
+            }
+        }
+        // ---- round 2: dL/d(features) and the weight-gradient accumulation ----
+        const bool first = base == blockIdx.x * kThreadsB;
+        group_mma_round(g, [&] {
+            constexpr uint32_t idesc_d = tc05::idesc_f16(128, 32);
+#pragma unroll
+            for (uint32_t s = 0; s < 4; ++s) {
+                const uint64_t ah = tc05::smem_desc(g.a_s + G_DH + s * 4096u, 2048u, 128u);
+                const uint64_t al = tc05::smem_desc(g.a_s + G_LO + s * 4096u, 2048u, 128u);
+                const uint64_t bh = tc05::smem_desc(g.b_s + WT_W0T_HI + s * 1024u, 512u, 128u);
+                const uint64_t bl = tc05::smem_desc(g.b_s + WT_W0T_LO + s * 1024u, 512u, 128u);
+                tc05::mma_f16(g.tmem & 0xFFFFu, ah, bh, idesc_d, s);
+                tc05::mma_f16(g.tmem & 0xFFFFu, al, bh, idesc_d, 1u);
+                tc05::mma_f16(g.tmem & 0xFFFFu, ah, bl, idesc_d, 1u);
+            }
+            constexpr uint32_t idesc_w = idesc_f16_mn(128, 64);
+#pragma unroll
+            for (uint32_t s = 0; s < 8; ++s)             // K = the 128 points = 8 x (K = 16): 8-point groups 2s, 2s+1
+                tc05::mma_f16(tmem_acc, tc05::smem_desc(g.a_s + G_DH + s * 256u, 128u, 2048u), tc05::smem_desc(g.a_s + G_IN + s * 256u, 128u, 2048u),
+                              idesc_w, (first && s == 0) ? 0u : 1u);
+        });
+        float din[32];
+        {
+            float acc[16];
+            tc05::tmem_ld16(g.tmem, acc);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) din[q] = acc[q] * inv_s_d;
+            tc05::tmem_ld16(g.tmem + 16, acc);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) din[16 + q] = acc[q] * inv_s_d;
+        }
+        // ---- scatter into the table (same arithmetic as kernel_grid_backward, hashencoder.cu:223-308) ----
+        const float two_b = 2.0f * bound;
+        const float u = (px + bound) / two_b, v = (py + bound) / two_b, w = (pz + bound) / two_b;
+        if (!valid || (u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f)) continue;
+#pragma unroll
+        for (int l = 0; l < kLevels; ++l) {
+            const LevelMeta m = lv[l];
+            float fx = fmaf(u, m.scale, 0.5f), fy = fmaf(v, m.scale, 0.5f), fz = fmaf(w, m.scale, 0.5f);
+            const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+            const uint32_t ix = (uint32_t)flx, iy = (uint32_t)fly, iz = (uint32_t)flz;
+            fx -= flx; fy -= fly; fz -= flz;
+            float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
+            const float gx = din[2 * l], gy = din[2 * l + 1];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t cx = ix + (c & 1), cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
+                uint32_t slot;
+                if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
+                else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
+                const float wgt = (((c & 1) ? fx : 1.0f - fx) * ((c & 2) ? fy : 1.0f - fy)) * ((c & 4) ? fz : 1.0f - fz);
+                atomicAdd(dst + slot, make_float2(wgt * gx, wgt * gy));
+            }
+        }
+    }
+    // ---- flush this group's accumulator: row = TMEM lane = unit; columns in IN-tile order ----
+    tc05::fence_after_sync();
+    if (blockIdx.x * kThreadsB < B) {                    // CTAs without work never issued an MMA: nothing to add
+        const int r = g.row;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float acc[16];
+            tc05::tmem_ld16(g.tmem + 64 + q * 16, acc);
+            if (r < 64) {                                // s_d [dW0 | db0]: features -> columns 3..34, xyz -> 0..2, the ones column -> 35
+                for (int c = 0; c < 16; ++c) {
+                    const int col = q * 16 + c;
+                    if (col < 32) atomicAdd(grad_w0b + r * 36 + 3 + col, acc[c]);
+                    else if (col < 35) atomicAdd(grad_w0b + r * 36 + (col - 32), acc[c]);
+                    else if (col == 35) atomicAdd(grad_w0b + r * 36 + 35, acc[c]);
+                }
+            } else if (q == 3) {                         // s_g dW1^T: columns 48..63 -> grad_w1[o][j]
+                for (int c = 0; c < 16; ++c) atomicAdd(grad_w1 + c * 64 + (r - 64), acc[c]);
+            }
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<512>(tmem_base);
+}
+
+bool use_v1_backward() {
+    static const bool v1 = [] { const char* e = getenv("AC_SDF_BWD_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
+    return v1;
+}
+
+int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout, uint32_t B, float bound, const float* scales, float* grad_table,
+                        float* grad_w0b, float* grad_w1, uint32_t stencil_M, float eps, const float* gout_fd, cudaStream_t st) {
+    const float2* table = reinterpret_cast<const float2*>(m->embeddings);
+    if (use_v1_backward()) {
+        ACB_SET_MAX_SMEM(sdf_backward_tc_kernel, T_TOTAL);
+        const uint32_t want = (B + kThreadsT - 1) / kThreadsT;
+        const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
+        sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, gout, B,
+                                                                 bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd);
+    } else {
+        ACB_SET_MAX_SMEM(sdf_backward_mma_kernel, M_TOTAL);
+        const uint32_t want = (B + kThreadsB - 1) / kThreadsB;
+        const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
+        sdf_backward_mma_kernel<<<grid, kThreadsB, M_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, gout, B,
+                                                                  bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd);
+    }
+    return acb::launched();
+}
+
 }  // namespace
 
 extern "C" int ac_nsr_sdf_backward_fused(const ac_nsr_model* m, const float* x, const float* grad_out, uint32_t B, float bound,
@@ -238,14 +537,7 @@ extern "C" int ac_nsr_sdf_backward_fused(const ac_nsr_model* m, const float* x, 
     if (!m || !m->embeddings || !m->offsets || !m->mlp_blob || !x || !grad_out || !scales || !grad_table || !grad_w0b || !grad_w1)
         return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sdf_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_TOTAL); attr = true; }
-    const uint32_t want = (B + kThreadsT - 1) / kThreadsT;
-    const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
-    sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, grad_out, B,
-        bound, scales, grad_table, grad_w0b, grad_w1, 0u, 0.f, nullptr);
-    return acb::launched();
+    return launch_sdf_backward(m, x, grad_out, B, bound, scales, grad_table, grad_w0b, grad_w1, 0u, 0.f, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ac_nsr_sdf_backward_stencil(const ac_nsr_model* m, const float* P, uint32_t M, float bound, float eps, const float* grad_centre,
@@ -255,13 +547,5 @@ extern "C" int ac_nsr_sdf_backward_stencil(const ac_nsr_model* m, const float* P
         return AC_E_INVALID_ARG;
     if (!(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
     if (M == 0) return AC_OK;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sdf_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_TOTAL); attr = true; }
-    const uint32_t B = 7u * M;
-    const uint32_t want = (B + kThreadsT - 1) / kThreadsT;
-    const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
-    sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, P, grad_centre, B,
-        bound, scales, grad_table, grad_w0b, grad_w1, M, eps, grad_fd);
-    return acb::launched();
+    return launch_sdf_backward(m, P, grad_centre, 7u * M, bound, scales, grad_table, grad_w0b, grad_w1, M, eps, grad_fd, (cudaStream_t)stream);
 }

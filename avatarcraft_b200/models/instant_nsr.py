@@ -138,6 +138,99 @@ class _SdfStencil(torch.autograd.Function):
         return None, grad_table, gw0b[:, :35].contiguous(), gw0b[:, 35].contiguous(), gw1, gb1, None, None, None
 
 
+def _shade_args(o, d, z, P, centre, fd, bg, num_steps, bound, eps, car, bufs):
+    n, T = z.shape
+    return _lib.NsrShadeArgs(rays_o=o.data_ptr(), rays_d=d.data_ptr(), z_vals=z.data_ptr(), points=P.data_ptr(), centre=centre.data_ptr(),
+                             fd=fd.data_ptr(), bg_color=None if bg is None else bg.data_ptr(), n_rays=n, n_samples=T, num_steps=int(num_steps),
+                             bound=float(bound), eps=float(eps), cos_anneal_ratio=float(car),
+                             rgb=bufs["rgb"].data_ptr(), depth=bufs["depth"].data_ptr(), weight_sum=bufs["wsum"].data_ptr(),
+                             normal=bufs["normal"].data_ptr(), eik_partial=bufs["eikp"].data_ptr(), weights=bufs["weights"].data_ptr(),
+                             pts_color=bufs["color"].data_ptr(), pts_alpha=bufs["alpha"].data_ptr())
+
+
+def _shade_forward(net, o, d, z, P, centre, fd, bg, num_steps, bound, eps, car):
+    """ac_nsr_shade_forward; returns the output buffers (dict) incl. eik_out = (eikonal, mask count)."""
+    n, T = z.shape
+    dev = z.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    bufs = {"rgb": torch.empty(n, 3, **f32), "depth": torch.empty(n, **f32), "wsum": torch.empty(n, **f32), "normal": torch.empty(n, 3, **f32),
+            "eikp": torch.empty(n, 2, **f32), "weights": torch.empty(n, T, **f32), "color": torch.empty(n, T, 3, **f32),
+            "alpha": torch.empty(n, T, **f32), "eik_out": torch.empty(2, **f32)}
+    m = net._device_model()
+    a = _shade_args(o, d, z, P, centre, fd, bg, num_steps, bound, eps, car, bufs)
+    _lib.check(_lib.lib().ac_nsr_shade_forward(ctypes.byref(m), ctypes.byref(a), _lib.ptr(bufs["eik_out"]), _lib.stream_ptr()), "ac_nsr_shade_forward")
+    return bufs
+
+
+def _shade_workspace(net, M, dev):
+    """fp16 term buffers [136, ld] / [160, ld] (zeroed once: the padding rows are never written) + the [136,160] GEMM output."""
+    ld = (M + 7) // 8 * 8
+    ws = getattr(net, "_shade_ws", None)
+    if ws is None or ws["ld"] != ld or ws["A"].device != dev:
+        ws = {"ld": ld, "A": torch.zeros(136, ld, device=dev, dtype=torch.float16), "B": torch.zeros(160, ld, device=dev, dtype=torch.float16),
+              "C": torch.empty(136, 160, device=dev, dtype=torch.float32), "scale": torch.empty(1, device=dev, dtype=torch.float32)}
+        net._shade_ws = ws
+    return ws
+
+
+def _shade_backward(net, o, d, z, P, centre, fd, bg, num_steps, bound, eps, car, bufs, g_rgb, g_wsum=None, g_normal=None, g_depth=None,
+                    g_eik=None, wsum_gt=None, opacity_weight=0.0, g_variance=None, g_b1=None, opacity_loss=None):
+    """ac_nsr_shade_backward + the ONE tensor-core GEMM that reduces the colour-MLP weight-gradient terms over the samples.
+    Returns g_centre [M,16], g_fd [6,M], C [136,160] (= scale * the three weight gradients, see the header) and scale [1]."""
+    n, T = z.shape
+    M, dev = n * T, z.device
+    L = _lib.lib()
+    ws = _shade_workspace(net, M, dev)
+    g_rgb = g_rgb.reshape(n, 3).float().contiguous()
+    _lib.check(L.ac_absmax_scale(_lib.ptr(g_rgb), 3 * n, 256.0, _lib.ptr(ws["scale"]), _lib.stream_ptr()), "ac_absmax_scale")
+    g_centre = torch.empty(M, 16, device=dev, dtype=torch.float32)
+    g_fd = torch.empty(6, M, device=dev, dtype=torch.float32)
+    opt = lambda t: None if t is None else t.data_ptr()
+    gr = _lib.NsrShadeGrads(g_rgb=g_rgb.data_ptr(), g_weight_sum=opt(g_wsum), g_normal=opt(g_normal), g_depth=opt(g_depth), g_eikonal=opt(g_eik),
+                            wsum_gt=opt(wsum_gt), opacity_weight=float(opacity_weight), eik_out=bufs["eik_out"].data_ptr(),
+                            scale=ws["scale"].data_ptr(), g_centre=g_centre.data_ptr(), g_fd=g_fd.data_ptr(), g_variance=opt(g_variance),
+                            terms_a=ws["A"].data_ptr(), terms_b=ws["B"].data_ptr(), g_b1=opt(g_b1), opacity_loss=opt(opacity_loss),
+                            terms_ld=ws["ld"])
+    m = net._device_model()
+    a = _shade_args(o, d, z, P, centre, fd, bg, num_steps, bound, eps, car, bufs)
+    _lib.check(L.ac_nsr_shade_backward(ctypes.byref(m), ctypes.byref(a), ctypes.byref(gr), _lib.stream_ptr()), "ac_nsr_shade_backward")
+    _lib.check(L.ac_sd_gemm_f16(_lib.ptr(ws["A"]), _lib.ptr(ws["B"]), None, None, 0, None, _lib.ptr(ws["C"]), 0, 136, 160, M, ws["ld"], ws["ld"],
+                                160, 0, 1, 1, 0, 0, 0, 0, 0, 0, _lib.stream_ptr()), "ac_sd_gemm_f16 (colour weight gradients)")
+    return g_centre, g_fd, ws["C"], ws["scale"]
+
+
+class _ShadeComposite(torch.autograd.Function):
+    """Everything of `run` after the SDF stencil (models/instant_nsr.py:210-299) as ONE kernel each way: normals, colour MLP
+    (tcgen05), NeuS alpha, transmittance scan, compositing, eikonal.  c0 / c1 / c2 are the weight-norm-folded colour
+    weights (graph inputs: the kernels read the packed blob built from the same parameters)."""
+
+    @staticmethod
+    def forward(ctx, centre, fd, c0, c1, c2, variance, net, o, d, z, P, bg, num_steps, bound, eps, car):
+        centre, fd = centre.contiguous(), fd.contiguous()
+        bufs = _shade_forward(net, o, d, z, P, centre, fd, bg, num_steps, bound, eps, car)
+        ctx.save_for_backward(centre, fd, o, d, z, P)
+        ctx.net, ctx.bg, ctx.cfg, ctx.bufs = net, bg, (num_steps, bound, eps, car), bufs
+        ctx.mark_non_differentiable(bufs["weights"], bufs["color"], bufs["alpha"])
+        net.last_eikonal_count = bufs["eik_out"][1]                      # samples inside the eikonal mask (split-patch weighting)
+        return bufs["rgb"], bufs["depth"], bufs["wsum"], bufs["normal"], bufs["eik_out"][0], bufs["weights"], bufs["color"], bufs["alpha"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_wsum, g_normal, g_eik, *_):
+        centre, fd, o, d, z, P = ctx.saved_tensors
+        n = z.shape[0]
+        f32 = dict(device=z.device, dtype=torch.float32)
+        cont = lambda t: None if t is None else t.float().contiguous()
+        g_var = torch.zeros(1, **f32)
+        num_steps, bound, eps, car = ctx.cfg
+        g_centre, g_fd, C, scale = _shade_backward(ctx.net, o, d, z, P, centre, fd, ctx.bg, num_steps, bound, eps, car, ctx.bufs,
+                                                   torch.zeros(n, 3, **f32) if g_rgb is None else g_rgb, cont(g_wsum), cont(g_normal),
+                                                   cont(g_depth), None if g_eik is None else g_eik.float().reshape(1).contiguous(),
+                                                   g_variance=g_var)
+        C = C / scale
+        return (g_centre, g_fd, C[64:128, 64:85].contiguous(), C[0:64, 0:64].contiguous(), C[128:131, 96:160].contiguous(), g_var.reshape(()),
+                None, None, None, None, None, None, None, None, None, None)
+
+
 class SingleVarianceNetwork(nn.Module):
     """exp(10 * variance), one learnable scalar (models/instant_nsr.py:720-726)."""
 
@@ -312,9 +405,10 @@ class NeRFRenderer(nn.Module):
         gradient (`with torch.no_grad()`, models/instant_nsr.py:175-185): the depths come from the fused
         kernel.  The differentiable part (:186-299) evaluates the 7 x N x T SDF points with the fused
         `_SdfStencil` op (one tensor-core launch forward that generates the six +-eps neighbours of every
-        section point itself; one fused backward: table scatter + weight gradients reduced in TMEM); the
-        per-sample algebra (normals, alpha, compositing, eikonal) and the colour MLP are torch ops here -- a
-        fused backward kernel for them is the next step."""
+        section point itself; one fused backward: table scatter + weight gradients reduced in TMEM) and everything
+        after it -- normals, colour MLP, NeuS alpha, compositing, eikonal -- with `_ShadeComposite` (one launch forward,
+        one backward + one tensor-core GEMM for the colour weight gradients).  Only the weight-norm fold of the small MLP
+        weights is left to torch autograd here; utils/train_utils.native_patch_step removes that too."""
         B, N = rays_o.shape[:2]
         o = rays_o.reshape(-1, 3).float().contiguous()
         d = rays_d.reshape(-1, 3).float().contiguous()
@@ -326,48 +420,26 @@ class NeRFRenderer(nn.Module):
                 z = z_override.to(dev, torch.float32).contiguous()
             else:
                 z = self._sample_depths(o, d, num_steps, upsample_steps, bound, jitter)
-            T = z.shape[1]
-            near, far = near_far_from_bound(o, d, bound)
-            gaps = torch.cat([z[:, 1:] - z[:, :-1], ((far - near) / num_steps).expand(n, 1)], -1)
-            z_mid = torch.cat([z[:, :-1] + 0.5 * gaps[:, :-1], z[:, -1:]], -1)
-            P = (o[:, None, :] + d[:, None, :] * z_mid[..., None]).clamp(-bound, bound).reshape(-1, 3)
+            P = self._section_points(o, d, z, bound)
             eps = 0.005 * (1.0 - normal_epsilon_ratio)
-        M = P.shape[0]
         sdf_w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in self.sdf_net]
         col_w = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in self.color_net]
         centre, fd = _SdfStencil.apply(P, self.encoder.embeddings, sdf_w[0], self.sdf_net[0].bias, sdf_w[1], self.sdf_net[1].bias,
                                        self, bound, eps)
-        sdf, feat = centre[:, :1], centre[:, 1:]
-        f = fd.reshape(3, 2, M)
-        grad = (0.5 * (f[:, 0] - f[:, 1]) / eps).t()
-        gnorm = torch.linalg.norm(grad, ord=2, dim=-1, keepdim=True)
-        normal = grad / (1e-5 + gnorm)
-        h = torch.cat([P, normal, feat], dim=-1)
-        h = torch.relu(torch.nn.functional.linear(h, col_w[0]))
-        h = torch.relu(torch.nn.functional.linear(h, col_w[1]))
-        color = torch.sigmoid(torch.nn.functional.linear(h, col_w[2]))
-        inv_s = torch.exp(self.deviation_net.variance * 10.0).clip(1e-6, 1e6)
-        dirs = d[:, None, :].expand(n, T, 3).reshape(-1, 3)
-        cosv = (dirs * normal).sum(-1, keepdim=True)
-        sp = torch.nn.functional.softplus
-        it = -(sp(-cosv * 0.5 + 0.5, beta=100) * (1.0 - cos_anneal_ratio) + sp(-cosv, beta=100) * cos_anneal_ratio)
-        half = it * gaps.reshape(-1, 1) * 0.5
-        c0, c1 = torch.sigmoid((sdf - half) * inv_s), torch.sigmoid((sdf + half) * inv_s)
-        alpha = ((c0 - c1 + 1e-5) / (c0 + 1e-5)).reshape(n, T).clip(0.0, 1.0)
-        trans = torch.cumprod(torch.cat([torch.ones(n, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
-        weights = alpha * trans
-        wsum = weights.sum(-1, keepdim=True)
-        color = color.reshape(n, T, 3)
-        image = (color * weights[..., None]).sum(1)
-        nmap = (normal.reshape(n, T, 3) * weights[..., None]).sum(1)
-        depth = (weights * ((z - near) / (far - near)).clamp(0, 1)).sum(-1)
-        relax = (torch.linalg.norm(P, ord=2, dim=-1).reshape(n, T) < 1.2).float()
-        gerr = (gnorm.reshape(n, T) - 1.0) ** 2
-        eik = (relax * gerr).sum() / (relax.sum() + 1e-5)
-        self.last_eikonal_count = relax.sum().detach()          # samples inside the eikonal mask (split-patch weighting)
-        bg = 1 if bg_color is None else torch.as_tensor(bg_color, dtype=torch.float32, device=dev)
-        image = image + (1 - wsum) * bg
-        return depth.reshape(B, N), weights, wsum, image.reshape(B, N, 3), nmap, eik, 0.0, color, alpha, z
+        bg = None if bg_color is None else torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
+        image, depth, wsum, nmap, eik, weights, color, alpha = _ShadeComposite.apply(
+            centre, fd, col_w[0], col_w[1], col_w[2], self.deviation_net.variance, self, o, d, z, P, bg, num_steps, bound, eps,
+            cos_anneal_ratio)
+        return depth.reshape(B, N), weights, wsum.reshape(n, 1), image.reshape(B, N, 3), nmap, eik, 0.0, color, alpha, z
+
+    @staticmethod
+    def _section_points(o, d, z, bound):
+        """[n*T, 3] mid-points of the sorted depths, clamped (models/instant_nsr.py:186-206): one kernel."""
+        n, T = z.shape
+        P = torch.empty(n * T, 3, device=z.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ac_nsr_section_points(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), n, T, float(bound), _lib.ptr(P), _lib.stream_ptr()),
+                   "ac_nsr_section_points")
+        return P
 
     def render(self, rays_o, rays_d, num_steps, bound, upsample_steps, staged=False, max_ray_batch=4096, bg_color=None,
                cos_anneal_ratio=1.0, normal_epsilon_ratio=1.0, render_can=True, verts=None, faces=None, Ts=None,

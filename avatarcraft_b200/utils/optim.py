@@ -52,7 +52,8 @@ class FlatAdam:
         self.param_groups = [{"params": self.params, "lr": self.lr}]       # torch.optim-style view (lr schedulers)
 
     def zero_grad(self, set_to_none: bool = False):
-        self.flat_grad.zero_()
+        with torch.cuda.device(self.flat_grad.device):
+            _lib.check(_lib.lib().ac_zero(_lib.ptr(self.flat_grad), self.numel * 4, _lib.stream_ptr()), "ac_zero")
         for p, (a, n) in zip(self.params, self._spans):                   # re-attach if autograd replaced .grad
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * a:
                 p.grad = self.flat_grad[a:a + n].view_as(p)

@@ -133,6 +133,71 @@ int ac_nsr_forward_sdf_stencil(const ac_nsr_model *model, const float *P, uint32
 int ac_nsr_sdf_backward_stencil(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
                                 const float *grad_centre, const float *grad_fd, const float *scales, float *grad_table,
                                 float *grad_w0b, float *grad_w1, void *stream);
+/* --------------------------------------------------------------------------------------
+ * The differentiable half of NeRFRenderer.run on the training path, after the SDF stencil
+ * (models/instant_nsr.py:210-299; driven by stylize.py:153-193): finite-difference normal, colour MLP, NeuS alpha,
+ * transmittance scan, compositing, eikonal -- forward and backward as one launch each.
+ *   n_rays rays x n_samples sorted depths (z_vals [n, T], T <= 128); M = n * T samples, m = ray * T + k.
+ *   points [M,3]: section points clamp(o + d * z_mid) (ac_nsr_section_points); centre [M,16], fd [6,M]: outputs of
+ *   ac_nsr_forward_sdf_stencil on `points`; num_steps: the coarse count (last interval = (far - near) / num_steps, :160,191).
+ * Forward writes rgb [n,3] (over bg_color [n,3], NULL = white), depth [n], weight_sum [n], normal [n,3],
+ *   eik_partial [n,2] (workspace), per-sample weights [M], pts_color [M,3], pts_alpha [M] (all required: the backward
+ *   reads them) and eik_out[0] = sum(m (|g| - 1)^2) / (sum(m) + 1e-5) over the launch (:266-272), eik_out[1] = sum(m).
+ * Backward: upstream gradients g_rgb [n,3] (required), g_weight_sum [n], g_normal [n,3], g_depth [n] (optional), g_eikonal
+ *   (optional DEVICE scalar); or the trainer's opacity term fused: wsum_gt [n] (optional) adds opacity_weight *
+ *   d/d ws mean(smooth_l1(clamp(ws,0,1), clamp(wsum_gt,0,1))) (stylize.py:187-193).
+ *   Writes g_centre [M,16] and g_fd [6,M] (the inputs of ac_nsr_sdf_backward_stencil), adds d loss / d variance to
+ *   *g_variance (optional), and writes the fp16 per-sample terms of the colour-MLP weight gradients, sample-contiguous:
+ *     terms_a [136, ld]: rows 0..63 d/d a2 (layer-1 pre-activation), 64..127 d/d a1, 128..130 d/d z2, all times `scale`
+ *     terms_b [160, ld]: rows 0..63 h1, 64..84 the layer-0 input (x, n, 15 features), 96..159 h2
+ *   (rows 131..135 / 85..95 are never written: allocate zeroed), so that ONE ac_sd_gemm_f16(A = terms_a, W = terms_b,
+ *   M = 136, N = 160, K = M samples) yields scale * [dC1 at [0:64, 0:64], dC0 at [64:128, 64:85], dC2 at [128:131, 96:160]].
+ *   scale: DEVICE scalar, a power of two with scale * max|g_rgb| <= ~256 (ac_absmax_scale(g_rgb, 3 n, 256, scale)).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const float *rays_o, *rays_d, *z_vals, *points, *centre, *fd, *bg_color;
+  uint32_t n_rays, n_samples, num_steps;
+  float bound, eps, cos_anneal_ratio;
+  float *rgb, *depth, *weight_sum, *normal, *eik_partial, *weights, *pts_color, *pts_alpha;
+} ac_nsr_shade_args;
+typedef struct {
+  const float *g_rgb, *g_weight_sum, *g_normal, *g_depth, *g_eikonal, *wsum_gt;
+  float opacity_weight;
+  const float *eik_out, *scale;
+  float *g_centre, *g_fd, *g_variance;
+  void *terms_a, *terms_b;
+  float *g_b1;           /* optional [16]: += column sums of g_centre (the six g_fd rows cancel) = d loss / d (sdf layer-1 bias) */
+  float *opacity_loss;   /* optional DEVICE scalar: += the value of the fused opacity term (needs wsum_gt) */
+  uint64_t terms_ld;     /* row stride of terms_a / terms_b in halves: >= M, a multiple of 8 (the GEMM's lda / ldw) */
+} ac_nsr_shade_grads;
+int ac_nsr_shade_forward(const ac_nsr_model *model, const ac_nsr_shade_args *args, float *eik_out, void *stream);
+int ac_nsr_shade_backward(const ac_nsr_model *model, const ac_nsr_shade_args *args, const ac_nsr_shade_grads *grads,
+                          void *stream);
+/* *scale_out = 2^floor(log2(target / max|x|)) over n floats (1 when x == 0): operand scale of the fp16 backward paths. */
+int ac_absmax_scale(const float *x, uint32_t n, float target, float *scale_out, void *stream);
+/* points [n*T,3] = clamp(o + d * z_mid, +-bound), z_mid = z + (z_next - z) / 2, last sample at its own depth (:186-206). */
+int ac_nsr_section_points(const float *rays_o, const float *rays_d, const float *z_vals, uint32_t n_rays,
+                          uint32_t n_samples, float bound, float *points, void *stream);
+/* Backward of the weight-norm fold W = g * v / |v|_row (models/instant_nsr.py:555-556,585-586) for up to 5 layers in one
+ * launch: dv += ..., dg += ... from dW [rows, ldw] * dW_scale (gradients of the folded weights). */
+typedef struct {
+  const float *dW, *v, *g;
+  float *dv, *dg;
+  int rows, cols, ldw;
+  const float *scale;    /* optional DEVICE scalar: dW holds scale * gradient (the fp16 operand scales of the backward kernels) */
+  float *db;             /* optional [rows]: += dW[:, db_col] / scale (a bias gradient kept in a column of the same accumulator) */
+  int db_col;
+} ac_weight_norm_layer;
+int ac_nsr_weight_norm_backward(const ac_weight_norm_layer *layers, uint32_t n_layers, void *stream);
+/* scales[0..1] = (s_d, s_g) of ac_nsr_sdf_backward_stencil / _fused from the gradients themselves (scales: 3 floats, the
+ * third is scratch = max|g|); no host synchronisation. */
+int ac_nsr_sdf_backward_scales(const ac_nsr_model *model, const float *g_centre, const float *g_fd, uint32_t M,
+                               float *scales, void *stream);
+/* out[i] = uniform [0,1) from a counter-based generator keyed by (seed, i): the per-sample jitter of the training path
+ * (models/instant_nsr.py:161-162 draws torch.rand).  ac_zero: cudaMemsetAsync on the stream. */
+int ac_fill_uniform(float *out, uint64_t n, uint64_t seed, void *stream);
+int ac_zero(void *p, uint64_t bytes, void *stream);
+
 /* NeRFNetwork.forward_color (models/instant_nsr.py:644-663, use_viewdirs=False):
  * x [B,3], normal [B,3], geo_feat [B,15] -> rgb [B,3]. */
 int ac_nsr_forward_color(const ac_nsr_model *model, const float *x, const float *normal,
