@@ -97,12 +97,12 @@ class _NativeStepState:
         self.scales = torch.zeros(3, **f32)
         self.g_eik = torch.zeros(1, **f32)
         self.opacity = torch.zeros(64, **f32)                          # one slot per patch of a step
-        self.jitter_calls = 0
 
 
 def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, batch_size=4096, w_eikonal=0.01,
-                      use_opacity=True, bkg_key=WHITE_BKG, rank=0, world=1, jitter=None):
-    """stylize.py:143-199 on this library's kernels only -- per patch (models/instant_nsr.py:133-299 with gradients):
+                      use_opacity=True, bkg_key=WHITE_BKG, rank=0, world=1, jitter=None, mark=None):
+    """`mark(name)`: optional callback invoked on the stream after the patch loop / the all-reduce / the Adam launch.
+    stylize.py:143-199 on this library's kernels only -- per patch (models/instant_nsr.py:133-299 with gradients):
          jitter (ac_fill_uniform) -> sample depths (ac_nsr_render, sampling only) -> section points -> 7-point SDF stencil
          forward -> shade forward (normals, colour MLP, alpha, compositing, eikonal) -> frozen net_gt opacity render ->
          shade backward (pixel gradient, eikonal and opacity terms seeded in-kernel) + ONE GEMM (colour weight gradients)
@@ -139,8 +139,9 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
             jit = jitter[s:e].float().contiguous()
         else:
             jit = torch.empty(m, num_steps, device=dev, dtype=torch.float32)
-            st.jitter_calls += 1
-            seed = (torch.initial_seed() * 0x9E3779B1 + st.jitter_calls * 2654435761 + rank) & 0x7FFFFFFFFFFFFFFF
+            # keyed by a draw from torch's CPU generator: reproducible under torch.manual_seed, restored by a resume
+            # (utils/checkpoint.py saves the generator state), and no device work or synchronisation
+            seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) + rank * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF
             _lib.check(L.ac_fill_uniform(_lib.ptr(jit), m * num_steps, seed, sp()), "ac_fill_uniform")
         z = net_style._sample_depths(o, d, num_steps, upsample_steps, bound, jit)
         P = net_style._section_points(o, d, z, bound)
@@ -196,8 +197,14 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
             layer(C.data_ptr(), 160, col[1], "color_net.1", cscale),
             layer(C.data_ptr() + 4 * (128 * 160 + 96), 160, col[2], "color_net.2", cscale))
         _lib.check(L.ac_nsr_weight_norm_backward(layers, 5, sp()), "ac_nsr_weight_norm_backward")
+    if mark is not None:          # bench.py: CUDA events between the phases of the step
+        mark("pass2")
     optimizer.all_reduce()
+    if mark is not None:
+        mark("allreduce")
     optimizer.step()
+    if mark is not None:
+        mark("adam")
     return _LazyStats(stats)
 
 

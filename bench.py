@@ -110,21 +110,44 @@ def cpu_threads():
     return n
 
 
+_CPU_MODEL = {}
+
+
+def cpu_reference_kind():
+    """"reference": the reference's own NeRFRenderer.run / NeRFNetwork (unmodified Python from baseline/_ref, torch CPU) with the
+    CUDA-only hash kernel replaced by the oracle's C restatement; "port": the oracle restatement of `run` (baseline/_ref absent)."""
+    from baseline import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
 def cpu_oracle_rate(n_rays, repeats=1):
-    """rays/s of the oracle port (torch CPU + C hash restatement, all host threads)."""
+    """rays/s of the reference's CPU implementation of the path (see cpu_reference_kind), all host threads."""
     import torch
     from avatarcraft_b200.utils import synthetic as syn
-    from oracle.nsr_oracle import OracleNSR
     torch.set_num_threads(cpu_threads())
-    m = OracleNSR(syn.synthetic_state_dict("trained", 43))
+    kind = cpu_reference_kind()
+    if "m" not in _CPU_MODEL:
+        sd = syn.synthetic_state_dict("trained", 43)
+        if kind == "reference":
+            from baseline import ref_loader
+            net = ref_loader.load_reference(cuda=False).NeRFNetwork()
+            net.load_state_dict(sd)
+            net.eval()
+            _CPU_MODEL["m"] = lambda o, d: net.run(o[None], d[None], NUM_STEPS, BOUND, UPSAMPLE_STEPS, None, cos_anneal_ratio=1.0,
+                                                   normal_epsilon_ratio=0.0, render_can=True)
+        else:
+            from oracle.nsr_oracle import OracleNSR
+            m = OracleNSR(sd)
+            _CPU_MODEL["m"] = lambda o, d: m.run(o, d, NUM_STEPS, BOUND, UPSAMPLE_STEPS)
     o, d = frame_rays(0)
     sel = slice(RAYS_PER_FRAME // 2 - n_rays // 2, RAYS_PER_FRAME // 2 + n_rays // 2)   # central rows: rays that hit
     best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        m.run(o[sel], d[sel], NUM_STEPS, BOUND, UPSAMPLE_STEPS)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            _CPU_MODEL["m"](o[sel], d[sel])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
     return n_rays / best, best
 
 
@@ -146,13 +169,16 @@ def run_reference(args):
         _, dt = cpu_oracle_rate(n_rays)
         t += dt
     value = n_rays * args.steps / t
-    sample = f"{n_rays} central rays of the 256x256 frame per step, 64+64 samples (oracle port, torch CPU + C hash grid)"
+    kind = cpu_reference_kind()
+    sample = (f"{n_rays} central rays of the 256x256 frame per step, 64+64 samples (" +
+              ("the reference's own NeRFRenderer.run, torch CPU, C restatement of its CUDA-only hash kernel)" if kind == "reference"
+               else "oracle port, torch CPU + C hash grid)"))
     print(json.dumps({
         "impl": "reference", "metric": "rays_per_sec_volume_render", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step": n_rays, "device": "host CPU"},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -235,15 +261,21 @@ def run_ours(args):
     try:
         if os.environ.get("AC_BENCH_SKIP_SDS"):          # profiling runs (ncu) only want the render launches
             raise RuntimeError("skipped (AC_BENCH_SKIP_SDS)")
-        full = measure_train(3, 3, world, rank, dev, sd_guidance=True)       # BASELINE.json configs[2] with the guidance in the loop
-        sds = {k: full[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches")}
-        nerf = measure_train(3, 3, world, rank, dev)                          # the same step with a stand-in pixel gradient
-        sds["nerf_side_only"] = {k: nerf[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches")}
-        c = measure_train(10, 3, world, rank, dev, coarse=True)               # coarse stage (one 4096-ray patch), stand-in gradient
-        sds["coarse_stage_nerf_side_only"] = {k: c[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches")}
+        full = measure_train(10, 3, world, rank, dev, sd_guidance=True)      # BASELINE.json configs[2] with the guidance in the loop
+        sds = {k: full[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "config", "gpu_launches", "phases_ms")}
+        nerf = measure_train(10, 3, world, rank, dev)                         # the same step with a stand-in pixel gradient
+        sds["nerf_side_only"] = {k: nerf[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "phases_ms")}
+        c = measure_train(20, 3, world, rank, dev, coarse=True)               # coarse stage (one 4096-ray patch), stand-in gradient
+        sds["coarse_stage_nerf_side_only"] = {k: c[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "phases_ms")}
+        if world == 1:
+            sds["reference_gpu_path"] = measure_reference_gpu(dev)            # the reference's own model code + CUDA kernel on this GPU
     except Exception as e:           # never lose the headline line to the secondary workload
         sds = {"metric": "sds_style_steps_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
     torch.set_grad_enabled(False)
+    try:
+        warp = measure_warp_frame(max(args.steps // 2, 5), dev, world, rank)   # BASELINE.json configs[3]: animate frame through the warp
+    except Exception as e:
+        warp = {"metric": "warp_frame_rays_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,8 +291,10 @@ def run_ours(args):
         achieved = algo_bytes / launch_s / 1e9
         tflops = RAYS_PER_FRAME * MLP_FLOP_PER_RAY / launch_s / 1e12
         cpu_rate, cpu_dt = cpu_oracle_rate(CPU_SAMPLE_RAYS)
-        prof = os.path.join(ROOT, "profiles", "r01_render_kernel_traffic.json")
-        traffic = json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
+        import glob
+        profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_render_kernel_traffic.json")))      # newest round's ncu capture
+        traffic = json.load(open(profs[-1])).get("dram_bytes_per_launch") if profs else None
+        traffic_src = os.path.relpath(profs[-1], ROOT) if profs else None
         line = {
             "metric": "rays_per_sec_volume_render", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -270,19 +304,20 @@ def run_ours(args):
                        "checkpoint": "synthetic trained-like seed 43", "parallelism": f"ray-shard x{world} (one view per rank)",
                        "l2": "flushed before every timed step (256 MiB memset); per-step CUDA events summed"},
             "roofline": {"bound": "hbm", "kernel": "nsr_render_tc_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "bound_ncu": "l1tex data pipe (gathers served by L1/L2; DRAM < 0.1 % of peak)",
                          "peak_source": pk["source"], "algorithmic_bytes_per_launch": algo_bytes,
                          "note": "algorithmic gather bytes (no reuse) per SURVEY.md 8(d); gathers are served from L1/L2, "
                                  "so frac may exceed 1 -- see traffic (ncu dram bytes) and profiles/",
                          "mlp_tflops": tflops, "mlp_frac_of_bf16_peak": tflops / pk["bf16_tflops"],
                          "measured_limiter": "L1 data pipe: l1tex__throughput 77 % of peak, issue slots 56 %, DRAM 0.06 % "
                                              "(ncu, profiles/r01f_render_kernel_tc_v5b.md)"},
-            "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": cpu_threads(), "kind": "port",
+            "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": cpu_threads(), "kind": cpu_reference_kind(),
                              "sample": f"{CPU_SAMPLE_RAYS}-ray batch (central rows) of the same frame, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 2 * RAYS_PER_FRAME * 12,
                     "d2h_bytes_per_step": RAYS_PER_FRAME * 12, "ms_per_step": ms_e2e / args.steps,
                     "api": "avatarcraft_b200.utils.render_utils.render_instantnsr_naive (pinned host rays in, pinned host rgb out)"},
-            "gpu_launches": int(launches), "clocks": clocks, "sds_step": sds}
+            "gpu_launches": int(launches), "clocks": clocks, "sds_step": sds, "warp_frame": warp}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -326,17 +361,26 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
         sd.cfg_parallel = world > 1          # every rank seeds the step identically (pixel_gradient(seed=...)): the CFG pair may be split
         emb = sd.get_text_embeds("a 3D rendering of a knight in bronze armour")
     count = [0]
+    events = []
+
+    def mark(name):
+        if events is not None and timing[0]:
+            e = torch.cuda.Event(enable_timing=True); e.record(); events.append((name, e))
+    timing = [False]
+    from avatarcraft_b200.utils.train_utils import native_patch_step
 
     def step():
+        mark("start")
         with torch.no_grad():                                                                            # pass 1, ray-sharded + one all-gather
             rgb = render_rays_sharded(lambda a, b: render_instantnsr_naive(net, a, b, rays_per_batch=4096, render_can=True, perturb=True)[0],
                                       o, d, rank, world)
+        mark("pass1")
         g = G
         if sd is not None:
             count[0] += 1
             g = sd.pixel_gradient(emb, rgb, side, side, 100.0, seed=77 + count[0])                        # SDS (models/diffusion.py:92-149)
-        with torch.enable_grad():
-            stylize_patch_step(net, gt, opt, o, d, g, batch_size=4096, rank=rank, world=world)           # pass 2 + allreduce + Adam
+        mark("guidance")
+        native_patch_step(net, gt, opt, o, d, g, batch_size=4096, rank=rank, world=world, mark=mark)      # pass 2 + allreduce + Adam
 
     for _ in range(max(warmup, 3)):
         step()
@@ -345,6 +389,7 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
         dist.barrier()
     l0 = _lib.lib().ac_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timing[0] = True
     e0.record()
     for _ in range(steps):
         step()
@@ -352,7 +397,11 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.barrier(); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return {"metric": "sds_style_steps_per_sec", "value": steps / (float(ms) * 1e-3), "unit": "steps/s", "n_gpus": world,
+    phases = {}
+    for (n0, a), (n1, b) in zip(events[:-1], events[1:]):            # rank 0's per-phase device time, averaged over the timed steps
+        if n1 != "start":
+            phases[n1] = phases.get(n1, 0.0) + a.elapsed_time(b) / steps
+    return {"metric": "sds_style_steps_per_sec", "phases_ms": {k: round(v, 3) for k, v in phases.items()}, "value": steps / (float(ms) * 1e-3), "unit": "steps/s", "n_gpus": world,
             "steps": steps, "warmup": max(warmup, 3), "ms_per_step": float(ms) / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("stylize.py coarse-stage step: 4096 rays (256x256 stride 4)" if coarse else
@@ -363,6 +412,111 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
                        "parallelism": f"pass 1 ray-sharded + all-gather, pass 2 patch-sharded x{world}, one 49 MB gradient all-reduce, "
                                       "SD guidance: classifier-free pair split over ranks, VAE replicated"},
             "gpu_launches": int(_lib.lib().ac_launch_count() - l0)}
+
+
+def measure_reference_gpu(dev):
+    """B-REF-GPU: the REFERENCE'S OWN model code (baseline/_ref/models/instant_nsr.py, unmodified) with
+    its own hash-encoder CUDA kernel compiled for sm_100a (oracle/_ref/_ref_hash_encoder.so) on this GPU: one 256x256 inference
+    frame in 4096-ray batches (render_instantnsr_naive's loop, utils/render_utils.py:514-600) and one pass-2 patch of the
+    trainer (stylize.py:153-199: render with gradients, pixel gradient + eikonal + opacity vs a frozen copy, backward)."""
+    import torch
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref not installed"}
+    try:
+        ref = ref_loader.load_reference(cuda=True)
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    from avatarcraft_b200.utils import synthetic as syn
+    sd = syn.synthetic_state_dict("trained", 43)
+    net = ref.NeRFNetwork(); net.load_state_dict(sd); net = net.to(dev).train()
+    gt = ref.NeRFNetwork(); gt.load_state_dict(sd); gt = gt.to(dev).eval()
+    for p in gt.parameters():
+        p.requires_grad_(False)
+    optim = torch.optim.Adam(net.parameters(), lr=5e-3)
+    o, d = frame_rays(0)
+    o, d = o.to(dev), d.to(dev)
+    G = torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(44)).to(dev)
+    kw = dict(num_steps=NUM_STEPS, upsample_steps=UPSAMPLE_STEPS, bound=BOUND, staged=False, bg_color=None, cos_anneal_ratio=1.0,
+              normal_epsilon_ratio=0.0, render_can=True)
+
+    def frame():
+        with torch.no_grad():
+            for s0 in range(0, RAYS_PER_FRAME, 4096):
+                net.render(o[None, s0:s0 + 4096], d[None, s0:s0 + 4096], perturb=False, **kw)
+
+    def patch(s0):
+        out = net.render(o[None, s0:s0 + 4096], d[None, s0:s0 + 4096], perturb=True, **kw)
+        with torch.no_grad():
+            og = gt.render(o[None, s0:s0 + 4096], d[None, s0:s0 + 4096], perturb=True, **kw)["weight_sum"]
+        loss = (out["rgb"].reshape(-1, 3) * G[s0:s0 + 4096]).sum() + 0.01 * out["gradient_error"] + \
+            torch.nn.functional.smooth_l1_loss(out["weight_sum"].clamp(0, 1), og.clamp(0, 1)) * 1e5
+        loss.backward()
+
+    def timed(fn, n):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms_frame = timed(frame, 2)
+    optim.zero_grad()
+    ms_patch = timed(lambda: patch(8 * 4096), 3)
+    optim.zero_grad()
+
+    def full_step():
+        frame()
+        optim.zero_grad()
+        for s0 in range(0, RAYS_PER_FRAME, 4096):
+            patch(s0)
+        optim.step()
+    ms_step = timed(full_step, 1)
+    return {"what": "reference models/instant_nsr.py (unmodified) + reference hashencoder.cu rebuilt for sm_100a, eager torch, this GPU",
+            "inference_frame_ms": ms_frame, "inference_rays_per_sec": RAYS_PER_FRAME / ms_frame * 1e3, "train_patch_ms": ms_patch,
+            "train_step_nerf_side_ms": ms_step, "train_steps_per_sec_nerf_side": 1e3 / ms_step}
+
+
+def measure_warp_frame(steps, dev, world, rank):
+    """BASELINE.json configs[3]: one render_warp.py --render_type animate frame at 256x256, 32+32 samples, batch 8192, on a
+    synthetic SMPL-shaped body (6890 vertices / 13 776 faces, 24 joints): per-frame posed-mesh preparation + mesh-guided
+    near/far + inverse-LBS warp of every sample (96 closest-point queries per ray) + the fused render.  Each rank renders its
+    own frame of the sequence (weak scaling, no collective)."""
+    import torch
+    import torch.distributed as dist
+    from avatarcraft_b200 import _lib
+    from avatarcraft_b200.models.instant_nsr import NeRFNetwork
+    from avatarcraft_b200.utils import synthetic as syn
+    from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
+    net = NeRFNetwork(); net.load_state_dict(syn.synthetic_state_dict("trained", 43)); net = net.to(dev).eval()
+    body = syn.synthetic_body()
+    o, d = syn.pinhole_rays(syn.orbit_pose(10.0 + 3.0 * rank), W_IMG, H_IMG)
+    o, d = o.to(dev), d.to(dev)
+
+    def frame():
+        return render_instantnsr_naive(net, o, d, 8192, render_can=False, perturb=False, verts=body["world_verts"], faces=body["faces"],
+                                       Ts=body["Ts"], num_steps=32, upsample_steps=32, bound=BOUND)
+    for _ in range(3):
+        frame()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.lib().ac_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        frame()
+    e1.record(); e1.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier(); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    per = float(ms) / steps
+    return {"metric": "warp_frame_rays_per_sec", "value": world * RAYS_PER_FRAME / per * 1e3, "unit": "rays/s", "ms_per_frame": per, "steps": steps,
+            "closest_point_queries_per_sec": world * RAYS_PER_FRAME * 96 / per * 1e3, "gpu_launches": int(_lib.lib().ac_launch_count() - l0),
+            "config": {"workload": "render_warp.py animate frame 256x256, 32+32 samples/ray, batch 8192, synthetic SMPL-shaped body "
+                                   "(6890 verts / 13 776 faces), mesh prep + near/far + warp (96 closest-point queries/ray) + render",
+                       "sdf_evals_per_ray": 496, "color_evals_per_ray": 64}}
 
 
 def run_train(args):

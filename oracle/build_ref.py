@@ -54,6 +54,28 @@ def build_raymarching():
     print("build_ref: built", target)
 
 
+def build_shencoder():
+    """The reference's spherical-harmonics extension (encoder/shencoder/src/{shencoder.cu,bindings.cpp}): the GPU pin of
+    ac_sh_encode_forward / _backward (tests/test_gpu_encoders.py)."""
+    src = "/root/reference/encoder/shencoder/src"
+    target = os.path.join(OUT, "_ref_sh_encoder.so")
+    if not os.path.isdir(src) or os.path.exists(target):
+        return
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+    load(name="_ref_sh_encoder", sources=[os.path.join(src, "shencoder.cu"), os.path.join(src, "bindings.cpp")],
+         extra_cflags=["-O3", "-std=c++17"],
+         extra_cuda_cflags=["-O3", "-std=c++17", "-U__CUDA_NO_HALF_OPERATORS__", "-U__CUDA_NO_HALF_CONVERSIONS__",
+                            "-U__CUDA_NO_HALF2_OPERATORS__"],
+         build_directory=OUT, verbose=False, is_python_module=False)
+    for f in os.listdir(OUT):
+        if f.endswith((".o", ".d")) or f in ("lock", "build.ninja", ".ninja_deps", ".ninja_log"):
+            os.remove(os.path.join(OUT, f))
+    print("build_ref: built", target)
+
+
 if __name__ == "__main__":
     main()
     build_raymarching()
+    build_shencoder()

@@ -102,3 +102,52 @@ def test_point_major_hash_ops_equal_reference_layout_ops():
     y = enc((torch.rand(100, 7, 3, device="cuda") * 2 - 1) * 1.6, 1.6)
     y.square().sum().backward()
     assert y.shape == (100, 7, 32) and enc.embeddings.grad is not None and float(enc.embeddings.grad.abs().sum()) > 0
+
+
+def _ref_sh_module():
+    """The reference's own shencoder.cu compiled for sm_100a by oracle/build_ref.py (test infrastructure)."""
+    import importlib.machinery, importlib.util, os
+    from tests.util import ROOT
+    so_path = os.path.join(ROOT, "oracle", "_ref", "_ref_sh_encoder.so")
+    if not os.path.exists(so_path):
+        pytest.skip("oracle/_ref/_ref_sh_encoder.so not built (run oracle/build_ref.py in the build container)")
+    loader = importlib.machinery.ExtensionFileLoader("_ref_sh_encoder", so_path)
+    spec = importlib.util.spec_from_loader("_ref_sh_encoder", loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_sh_ops_against_reference_kernel(degree):
+    """ac_sh_encode_forward / _backward next to the REFERENCE'S OWN kernel_sh / kernel_sh_backward (shencoder.cu:28-384) on the
+    same inputs (unit and non-unit directions).  The reference evaluates 64 hard-coded polynomials, this library a Legendre
+    recurrence: same polynomials, different association, so values agree to fp32 rounding (1e-6 relative to the largest
+    coefficient of the degree), not bit for bit."""
+    from avatarcraft_b200.encoder.shencoder.backend import _backend
+    ref = _ref_sh_module()
+    B, C = 50000, degree * degree
+    g = torch.Generator().manual_seed(100 + degree)
+    x = torch.randn(B, 3, generator=g)
+    x[: B // 2] /= x[: B // 2].norm(dim=-1, keepdim=True)                  # half unit directions, half arbitrary points in ~[-3, 3]
+    x[:3] = torch.eye(3)
+    x = x.cuda().contiguous()
+    out_r = torch.empty(B, C, device="cuda"); jac_r = torch.empty(B, 3 * C, device="cuda")
+    out_m = torch.empty_like(out_r); jac_m = torch.empty_like(jac_r)
+    ref.sh_encode_forward(x, out_r, B, 3, degree, True, jac_r)
+    _backend.sh_encode_forward(x, out_m, B, 3, degree, True, jac_m)
+    torch.cuda.synchronize()
+    so_, sj = float(out_r.abs().max()), float(jac_r.abs().max())
+    eo, ej = float((out_m - out_r).abs().max()), float((jac_m - jac_r).abs().max())
+    print(f"SH degree {degree}: max |out - ref| = {eo:.2e} (scale {so_:.2e}), max |dy_dx - ref| = {ej:.2e} (scale {sj:.2e})")
+    # unit half: coefficients are O(1), absolute agreement to a few ulps
+    eu = float((out_m[: B // 2] - out_r[: B // 2]).abs().max())
+    print(f"             unit directions only: max |out - ref| = {eu:.2e}")
+    assert eu <= 1e-6 * degree * degree                                      # O(1) coefficients: a few ulps per recurrence step
+    assert eo <= 1e-6 * max(so_, 1.0) and ej <= 1e-6 * max(sj, 1.0)
+    grad = torch.randn(B, C, generator=g).cuda()
+    gi_r = torch.zeros(B, 3, device="cuda"); gi_m = torch.zeros(B, 3, device="cuda")
+    ref.sh_encode_backward(grad, x, B, 3, degree, jac_r, gi_r)
+    _backend.sh_encode_backward(grad, x, B, 3, degree, jac_r, gi_m)          # same Jacobian in: the contraction alone
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(gi_m.cpu().numpy(), gi_r.cpu().numpy(), atol=1e-5 * max(float(gi_r.abs().max()), 1.0), rtol=1e-5)

@@ -177,6 +177,20 @@ def test_importance_round_bins_and_merge_bit_exact(T, inv_s):
     np.testing.assert_allclose(alpha_d.numpy(), alpha_o.numpy(), atol=1e-6)
     _, z_new, b, z_out, order = device_round(alpha_o.cuda())
     same = (b[..., 0] == lo_o.numpy()) & (b[..., 1] == hi_o.numpy())
+    # Every bin that differs must be a tie: u within two ulps of the CDF knot between the two candidate bins.  (The CDF is a
+    # running fp32 sum; torch.cumsum adds left to right, the kernel scans in a tree, so knots differ in the last bit and
+    # searchsorted(right=True) may land on either side of a knot that coincides with u.  No other mismatch is tolerated.)
+    w = alpha_o * torch.cumprod(torch.cat([torch.ones_like(alpha_o[:, :1]), 1.0 - alpha_o + 1e-7], -1), -1)[:, :-1] + 1e-5
+    pdf = w / w.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1).numpy()
+    u = np.linspace(0.5 / 16, 1.0 - 0.5 / 16, 16, dtype=np.float32)
+    bad = np.argwhere(~same)
+    for ray, iu in bad:
+        lo_d, lo_r = int(b[ray, iu, 0]), int(lo_o[ray, iu])
+        assert abs(lo_d - lo_r) == 1, (ray, iu, lo_d, lo_r)
+        knot = float(cdf[ray, max(lo_d, lo_r)])
+        assert abs(float(u[iu]) - knot) <= 2.4e-7 * max(knot, 0.5), (ray, iu, float(u[iu]), knot)
+    print(f"importance bins T={T}: {same.size - len(bad)} of {same.size} identical, {len(bad)} ties at a CDF knot (each verified)")
     assert same.mean() > 0.999, same.mean()
     dz = np.abs(z_new.numpy() - z_new_o.numpy())
     width = np.take_along_axis(z.numpy(), hi_o.numpy(), 1) - np.take_along_axis(z.numpy(), lo_o.numpy(), 1)
@@ -208,7 +222,13 @@ def test_fused_render_against_reference_fixture(name):
     assert psnr(rgb, g["rgb"]) >= 40.0                               # north_star gate
     assert_close_frac(rgb, g["rgb"], 2e-3, 0.03, "rgb")              # >= 97 % of pixel channels within 2e-3
     dz = np.abs(z.cpu().numpy() - g["z_vals"]).max(1)
-    assert (dz <= 1e-4).mean() >= 0.85, (dz <= 1e-4).mean()
+    print(f"{name}: rays whose {z.shape[1]} depths agree with the reference to 1e-4: {(dz <= 1e-4).mean():.4f}, to 1e-5: {(dz <= 1e-5).mean():.4f}; "
+          f"PSNR {psnr(rgb, g['rgb']):.1f} dB")
+    # Measured on B200 (r02f): c1 1.000, c2 0.949, c4 0.977, c3 (training-mode jitter) 0.892.  The remainder are rays on
+    # which an importance sample sits at a CDF knot of a near-flat pdf: a last-bit difference in one signed distance (CPU GEMM
+    # summation order there, fp16x3 tensor-core products here) moves 16 new depths; on identical (z, sdf) the bins are
+    # bit-identical (test_importance_round_bins_and_merge_bit_exact).  Jittered coarse depths put more samples on such knots.
+    assert (dz <= 1e-4).mean() >= (0.88 if training else 0.93), (dz <= 1e-4).mean()
     ok = dz <= 1e-5                  # rays whose 128 depths coincide: everything downstream must agree too,
     assert ok.sum() > 0              # up to the chaos of sigmoid(inv_s ~ 403 * sdf) on single samples
     np.testing.assert_allclose(wsum.reshape(-1).cpu().numpy()[ok], g["weight_sum"][ok], atol=2e-3)
@@ -233,7 +253,8 @@ def test_fused_render_against_live_oracle_random_rays():
     out = net.run(o.cuda()[None], d.cuda()[None], 64, 1.6, 64, bg.cuda(), 1.0, 0.0)
     assert psnr(out[3].reshape(-1, 3).cpu().numpy(), ref[3].reshape(-1, 3).numpy()) >= 45.0
     dz = (out[9].cpu() - ref[9]).abs().max(1)[0].numpy()
-    assert (dz <= 1e-4).mean() >= 0.90
+    print(f"live oracle, random rays: depth coincidence (1e-4) {(dz <= 1e-4).mean():.4f}")
+    assert (dz <= 1e-4).mean() >= 0.93
     assert abs(float(out[5]) - float(ref[5])) < 1e-3
 
 

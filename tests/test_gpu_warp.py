@@ -34,12 +34,21 @@ def test_warp_samples_to_canonical_against_float64_oracle(body):
     can, dirs, closest, mask, face, d2 = warp_samples_to_canonical(pts.cuda(), body["world_verts"], body["faces"], body["Ts"], 0.05,
                                                                   return_query=True)
     np.testing.assert_allclose(d2.cpu().numpy(), d2_o, atol=2e-6, rtol=1e-4)
-    same_face = face.cpu().numpy() == face_o
-    # Closest points on a shared vertex / edge tie exactly between the incident faces; which one wins depends on
-    # rounding and scan order (igl's own choice is unknown anyway).  The distance is what pins the query.
-    assert same_face.mean() > 0.5
-    np.testing.assert_allclose(closest.cpu().numpy()[same_face], closest_o[same_face], atol=5e-5)   # ties: equidistant, different spot
-    np.testing.assert_allclose(can.cpu().numpy()[same_face], can_o[same_face], atol=2e-4)
+    face_d, same_face = face.cpu().numpy(), face.cpu().numpy() == face_o
+    # Off a closed surface the closest point is on an edge or a vertex about a third of the time (their Voronoi regions have
+    # volume), i.e. it belongs to two or more faces at the same distance: the face INDEX is then a tie (igl's own choice is
+    # unknown anyway) while the closest point -- and with it the barycentric blend of the per-vertex transforms, which only
+    # involves the shared vertices -- is unique.  So: the point itself must agree everywhere, and every differing index must
+    # be a face that shares a vertex with the oracle's.
+    print(f"closest-point query: face index identical on {same_face.mean():.4f} of {same_face.size} points")
+    F = np.asarray(body["faces"])
+    shares = np.array([len(set(F[a]) & set(F[b])) > 0 for a, b in zip(face_d[~same_face].ravel(), face_o[~same_face].ravel())])
+    print(f"  differing indices that are incident faces (share a vertex with the oracle's face): {shares.mean():.4f}")
+    assert shares.all()
+    dc = np.abs(closest.cpu().numpy() - closest_o).max(-1)
+    print(f"  closest point within 5e-5 of the oracle's on {(dc <= 5e-5).mean():.4f} of all points (max {dc.max():.2e})")
+    assert (dc <= 5e-5).mean() >= 0.999          # a handful may sit exactly between two different spots of a concave fold
+    np.testing.assert_allclose(can.cpu().numpy()[dc <= 5e-5], can_o[dc <= 5e-5], atol=2e-4)
     assert np.abs(can.cpu().numpy() - can_o).max() < 5e-3                 # blended transform is continuous across ties
     safe = np.abs(d2_o - 0.05) > 1e-6
     assert (mask.cpu().numpy() == mask_o)[safe].all()

@@ -63,3 +63,26 @@ def test_device_only_stages_refuse_cpu():
         ray_gen.pinhole_rays_device(np.eye(4), 8, 8, "cpu")
     with pytest.raises(RuntimeError):
         FlatAdam([torch.nn.Parameter(torch.zeros(4))])
+
+
+def test_models_neus_matches_reference_fixture():
+    """avatarcraft_b200.models.neus (legacy MLP NeuS API, models/neus.py:647,784) on the CPU against outputs of the reference's
+    own module (tests/golden/neus_small.npz, written by oracle/make_golden_neus.py): same state-dict keys, same render."""
+    import numpy as np
+    import torch
+    from tests.util import GOLDEN
+    from avatarcraft_b200.models.neus import build_neus, NeuSRenderer
+    g = dict(np.load(os.path.join(GOLDEN, "neus_small.npz")))
+    neus, params = build_neus(n_sdf=4, n_color=2, w_sdf=48, w_color=32, w_geo_feat=24, skip=[2], use_id=False)
+    assert isinstance(neus, NeuSRenderer) and len(params) > 0
+    neus = neus.cpu()
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    assert set(sd) == set(neus.state_dict())
+    neus.load_state_dict(sd)
+    o, d, near, far = (torch.from_numpy(g[k]) for k in ("rays_o", "rays_d", "near", "far"))
+    for tag, imp in (("coarse", -1), ("fine", 64)):
+        r = neus.render(o, d, near, far, perturb_overwrite=0, n_importance_overwrite=imp, background_rgb=torch.ones(1, 3), cos_anneal_ratio=0.7)
+        assert set(r) == {"color_fine", "s_val", "cdf_fine", "weight_sum", "weight_max", "gradients", "weights", "gradient_error",
+                          "inside_sphere"}
+        for k in ("color_fine", "weight_sum", "weights", "gradient_error", "cdf_fine", "s_val"):
+            np.testing.assert_allclose(r[k].detach().numpy(), g[f"{tag}.{k}"], atol=2e-5, rtol=1e-4, err_msg=f"{tag}.{k}")
