@@ -160,7 +160,7 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
         g_eik = None
         if w_eikonal > 0.0:
             if scale != 1.0:        # a split patch: this rank's share of the masked mean (one scalar all-reduce)
-                share = masked_mean_share(bufs["eik_out"][1])
+                share = masked_mean_share(bufs["eik_out"][1], group=optimizer.group)
                 st.g_eik.copy_((share * w_eikonal).reshape(1))
                 stats["eikonal"].append((bufs["eik_out"][0:1], share))
             else:
