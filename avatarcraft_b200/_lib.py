@@ -153,6 +153,10 @@ _SIGNATURES = {
     "ac_sd_geglu_f16": (_I, [_V, _I64, _I, _V, _V]),
     "ac_sd_softmax_f16": (_I, [_V, _I64, _I, _I64, _I64, _F, _V, _V]),
     "ac_sd_cast_f16": (_I, [_V, _I64, _V, _V]),
+    "ac_sd_group_norm_backward": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _V, _I, _V, _V, _V, _V, _V]),
+    "ac_sd_softmax_backward_f16": (_I, [_V, _V, _I64, _I, _I64, _F, _V, _V]),
+    "ac_sd_transpose_f16": (_I, [_V, _I, _I, _I64, _V, _I64, _V]),
+    "ac_sd_conv_s2_dgrad_operand_f16": (_I, [_V, _I, _I, _I, _I, _I, _I, _V, _V]),
     "ac_nsr_debug_tc_layer": (_I, [_V, _V, _V, _V]),
     "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V, _V, _V]),
 }

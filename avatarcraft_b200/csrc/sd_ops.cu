@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) sd_gemm_tma_kernel(const __grid_
                 // CTA's 128 output pixels shifted by the tap, fetched as one 4-D box (C, W, H, B) whose out-of-image part
                 // the TMA unit zero-fills (= the conv's zero padding).  No im2col buffer exists.
                 const int kt_g = kt_begin + kt, tap = kt_g / cv.cblocks, cb = kt_g - tap * cv.cblocks;
-                const int pix = m0 / cv.W, b0 = pix / cv.H, h0 = pix - b0 * cv.H;
-                tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, cb * 64, tap % 3 - 1, h0 + tap / 3 - 1, b0);
+                const int pix = m0 / cv.W, b0 = pix / cv.H, h0 = pix - b0 * cv.H, x0 = m0 - pix * cv.W;   // x0 != 0: rows wider than a tile
+                tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, cb * 64, x0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
             } else {
                 tma_load_4d(smem_s + s * STAGE_BYTES, &tmA, full_bar + s, k0, m0, a_zi ? zi : 0, a_zo ? zo : 0);
             }
@@ -723,6 +723,117 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) out[t] = __float2half_rn(x[t]);
 }
 
+// ---- backward of GroupNorm(+SiLU) over NHWC (the VAE encoder's input gradient IS the SDS gradient) ----------------------
+// y = act(gamma * xhat + beta), xhat = (x - mean) rstd.  With dz = dy * act'(z):
+//   dx = rstd * (gamma dz - s1 / n - xhat s2 / n),  s1 = sum_group gamma dz,  s2 = sum_group gamma dz xhat,  n = HW * C / G.
+__device__ __forceinline__ float gn_dz(float x, float dy, float mean, float rstd, float g, float b, int act, float& xhat) {
+    xhat = (x - mean) * rstd;
+    if (!act) return dy;
+    const float z = fmaf(g, xhat, b), sg = 1.0f / (1.0f + __expf(-z));
+    return dy * (sg * (1.0f + z * (1.0f - sg)));
+}
+// pass 1: grid (chunks, B), same mapping as gn_stats_kernel; sums[b][g] = (s1, s2) through fp64 atomics
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act, int HW, int C, int G,
+                                                            int px_per_block, double* __restrict__ sums) {
+    extern __shared__ float shf[];
+    const int b = blockIdx.y, cpg = C / G;
+    const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1], ga = gamma[c], be = beta[c];
+        float s1 = 0.f, s2 = 0.f;
+        long long at = ((long long)b * HW + p0) * C + c;
+        for (int p = p0; p < p1; ++p, at += C) {
+            float xh;
+            const float dz = gn_dz(x[at], dy[at], mean, rstd, ga, be, act, xh) * ga;
+            s1 += dz; s2 = fmaf(dz, xh, s2);
+        }
+        shf[2 * c] = s1; shf[2 * c + 1] = s2;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s1 += (double)shf[2 * c]; s2 += (double)shf[2 * c + 1]; }
+        atomicAdd(&sums[((long long)b * G + g) * 2], s1);
+        atomicAdd(&sums[((long long)b * G + g) * 2 + 1], s2);
+    }
+}
+// pass 2: elementwise; dx (+ add) -> fp32 and / or fp16
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, int act, long long total,
+                                                           int HW, int C, int G, const double* __restrict__ sums, const float* __restrict__ add,
+                                                           float* __restrict__ dx32, __half* __restrict__ dx16) {
+    const int cpg = C / G;
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        const int b = (int)(t / ((long long)HW * C)), g = c / cpg;
+        const long long sg = ((long long)b * G + g) * 2;
+        const float mean = stats[sg], rstd = stats[sg + 1], ga = gamma[c];
+        float xh;
+        const float dz = gn_dz(x[t], dy[t], mean, rstd, ga, beta[c], act, xh) * ga;
+        float v = rstd * (dz - (float)sums[sg] * inv_n - xh * (float)sums[sg + 1] * inv_n);
+        if (add) v += add[t];
+        if (dx32) dx32[t] = v;
+        if (dx16) dx16[t] = __float2half_rn(v);
+    }
+}
+
+// softmax backward: dS = P (dP - sum_row(P dP)) * scale.  One warp per row; P fp16 [rows, ld], dP fp32 [rows, ld] -> dS fp16.
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __half* __restrict__ P, const float* __restrict__ dP, long long rows, int L, long long ld,
+                                                          float scale, __half* __restrict__ dS) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half* pr = P + row * ld;
+    const float* dr = dP + row * ld;
+    float r = 0.f;
+    for (int c = lane; c < L; c += 32) r = fmaf(__half2float(pr[c]), dr[c], r);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    for (int c = lane; c < (int)ld; c += 32) dS[row * ld + c] = c < L ? __float2half_rn(__half2float(pr[c]) * (dr[c] - r) * scale) : __half(0.f);
+}
+
+// fp16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, long long ld_in, __half* __restrict__ out,
+                                                            long long ld_out) {
+    __shared__ __half tile[32][34];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = in[(long long)(r0 + j) * ld_in + c0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+        if (c0 + j < cols && r0 + tx < rows) out[(long long)(c0 + j) * ld_out + r0 + tx] = tile[tx][j];
+}
+
+// Operand of the input gradient of a 3x3 / stride-2 convolution with zero padding on the bottom / right only (the VAE's
+// Downsample2D): dy fp32 NHWC [B,Ho,Wo,N] -> fp16 [B*H*W, 9*Np]; row (b, y, x), K index (ky*3 + kx)*Np + n holds
+// dy[b, (y-ky)/2, (x-kx)/2, n] when y-ky and x-kx are even, non-negative and inside, else 0.  A GEMM with
+// W[c][(ky*3+kx)*Np + n] = w[n][c][ky][kx] then gives d_in [B*H*W, C].
+__global__ void __launch_bounds__(256) conv_s2_dgrad_operand_kernel(const float* __restrict__ dy, int B, int Ho, int Wo, int N, int Np, int H, int W,
+                                                                    __half* __restrict__ out) {
+    const int chunks = Np / 8;
+    const long long total = (long long)B * H * W * 9 * chunks;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % chunks);
+        long long r = t / chunks;
+        const int tap = (int)(r % 9); r /= 9;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        const int yy = y - tap / 3, xx = x - tap % 3;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (yy >= 0 && xx >= 0 && !(yy & 1) && !(xx & 1) && (yy >> 1) < Ho && (xx >> 1) < Wo) {
+            const float* src = dy + (((long long)b * Ho + (yy >> 1)) * Wo + (xx >> 1)) * N + ch * 8;
+            for (int j = 0; j < 8; ++j) if (ch * 8 + j < N) v[j] = src[j];
+        }
+        reinterpret_cast<uint4*>(out)[t] = pack8(v);
+    }
+}
+
 inline int grid_for(long long work, int block, int per_sm) {
     const long long want = (work + block - 1) / block;
     const long long cap = (long long)acb::sm_count() * per_sm;
@@ -787,12 +898,18 @@ int ac_sd_conv3x3_f16(const void* act, const void* W, const float* bias, const f
     // out fp32 NHWC [B,H,Wd,N] (+ bias[N], + group_bias[B,N], + residual [B,H,Wd,N]).
     if (!act || !W || !out || B <= 0 || H <= 0 || Wd <= 0 || C <= 0 || N <= 0 || (C & 63)) return AC_E_INVALID_ARG;
     if (((uintptr_t)act | (uintptr_t)W) & 15) return AC_E_INVALID_ARG;
-    // the 128 output pixels of a tile must be whole image rows: (bw, bh, bb) = box extents over (W, H, B)
+    // the 128 output pixels of a tile must be whole image rows, or 128 consecutive pixels of one row when rows are wider
+    // (the VAE's 256 / 512-pixel maps): (bw, bh, bb) = box extents over (W, H, B)
     int bw = Wd, bh, bb = 1;
-    if (Wd > 128 || 128 % Wd) return AC_E_UNSUPPORTED;
-    bh = 128 / Wd;
-    if (bh > H) { if (bh % H) return AC_E_UNSUPPORTED; bb = bh / H; bh = H; }
-    else if (H % bh) return AC_E_UNSUPPORTED;
+    if (Wd > 128) {
+        if (Wd % 128) return AC_E_UNSUPPORTED;
+        bw = 128; bh = 1;
+    } else {
+        if (128 % Wd) return AC_E_UNSUPPORTED;
+        bh = 128 / Wd;
+        if (bh > H) { if (bh % H) return AC_E_UNSUPPORTED; bb = bh / H; bh = H; }
+        else if (H % bh) return AC_E_UNSUPPORTED;
+    }
     const long long M = (long long)B * H * Wd;
     if (M > 0x7FFFFFFF) return AC_E_INVALID_ARG;
     GemmParams p;
@@ -915,6 +1032,47 @@ int ac_sd_softmax_f16(const float* scores, int64_t rows, int L, int64_t ld_in, i
 int ac_sd_cast_f16(const float* x, int64_t n, void* out, void* stream) {
     if (!x || !out || n <= 0) return AC_E_INVALID_ARG;
     cast_f16_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<__half*>(out));
+    return acb::launched();
+}
+
+int ac_sd_group_norm_backward(const float* x, const float* dy, int B, int HW, int C, int G, const float* stats, const float* gamma, const float* beta,
+                              int silu_act, const float* add, float* dx32, void* dx16, double* sums_workspace, void* stream) {
+    if (!x || !dy || !stats || !gamma || !beta || !sums_workspace || (!dx32 && !dx16) || B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G)
+        return AC_E_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * B * G, st) != cudaSuccess) return acb::cuda_fail();
+    const int px = HW >= 2048 ? 32 : (HW >= 256 ? 8 : 2);
+    dim3 grid((HW + px - 1) / px, B);
+    gn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(x, dy, stats, gamma, beta, silu_act, HW, C, G, px, sums_workspace);
+    if (int rc = acb::launched()) return rc;
+    const long long total = (long long)B * HW * C;
+    gn_bwd_apply_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(x, dy, stats, gamma, beta, silu_act, total, HW, C, G, sums_workspace, add, dx32,
+                                                                   reinterpret_cast<__half*>(dx16));
+    return acb::launched();
+}
+
+int ac_sd_softmax_backward_f16(const void* probs, const float* dprobs, int64_t rows, int L, int64_t ld, float scale, void* dscores, void* stream) {
+    if (!probs || !dprobs || !dscores || rows <= 0 || L <= 0 || ld < L) return AC_E_INVALID_ARG;
+    const long long blocks = (rows + 7) / 8;
+    if (blocks > 0x7FFFFFFFll) return AC_E_INVALID_ARG;
+    softmax_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(probs), dprobs, rows, L, ld, scale,
+                                                                             reinterpret_cast<__half*>(dscores));
+    return acb::launched();
+}
+
+int ac_sd_transpose_f16(const void* in, int rows, int cols, int64_t ld_in, void* out, int64_t ld_out, void* stream) {
+    if (!in || !out || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < rows) return AC_E_INVALID_ARG;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    if (grid.y > 65535) return AC_E_INVALID_ARG;
+    transpose_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(in), rows, cols, ld_in, reinterpret_cast<__half*>(out), ld_out);
+    return acb::launched();
+}
+
+int ac_sd_conv_s2_dgrad_operand_f16(const float* dy, int B, int Ho, int Wo, int N, int H, int W, void* out, void* stream) {
+    if (!dy || !out || B <= 0 || Ho <= 0 || Wo <= 0 || N <= 0 || H <= 0 || W <= 0) return AC_E_INVALID_ARG;
+    const int Np = (N + 7) / 8 * 8;
+    const long long total = (long long)B * H * W * 9 * (Np / 8);
+    conv_s2_dgrad_operand_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dy, B, Ho, Wo, N, Np, H, W, reinterpret_cast<__half*>(out));
     return acb::launched();
 }
 

@@ -78,6 +78,25 @@ class HashTextEncoder(nn.Module):
         return (self.final_layer_norm(self.encoder(x, mask=mask)),)
 
 
+class _NativeVaeMoments(torch.autograd.Function):
+    """quant_conv(encoder(x)) of the frozen VAE with both directions on the native kernels (models/sd_vae_native.py): the
+    autograd graph of the SDS step (models/diffusion.py:104-148) only sees this one node between the bilinear resize and the
+    posterior sample.  The incoming gradient is scaled by a power of two (device scalar, no sync) so that its fp16 GEMM
+    operands keep their precision; the backward is linear in it."""
+
+    @staticmethod
+    def forward(ctx, x, vae):
+        from . import sd_vae_native
+        moments, ctx.backward_fn = sd_vae_native.encode_moments(vae, x.detach())
+        return moments
+
+    @staticmethod
+    def backward(ctx, g):
+        gmax = g.abs().amax().clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(64.0 / gmax)).clamp(-60.0, 60.0))
+        return ctx.backward_fn(g * scale) / scale, None
+
+
 class StableDiffusion(nn.Module):
     def __init__(self, device, version="1.5", weights_dir=None, unet=None, vae=None, text_encoder=None, tokenizer=None,
                  unet_config=None, seed=0):
@@ -103,6 +122,7 @@ class StableDiffusion(nn.Module):
         # (latents, t, noise): the trainer guarantees that through pixel_gradient(seed=...) on the all-gathered pass-1 image
         # and switches it on; anywhere else the ranks draw their own randoms, so it is off by default.
         self.cfg_parallel = False
+        self.native_vae = True          # VAE encoder forward + backward on the native kernels (CUDA only); False = torch autograd ops
         self._user_text_encoder = text_encoder is not None
         if weights_dir is not None:
             self._load_diffusers_dir(weights_dir)
@@ -157,7 +177,11 @@ class StableDiffusion(nn.Module):
     # ---- the SDS step ----------------------------------------------------------------------------------------------
     def encode_imgs(self, imgs):
         """imgs [B,3,H,W] in [0,1] -> latents [B,4,H/8,W/8] = posterior.sample() * 0.18215 (:304-312)."""
-        posterior = self.vae.encode(2 * imgs - 1).latent_dist
+        if imgs.is_cuda and self.native_vae:          # both directions of the encoder on the sm_100a kernels
+            from .sd_vae import DiagonalGaussian
+            posterior = DiagonalGaussian(_NativeVaeMoments.apply(2 * imgs - 1, self.vae))
+        else:                                          # torch ops (CPU unit tests, A/B)
+            posterior = self.vae.encode(2 * imgs - 1).latent_dist
         return posterior.sample() * 0.18215
 
     def decode_latents(self, latents):

@@ -397,6 +397,22 @@ int ac_sd_geglu_f16(const float *x, int64_t M, int inner, void *out, void *strea
 int ac_sd_softmax_f16(const float *scores, int64_t rows, int L, int64_t ld_in, int64_t ld_out, float scale, void *out,
                       void *stream);
 int ac_sd_cast_f16(const float *x, int64_t n, void *out, void *stream);
+/* Backward pieces of the VAE encoder of the SDS step (models/diffusion.py:304-312 encodes WITH gradient, :148 back-propagates
+ * the latent gradient to the image; the weights are frozen, so only data gradients exist):
+ *   ac_sd_group_norm_backward   x, dy NHWC [B,HW,C], stats [B,G,2] of the forward -> dx (+ add) as fp32 and / or fp16;
+ *                               y = silu_act ? silu(gn(x)) : gn(x); sums_workspace: 2*B*G doubles.
+ *   ac_sd_softmax_backward_f16  dS = P (dP - rowsum(P dP)) * scale; P fp16, dP fp32, both [rows, ld] -> dS fp16 [rows, ld].
+ *   ac_sd_transpose_f16         fp16 [rows, cols] -> [cols, rows].
+ *   ac_sd_conv_s2_dgrad_operand_f16  GEMM operand [B*H*W, 9*Np] of the input gradient of the 3x3 stride-2 convolution with
+ *                               bottom/right zero padding (Downsample2D of the VAE) from dy NHWC [B,Ho,Wo,N]; Np = N rounded up to 8.
+ * Input gradients of the stride-1 convolutions are ac_sd_conv3x3_f16 / ac_sd_gemm_f16 with the flipped, transposed weights. */
+int ac_sd_group_norm_backward(const float *x, const float *dy, int B, int HW, int C, int G, const float *stats, const float *gamma,
+                              const float *beta, int silu_act, const float *add, float *dx32, void *dx16, double *sums_workspace,
+                              void *stream);
+int ac_sd_softmax_backward_f16(const void *probs, const float *dprobs, int64_t rows, int L, int64_t ld, float scale, void *dscores,
+                               void *stream);
+int ac_sd_transpose_f16(const void *in, int rows, int cols, int64_t ld_in, void *out, int64_t ld_out, void *stream);
+int ac_sd_conv_s2_dgrad_operand_f16(const float *dy, int B, int Ho, int Wo, int N, int H, int W, void *out, void *stream);
 
 /* Unit test of the tensor-core layer in isolation: feats [128,32] fp32 x (sdf layer 0 feature
  * columns)^T -> out [128,64] pre-activations WITHOUT bias / xyz terms (3xTF32 tcgen05.mma). */

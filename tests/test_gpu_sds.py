@@ -168,3 +168,86 @@ def test_sds_step_runs_end_to_end_with_native_unet():
     sd.mannual_backward(emb, rgb, guidance_scale=100)
     assert _lib.lib().ac_launch_count() - before > 100
     assert rgb.grad is not None and torch.isfinite(rgb.grad).all() and float(rgb.grad.abs().max()) > 0
+
+
+def _vae_native_vs_torch(vae, size, seed):
+    """moments and d(loss)/d(image) of the VAE encoder: native kernels (both directions) vs torch fp32 autograd, same weights."""
+    from avatarcraft_b200.models import sd_vae_native
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(1, 3, size, size, generator=g) * 2 - 1).cuda()
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False          # a true fp32 reference
+    try:
+        xr = x.clone().requires_grad_(True)
+        mom_r = vae.quant_conv(vae.encoder(xr))
+        R = torch.randn(mom_r.shape, generator=g).cuda()
+        (mom_r * R).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    before = _lib.lib().ac_launch_count()
+    mom_n, backward = sd_vae_native.encode_moments(vae, x)
+    gx = backward(R * 8.0) / 8.0                                   # the caller's power-of-two operand scale
+    launches = _lib.lib().ac_launch_count() - before
+    return rel(mom_n, mom_r.detach()), rel(gx, xr.grad), launches
+
+
+def test_native_vae_encoder_forward_backward_tiny():
+    torch.manual_seed(1)
+    vae = sd_vae.AutoencoderKL.tiny().cuda().eval()
+    for p in vae.parameters():
+        p.requires_grad_(False)
+    e_f, e_b, launches = _vae_native_vs_torch(vae, 64, 3)
+    print(f"native VAE encoder (tiny) vs torch fp32: moments rel L2 {e_f:.2e}, image gradient rel L2 {e_b:.2e}, {launches} launches")
+    assert launches > 50 and e_f < 5e-3 and e_b < 2e-2
+
+
+def test_native_vae_encoder_forward_backward_sd_size():
+    """The VAE of Stable Diffusion 1.5 / 2.x at the SDS step's size (512x512 -> [1,8,64,64]), random weights: both directions
+    of the native path against torch fp32 (cuDNN / cuBLAS, TF32 off) autograd on identical weights."""
+    torch.manual_seed(2)
+    vae = sd_vae.AutoencoderKL().cuda().eval()
+    for p in vae.parameters():
+        p.requires_grad_(False)
+    e_f, e_b, launches = _vae_native_vs_torch(vae, 512, 4)
+    print(f"native VAE encoder (SD size, 512x512) vs torch fp32: moments rel L2 {e_f:.2e}, image gradient rel L2 {e_b:.2e}, {launches} launches")
+    assert e_f < 5e-3 and e_b < 2e-2
+
+
+def test_sds_pixel_gradient_native_vae_equals_autograd_vae():
+    """StableDiffusion.pixel_gradient with the native VAE (default) vs the torch-autograd VAE on the same seed: same t, noise and
+    posterior sample, so the two image gradients must agree to operand rounding."""
+    torch.manual_seed(0)
+    sd = diffusion.StableDiffusion("cuda", "1.5", unet_config=sd_unet.UNetConfig.tiny(), vae=sd_vae.AutoencoderKL.tiny())
+    emb = sd.get_text_embeds("a bronze statue")
+    rgb = torch.rand(64 * 64, 3, device="cuda")
+    g_native = sd.pixel_gradient(emb, rgb, 64, 64, 100.0, seed=5)
+    sd.native_vae = False
+    g_torch = sd.pixel_gradient(emb, rgb, 64, 64, 100.0, seed=5)
+    assert torch.isfinite(g_native).all() and float(g_torch.abs().max()) > 0
+    e = rel(g_native, g_torch)
+    print(f"SDS pixel gradient, native VAE vs torch VAE: rel L2 {e:.2e}")
+    assert e < 5e-2           # the clamp(-1, 1) of the latent gradient sits between the two VAE passes: a few latents flip sides
+
+
+def test_native_unet_sd15_size_against_torch_fp32():
+    """The full SD-1.5-shaped UNet (859.5 M parameters, random init) on the (uncond, text) pair of the SDS step: native tcgen05
+    forward vs torch fp32 ops on identical weights (rel L2 <= 2e-3: fp16 operands, fp32 accumulation, ~60 GEMM layers)."""
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        unet = sd_unet.UNet2DConditionModel(sd_unet.UNetConfig.sd15()).eval()
+    x = torch.randn(2, 4, 64, 64, device="cuda")
+    ctx = torch.randn(2, 77, 768, device="cuda")
+    t = torch.tensor([417], device="cuda")
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    with torch.no_grad():
+        y = unet(x, t, encoder_hidden_states=ctx).sample
+        sd_ops.NATIVE = False
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            ref = unet(x, t, encoder_hidden_states=ctx).sample
+        finally:
+            sd_ops.NATIVE = True
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    e = rel(y, ref)
+    print(f"native UNet (SD-1.5 size) vs torch fp32: rel L2 {e:.2e}")
+    assert e < 2e-3
