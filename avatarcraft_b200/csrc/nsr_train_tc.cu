@@ -272,12 +272,15 @@ static_assert(M_TOTAL <= 227 * 1024, "shared memory budget");
 // kind::f16, fp32 accumulate, A and B both MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t idesc_f16_mn(uint32_t M, uint32_t N) { return tc05::idesc_f16(M, N) | (1u << 15) | (1u << 16); }
 
+// SPLIT = true: the table scatter is left to sdf_scatter_kernel; this kernel writes dL/d(features) of every point to
+// din_t [32][B] (feature-major, so both kernels' accesses are coalesced) instead.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
                                                                         const float* __restrict__ blob, float S, uint32_t H,
                                                                         const float* __restrict__ x, const float* __restrict__ gout, uint32_t B,
                                                                         float bound, const float* __restrict__ scales, float* __restrict__ grad_table,
                                                                         float* __restrict__ grad_w0b, float* __restrict__ grad_w1, const uint32_t stencil_M,
-                                                                        const float eps, const float* __restrict__ gout_fd) {
+                                                                        const float eps, const float* __restrict__ gout_fd, float* __restrict__ din_t) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float4* xb = reinterpret_cast<float4*>(smem + M_XB);
     float* w1t = reinterpret_cast<float*>(smem + M_W1T);
@@ -457,6 +460,13 @@ __global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const fl
 #pragma unroll
             for (int q = 0; q < 16; ++q) din[16 + q] = acc[q] * inv_s_d;
         }
+        if constexpr (SPLIT) {
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) din_t[(size_t)q * B + b] = din[q];
+            }
+            continue;
+        }
         // ---- scatter into the table (same arithmetic as kernel_grid_backward, hashencoder.cu:223-308) ----
         const float two_b = 2.0f * bound;
         const float u = (px + bound) / two_b, v = (py + bound) / two_b, w = (pz + bound) / two_b;
@@ -506,13 +516,101 @@ __global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const fl
     if (warp == 0) tc05::tmem_dealloc<512>(tmem_base);
 }
 
+// The table scatter of the split backward: grad_table[corner] += w_corner * din (hashencoder.cu:223-308) for every point and
+// level.  A block takes 256 consecutive points; warp w handles levels 2w and 2w+1 of all of them, 32 consecutive points per
+// instruction (consecutive samples of a ray: the din_t reads are coalesced).  No shared-memory tiles, full occupancy: this
+// kernel is bound by the SM's reduction path to L2 alone, the gather / MMA kernel no longer waits behind it.
+__global__ void __launch_bounds__(256) sdf_scatter_kernel(const int32_t* __restrict__ offsets, float S, uint32_t H, const float* __restrict__ x,
+                                                          uint32_t B, float bound, uint32_t stencil_M, float eps, const float* __restrict__ din_t,
+                                                          float* __restrict__ grad_table) {
+    __shared__ LevelMeta lv[kLevels];
+    if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(offsets, threadIdx.x, S, H, 3);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const float two_b = 2.0f * bound;
+    for (uint32_t base = blockIdx.x * 256u; base < B; base += gridDim.x * 256u) {
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t b = base + it * 32 + lane;            // warp-uniform trip counts: every lane joins the shuffles below
+            bool inr = b < B;
+            float u = 0.f, v = 0.f, w = 0.f;
+            if (inr) {
+                uint32_t blk = 0, smp = b;
+                if (stencil_M) { blk = b / stencil_M; smp = b - blk * stencil_M; }
+                float px = x[3 * (size_t)smp], py = x[3 * (size_t)smp + 1], pz = x[3 * (size_t)smp + 2];
+                if (blk) {
+                    const float e = (blk & 1) ? eps : -eps;
+                    const uint32_t ax = (blk - 1) >> 1;
+                    if (ax == 0) px = clampf(px + e, -bound, bound);
+                    else if (ax == 1) py = clampf(py + e, -bound, bound);
+                    else pz = clampf(pz + e, -bound, bound);
+                }
+                u = (px + bound) / two_b; v = (py + bound) / two_b; w = (pz + bound) / two_b;
+                inr = !((u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f));
+            }
+            if (!__any_sync(full, inr)) continue;
+#pragma unroll 1
+            for (int ll = 0; ll < 2; ++ll) {
+                const int l = 2 * warp + ll;
+                const LevelMeta m = lv[l];
+                float gx = 0.f, gy = 0.f;
+                if (inr) { gx = din_t[(size_t)(2 * l) * B + b]; gy = din_t[(size_t)(2 * l + 1) * B + b]; }
+                float fx = fmaf(u, m.scale, 0.5f), fy = fmaf(v, m.scale, 0.5f), fz = fmaf(w, m.scale, 0.5f);
+                const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+                const uint32_t ix = (uint32_t)flx, iy = (uint32_t)fly, iz = (uint32_t)flz;
+                fx -= flx; fy -= fly; fz -= flz;
+                float val[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float wgt = (((c & 1) ? fx : 1.0f - fx) * ((c & 2) ? fy : 1.0f - fy)) * ((c & 4) ? fz : 1.0f - fz);
+                    val[2 * c] = wgt * gx; val[2 * c + 1] = wgt * gy;
+                }
+                // Lanes are consecutive samples of one ray: those inside the same grid cell are a contiguous run and add into
+                // the same eight corners.  Sum each run in registers (segmented scan) and let its last lane issue the
+                // reductions: one packet per (run, corner) instead of one per (sample, corner).
+                const uint32_t k1 = inr ? (ix | (iy << 16)) : 0xFFFFFFFFu, k2 = inr ? iz : (0x80000000u | (uint32_t)lane);
+                const uint32_t p1 = __shfl_up_sync(full, k1, 1), p2 = __shfl_up_sync(full, k2, 1);
+                const bool head = lane == 0 || k1 != p1 || k2 != p2;
+                const unsigned heads = __ballot_sync(full, head);
+                bool emit = inr;
+                if (heads != full) {
+                    const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+                    emit = inr && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        float a = val[q];
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const float t = __shfl_up_sync(full, a, d);
+                            if (lane - d >= start) a += t;
+                        }
+                        val[q] = a;
+                    }
+                }
+                if (!emit) continue;
+                float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t cx = ix + (c & 1), cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
+                    uint32_t slot;
+                    if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
+                    else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
+                    atomicAdd(dst + slot, make_float2(val[2 * c], val[2 * c + 1]));
+                }
+            }
+        }
+    }
+}
+
 bool use_v1_backward() {
     static const bool v1 = [] { const char* e = getenv("AC_SDF_BWD_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
     return v1;
 }
 
 int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout, uint32_t B, float bound, const float* scales, float* grad_table,
-                        float* grad_w0b, float* grad_w1, uint32_t stencil_M, float eps, const float* gout_fd, cudaStream_t st) {
+                        float* grad_w0b, float* grad_w1, uint32_t stencil_M, float eps, const float* gout_fd, cudaStream_t st,
+                        void* workspace = nullptr, uint64_t workspace_bytes = 0) {
     const float2* table = reinterpret_cast<const float2*>(m->embeddings);
     if (use_v1_backward()) {
         ACB_SET_MAX_SMEM(sdf_backward_tc_kernel, T_TOTAL);
@@ -521,11 +619,25 @@ int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout
         sdf_backward_tc_kernel<<<grid, kThreadsT, T_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, gout, B,
                                                                  bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd);
     } else {
-        ACB_SET_MAX_SMEM(sdf_backward_mma_kernel, M_TOTAL);
         const uint32_t want = (B + kThreadsB - 1) / kThreadsB;
         const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
-        sdf_backward_mma_kernel<<<grid, kThreadsB, M_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, gout, B,
-                                                                  bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd);
+        if (workspace && workspace_bytes >= (uint64_t)B * 32u * sizeof(float)) {
+            // split: gather + MMA kernel writes dL/d(features) to the workspace, a full-occupancy kernel scatters it
+            float* din_t = reinterpret_cast<float*>(workspace);
+            ACB_SET_MAX_SMEM(sdf_backward_mma_kernel<true>, M_TOTAL);
+            sdf_backward_mma_kernel<true><<<grid, kThreadsB, M_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x,
+                                                                            gout, B, bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd,
+                                                                            din_t);
+            if (int rc = acb::launched()) return rc;
+            const uint32_t blocks = (B + 255u) / 256u, cap = (uint32_t)acb::sm_count() * 8u;
+            sdf_scatter_kernel<<<blocks < cap ? blocks : cap, 256, 0, st>>>(m->offsets, m->log2_per_level_scale, m->base_resolution, x, B, bound, stencil_M,
+                                                                           eps, din_t, grad_table);
+            return acb::launched();
+        }
+        ACB_SET_MAX_SMEM(sdf_backward_mma_kernel<false>, M_TOTAL);
+        sdf_backward_mma_kernel<false><<<grid, kThreadsB, M_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x,
+                                                                         gout, B, bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd,
+                                                                         nullptr);
     }
     return acb::launched();
 }
@@ -548,4 +660,27 @@ extern "C" int ac_nsr_sdf_backward_stencil(const ac_nsr_model* m, const float* P
     if (!(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
     if (M == 0) return AC_OK;
     return launch_sdf_backward(m, P, grad_centre, 7u * M, bound, scales, grad_table, grad_w0b, grad_w1, M, eps, grad_fd, (cudaStream_t)stream);
+}
+
+extern "C" uint64_t ac_nsr_sdf_backward_workspace_bytes(uint32_t n_points) { return (uint64_t)n_points * 32u * sizeof(float); }
+
+extern "C" int ac_nsr_sdf_backward_fused_ws(const ac_nsr_model* m, const float* x, const float* grad_out, uint32_t B, float bound, const float* scales,
+                                            float* grad_table, float* grad_w0b, float* grad_w1, void* workspace, uint64_t workspace_bytes,
+                                            void* stream) {
+    if (!m || !m->embeddings || !m->offsets || !m->mlp_blob || !x || !grad_out || !scales || !grad_table || !grad_w0b || !grad_w1)
+        return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    return launch_sdf_backward(m, x, grad_out, B, bound, scales, grad_table, grad_w0b, grad_w1, 0u, 0.f, nullptr, (cudaStream_t)stream, workspace,
+                               workspace_bytes);
+}
+
+extern "C" int ac_nsr_sdf_backward_stencil_ws(const ac_nsr_model* m, const float* P, uint32_t M, float bound, float eps, const float* grad_centre,
+                                              const float* grad_fd, const float* scales, float* grad_table, float* grad_w0b, float* grad_w1,
+                                              void* workspace, uint64_t workspace_bytes, void* stream) {
+    if (!m || !m->embeddings || !m->offsets || !m->mlp_blob || !P || !grad_centre || !grad_fd || !scales || !grad_table || !grad_w0b || !grad_w1)
+        return AC_E_INVALID_ARG;
+    if (!(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
+    if (M == 0) return AC_OK;
+    return launch_sdf_backward(m, P, grad_centre, 7u * M, bound, scales, grad_table, grad_w0b, grad_w1, M, eps, grad_fd, (cudaStream_t)stream, workspace,
+                               workspace_bytes);
 }

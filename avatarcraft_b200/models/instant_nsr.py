@@ -78,13 +78,23 @@ class _SdfQuery(torch.autograd.Function):
             # by 1e5); they are device scalars, so nothing synchronises.
             scales = _fp16_scales(gout.abs().amax(), net)
             acc0 = torch.zeros(64, 36, **f32); acc1 = torch.zeros(16, 64, **f32)
-            _lib.check(_lib.lib().ac_nsr_sdf_backward_fused(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound, _lib.ptr(scales),
-                                                            _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.stream_ptr()),
-                       "ac_nsr_sdf_backward_fused")
+            ws = _backward_workspace(net, B, dev)
+            _lib.check(_lib.lib().ac_nsr_sdf_backward_fused_ws(ctypes.byref(m), _lib.ptr(x), _lib.ptr(gout), B, ctx.bound, _lib.ptr(scales),
+                                                               _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.ptr(ws), ws.numel(),
+                                                               _lib.stream_ptr()), "ac_nsr_sdf_backward_fused_ws")
             gw0b = acc0 / scales[0]
             gw1 = acc1 / scales[1]
         gw0, gb0 = gw0b[:, :35].contiguous(), gw0b[:, 35].contiguous()
         return None, grad_table, gw0, gb0, gw1, gout.sum(0), None, None
+
+
+def _backward_workspace(net, n_points, dev):
+    """Scratch of the split SDF backward (d loss / d features of every point, [32, n_points] fp32), kept on the model."""
+    need = int(_lib.lib().ac_nsr_sdf_backward_workspace_bytes(int(n_points)))
+    ws = getattr(net, "_sdf_bwd_ws", None)
+    if ws is None or ws.numel() < need or ws.device != dev:
+        ws = net._sdf_bwd_ws = torch.empty(need, device=dev, dtype=torch.uint8)
+    return ws
 
 
 def _fp16_scales(gmax, net):
@@ -128,9 +138,10 @@ class _SdfStencil(torch.autograd.Function):
         scales = _fp16_scales(torch.maximum(g_centre.abs().amax(), g_fd.abs().amax()), net)
         acc0 = torch.zeros(64, 36, **f32); acc1 = torch.zeros(16, 64, **f32)
         m = net._device_model()
-        _lib.check(_lib.lib().ac_nsr_sdf_backward_stencil(ctypes.byref(m), _lib.ptr(P), M, ctx.bound, ctx.eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
-                                                          _lib.ptr(scales), _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.stream_ptr()),
-                   "ac_nsr_sdf_backward_stencil")
+        ws = _backward_workspace(net, 7 * M, dev)
+        _lib.check(_lib.lib().ac_nsr_sdf_backward_stencil_ws(ctypes.byref(m), _lib.ptr(P), M, ctx.bound, ctx.eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
+                                                             _lib.ptr(scales), _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.ptr(ws),
+                                                             ws.numel(), _lib.stream_ptr()), "ac_nsr_sdf_backward_stencil_ws")
         gw0b = acc0 / scales[0]
         gw1 = acc1 / scales[1]
         gb1 = g_centre.sum(0)

@@ -132,18 +132,38 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
         if len(patches) > st.opacity.numel():
             st.opacity = torch.zeros(len(patches), device=dev, dtype=torch.float32)
         _lib.check(L.ac_zero(_lib.ptr(st.opacity), st.opacity.numel() * 4, sp()), "ac_zero")
+    # Everything that does not depend on the pixel gradient or on the patch order is done ONCE for all of this rank's rays: the
+    # parameters only change at optimizer.step(), so the sampled depths of every patch (and the frozen net's opacities) are
+    # the same whether computed patch by patch (the reference, stylize.py:153-181) or in one launch -- and a 4096-ray
+    # sampling launch is latency bound (one ray per warp), 16 of them cost 8x one 65 536-ray launch.
+    if len(patches) == 1:
+        idx = None
+        o_all, d_all = rays_o[patches[0][0]:patches[0][1]].float().contiguous(), rays_d[patches[0][0]:patches[0][1]].float().contiguous()
+    else:
+        idx = torch.cat([torch.arange(s, e, device=dev) for s, e, _ in patches]) if world > 1 else None
+        o_all = (rays_o if idx is None else rays_o[idx]).float().contiguous()
+        d_all = (rays_d if idx is None else rays_d[idx]).float().contiguous()
+    n_all = o_all.shape[0]
+    if jitter is not None:
+        first = patches[0][0] if len(patches) == 1 else 0
+        jit_all = (jitter[first:first + n_all] if idx is None else jitter[idx]).float().contiguous()
+    else:
+        jit_all = torch.empty(n_all, num_steps, device=dev, dtype=torch.float32)
+        # keyed by a draw from torch's CPU generator: reproducible under torch.manual_seed, restored by a resume
+        # (utils/checkpoint.py saves the generator state), and no device work or synchronisation
+        seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) + rank * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF
+        _lib.check(L.ac_fill_uniform(_lib.ptr(jit_all), n_all * num_steps, seed, sp()), "ac_fill_uniform")
+    z_all = net_style._sample_depths(o_all, d_all, num_steps, upsample_steps, bound, jit_all)
+    wsum_gt_all = None
+    if use_opacity and net_gt is not None:
+        with torch.no_grad():
+            wsum_gt_all = net_gt.run(o_all[None], d_all[None], num_steps, bound, upsample_steps, None, 1.0, 0.0, per_sample_outputs=False)[2].reshape(-1)
+    at = 0
     for ip, (s, e, scale) in enumerate(patches):
-        o, d = rays_o[s:e].float().contiguous(), rays_d[s:e].float().contiguous()
         m = e - s
-        if jitter is not None:
-            jit = jitter[s:e].float().contiguous()
-        else:
-            jit = torch.empty(m, num_steps, device=dev, dtype=torch.float32)
-            # keyed by a draw from torch's CPU generator: reproducible under torch.manual_seed, restored by a resume
-            # (utils/checkpoint.py saves the generator state), and no device work or synchronisation
-            seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) + rank * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF
-            _lib.check(L.ac_fill_uniform(_lib.ptr(jit), m * num_steps, seed, sp()), "ac_fill_uniform")
-        z = net_style._sample_depths(o, d, num_steps, upsample_steps, bound, jit)
+        o, d, z = o_all[at:at + m], d_all[at:at + m], z_all[at:at + m]
+        wsum_gt = None if wsum_gt_all is None else wsum_gt_all[at:at + m]
+        at += m
         P = net_style._section_points(o, d, z, bound)
         Mp = P.shape[0]
         centre = torch.empty(Mp, 16, device=dev, dtype=torch.float32)
@@ -153,10 +173,6 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
                    "ac_nsr_forward_sdf_stencil")
         bg = None if bkg_key % 4 == WHITE_BKG else torch.zeros(m, 3, device=dev)
         bufs = M._shade_forward(net_style, o, d, z, P, centre, fd, bg, num_steps, bound, eps, car)
-        wsum_gt = None
-        if use_opacity and net_gt is not None:
-            with torch.no_grad():
-                wsum_gt = net_gt.run(o[None], d[None], num_steps, bound, upsample_steps, None, 1.0, 0.0, per_sample_outputs=False)[2]
         g_eik = None
         if w_eikonal > 0.0:
             if scale != 1.0:        # a split patch: this rank's share of the masked mean (one scalar all-reduce)
@@ -180,9 +196,10 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
                    "ac_nsr_sdf_backward_scales")
         _lib.check(L.ac_zero(_lib.ptr(st.acc), st.acc.numel() * 4, sp()), "ac_zero")
         acc0, acc1 = st.acc[:64 * 36], st.acc[64 * 36:]
-        _lib.check(L.ac_nsr_sdf_backward_stencil(ctypes.byref(model), _lib.ptr(P), Mp, bound, eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
-                                                 _lib.ptr(st.scales), _lib.ptr(G["encoder.embeddings"]), _lib.ptr(acc0), _lib.ptr(acc1), sp()),
-                   "ac_nsr_sdf_backward_stencil")
+        ws = M._backward_workspace(net_style, 7 * Mp, dev)
+        _lib.check(L.ac_nsr_sdf_backward_stencil_ws(ctypes.byref(model), _lib.ptr(P), Mp, bound, eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
+                                                    _lib.ptr(st.scales), _lib.ptr(G["encoder.embeddings"]), _lib.ptr(acc0), _lib.ptr(acc1),
+                                                    _lib.ptr(ws), ws.numel(), sp()), "ac_nsr_sdf_backward_stencil_ws")
         sdf, col, P_ = net_style.sdf_net, net_style.color_net, _lib.ptr
         s0, s1 = st.scales[0:1], st.scales[1:2]
 

@@ -133,6 +133,17 @@ int ac_nsr_forward_sdf_stencil(const ac_nsr_model *model, const float *P, uint32
 int ac_nsr_sdf_backward_stencil(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
                                 const float *grad_centre, const float *grad_fd, const float *scales, float *grad_table,
                                 float *grad_w0b, float *grad_w1, void *stream);
+/* The same two backward entry points with a caller-provided workspace of ac_nsr_sdf_backward_workspace_bytes(points) bytes
+ * (points = B, or 7 M for the stencil): the work is then split into a gather + tensor-core kernel that leaves d loss /
+ * d(features) of every point in the workspace and a full-occupancy kernel that scatters it into grad_table -- faster than the
+ * fused kernel, whose reductions and gathers wait on each other.  workspace = NULL (or too small) runs the fused kernel. */
+uint64_t ac_nsr_sdf_backward_workspace_bytes(uint32_t n_points);
+int ac_nsr_sdf_backward_fused_ws(const ac_nsr_model *model, const float *x, const float *grad_out, uint32_t B, float bound,
+                                 const float *scales, float *grad_table, float *grad_w0b, float *grad_w1, void *workspace,
+                                 uint64_t workspace_bytes, void *stream);
+int ac_nsr_sdf_backward_stencil_ws(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
+                                   const float *grad_centre, const float *grad_fd, const float *scales, float *grad_table,
+                                   float *grad_w0b, float *grad_w1, void *workspace, uint64_t workspace_bytes, void *stream);
 /* --------------------------------------------------------------------------------------
  * The differentiable half of NeRFRenderer.run on the training path, after the SDF stencil
  * (models/instant_nsr.py:210-299; driven by stylize.py:153-193): finite-difference normal, colour MLP, NeuS alpha,
