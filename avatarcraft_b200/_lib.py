@@ -161,6 +161,7 @@ _SIGNATURES = {
     "ac_sd_transpose_f16": (_I, [_V, _I, _I, _I64, _V, _I64, _V]),
     "ac_sd_conv_s2_dgrad_operand_f16": (_I, [_V, _I, _I, _I, _I, _I, _I, _V, _V]),
     "ac_nsr_debug_tc_layer": (_I, [_V, _V, _V, _V]),
+    "ac_nsr_upsample_round": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V]),
     "ac_nsr_debug_upsample": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V, _V, _V, _V, _V]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

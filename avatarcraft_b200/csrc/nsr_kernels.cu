@@ -626,4 +626,12 @@ int ac_nsr_debug_upsample(const float* rays_o, const float* rays_d, const float*
     return acb::launched();
 }
 
+// One importance round as a stage-level operator (NeRFRenderer.up_sample + cat_z_vals, models/instant_nsr.py:410-475) for callers
+// that evaluate the signed distance between rounds themselves -- the warped (render_can=False) path, whose coarse points go
+// through the SMPL warp first (:166-172).  Same kernel as the parity-test entry above, computed section alphas.
+int ac_nsr_upsample_round(const float* rays_o, const float* rays_d, const float* z, const float* sdf, uint32_t n_rays, uint32_t T, float inv_s,
+                          float* z_new, int32_t* bins, float* z_out, int32_t* order, void* stream) {
+    return ac_nsr_debug_upsample(rays_o, rays_d, z, sdf, n_rays, T, inv_s, nullptr, nullptr, z_new, bins, z_out, order, stream);
+}
+
 }  // extern "C"

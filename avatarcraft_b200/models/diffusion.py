@@ -106,9 +106,9 @@ class StableDiffusion(nn.Module):
         self.min_step = int(self.num_train_timesteps * 0.02)
         self.max_step = int(self.num_train_timesteps * 0.98)
         self.use_depth = version == "2.0"
-        if version not in ("1.5", "2.0"):
-            raise ValueError("sd_version must be '1.5' or '2.0' (models/diffusion.py:45-49)")
-        cfg = unet_config or (UNetConfig.sd2_depth() if self.use_depth else UNetConfig.sd15())
+        if version not in ("1.5", "2.0", "2.1"):
+            raise ValueError("sd_version must be '1.5' or '2.0' (models/diffusion.py:45-49), or '2.1' (BASELINE config 5)")
+        cfg = unet_config or (UNetConfig.sd2_depth() if self.use_depth else UNetConfig.sd21() if version == "2.1" else UNetConfig.sd15())
         on_cuda = self.device.type == "cuda"
         # modules are created (and randomly initialised) directly on the target device: 0.94 G parameters take seconds
         # on the GPU and most of a minute on the host; the seed makes the random networks identical on every rank

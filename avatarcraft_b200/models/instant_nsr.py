@@ -391,8 +391,8 @@ class NeRFRenderer(nn.Module):
             for i in range(rounds):
                 z_new = torch.empty(n, 16, device=dev); bins = torch.empty(n, 16, 2, dtype=torch.int32, device=dev)
                 z_out = torch.empty(n, T + 16, device=dev); order = torch.empty(n, T + 16, dtype=torch.int32, device=dev)
-                _lib.check(L.ac_nsr_debug_upsample(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), _lib.ptr(sdf), n, T, float(64 * 2 ** i),
-                                                   None, None, _lib.ptr(z_new), _lib.ptr(bins), _lib.ptr(z_out), _lib.ptr(order),
+                _lib.check(L.ac_nsr_upsample_round(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), _lib.ptr(sdf), n, T, float(64 * 2 ** i),
+                                                   _lib.ptr(z_new), _lib.ptr(bins), _lib.ptr(z_out), _lib.ptr(order),
                                                    _lib.stream_ptr()), "ac_nsr_upsample_round")
                 if i + 1 < rounds:
                     p_new = (o[:, None] + d[:, None] * z_new[..., None]).clamp(-bound, bound)        # un-warped (:464-465)

@@ -38,6 +38,11 @@ class UNetConfig:
         return UNetConfig(in_channels=5, cross_attention_dim=1024, attention_head_dim=(5, 10, 20, 20), use_linear_projection=True)
 
     @staticmethod
+    def sd21():
+        """Stable Diffusion 2.1 (base and v-pred share it): OpenCLIP-H text width 1024, 64-wide heads, linear projections."""
+        return UNetConfig(in_channels=4, cross_attention_dim=1024, attention_head_dim=(5, 10, 20, 20), use_linear_projection=True)
+
+    @staticmethod
     def tiny():
         return UNetConfig(block_out_channels=(32, 64, 64, 64), cross_attention_dim=48, attention_head_dim=(2, 2, 4, 4), norm_num_groups=8)
 

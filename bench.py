@@ -269,6 +269,11 @@ def run_ours(args):
         sds["coarse_stage_nerf_side_only"] = {k: c[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "phases_ms")}
         if world == 1:
             sds["reference_gpu_path"] = measure_reference_gpu(dev)            # the reference's own model code + CUDA kernel on this GPU
+        try:
+            c5 = measure_train(4, 4, world, rank, dev, sd_guidance=True, config5=True)    # BASELINE.json configs[4]: one step per camera box
+            sds["config5_512_multibbox_sd21"] = {k: c5[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "phases_ms", "config")}
+        except Exception as e:
+            sds["config5_512_multibbox_sd21"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     except Exception as e:           # never lose the headline line to the secondary workload
         sds = {"metric": "sds_style_steps_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
     torch.set_grad_enabled(False)
@@ -323,7 +328,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=False):
+BBOXES = {"body": dict(center=(0.0, 0.0, 0.0), dist=1.7), "head": dict(center=(0.0, 0.45, 0.0), dist=0.6),
+          "upper": dict(center=(0.0, 0.2, 0.0), dist=1.0), "lower": dict(center=(0.0, -0.35, 0.0), dist=1.0)}
+
+
+def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=False, config5=False):
     """Secondary workload (BASELINE.json configs[2]): one stylisation optimiser step of stylize.py on a 256x256 view =
     65 536 rays = 16 patches of batch_size 4096 (or, `coarse`, the stride-4 sub-sampled view = one patch):
     pass 1 no-grad render (ray-sharded + one all-gather), the pixel gradient, pass 2 patch re-renders with gradients +
@@ -351,16 +360,22 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
     side = 64 if coarse else 256
     if coarse:            # coarse stage of stylize.py: the 256x256 view sub-sampled with stride 4 = ONE 4096-ray patch
         o, d = o.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3), d.reshape(256, 256, 3)[::4, ::4].reshape(-1, 3)
+    views = None
+    if config5:           # BASELINE.json configs[4]: 512x512 views of four camera boxes, cycled step by step; SD-2.1-shaped UNet
+        side = 512
+        views = [tuple(t.contiguous().to(dev) for t in syn.pinhole_rays(syn.orbit_pose(30.0 + 90.0 * i, **bb), 512, 512))
+                 for i, bb in enumerate(BBOXES.values())]
+        o, d = views[0]
     o, d = o.contiguous().to(dev), d.contiguous().to(dev)      # fine stage (BASELINE.json configs[2]): 65 536 rays = 16 patches of 4096
     G = torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(44)).to(dev)
     torch.manual_seed(1000 + rank)
     sd = emb = None
     if sd_guidance:       # the real guidance: SD-1.5-shaped UNet (native tcgen05 forward) + VAE encoder with gradient, random weights
         from avatarcraft_b200.models.diffusion import StableDiffusion
-        sd = StableDiffusion(dev, "1.5")
+        sd = StableDiffusion(dev, "2.1" if config5 else "1.5")
         sd.cfg_parallel = world > 1          # every rank seeds the step identically (pixel_gradient(seed=...)): the CFG pair may be split
         emb = sd.get_text_embeds("a 3D rendering of a knight in bronze armour")
-    count = [0]
+    count = [0, 0]
     events = []
 
     def mark(name):
@@ -370,6 +385,12 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
     from avatarcraft_b200.utils.train_utils import native_patch_step
 
     def step():
+        nonlocal o, d, G
+        if views is not None:
+            o, d = views[count[1] % len(views)]
+            count[1] += 1
+            if G.shape[0] != o.shape[0]:
+                G = torch.randn(o.shape[0], 3, generator=torch.Generator().manual_seed(44)).to(dev)
         mark("start")
         with torch.no_grad():                                                                            # pass 1, ray-sharded + one all-gather
             rgb = render_rays_sharded(lambda a, b: render_instantnsr_naive(net, a, b, rays_per_batch=4096, render_can=True, perturb=True)[0],
@@ -405,10 +426,12 @@ def measure_train(steps, warmup, world, rank, dev, sd_guidance=False, coarse=Fal
             "steps": steps, "warmup": max(warmup, 3), "ms_per_step": float(ms) / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("stylize.py coarse-stage step: 4096 rays (256x256 stride 4)" if coarse else
+                                    "multi-bbox stylize step on a 512x512 view (4 camera boxes body/head/upper/lower cycled): 262 144 rays = 64 patches "
+                                    "of batch_size 4096, SD-2.1-shaped fp16 UNet, guidance at 512x512 without resize" if config5 else
                                     "stylize.py step on a 256x256 view: 65 536 rays = 16 patches of batch_size 4096") + ", 64+64 samples, pass1 + pass2 "
                                    "(grad, eikonal 0.01, opacity vs frozen copy) + grad all-reduce + Adam; pixel gradient " +
-                                   ("from the SDS guidance: SD-1.5-shaped UNet (859.5 M params, random init, native tcgen05 forward on the "
-                                    "(uncond, text) pair) + VAE encoder forward/backward at 512x512" if sd_guidance else "randn seed 44 (guidance excluded)"),
+                                   ("from the SDS guidance: SD-" + ("2.1" if config5 else "1.5") + "-shaped UNet (random init, native tcgen05 forward on the "
+                                    "(uncond, text) pair, fp16 operands) + native VAE encoder forward/backward at 512x512" if sd_guidance else "randn seed 44 (guidance excluded)"),
                        "parallelism": f"pass 1 ray-sharded + all-gather, pass 2 patch-sharded x{world}, one 49 MB gradient all-reduce, "
                                       "SD guidance: classifier-free pair split over ranks, VAE replicated"},
             "gpu_launches": int(_lib.lib().ac_launch_count() - l0)}

@@ -267,6 +267,10 @@ int ac_nsr_render(const ac_nsr_model *model, const ac_nsr_render_args *args, voi
 int ac_nsr_debug_upsample(const float *rays_o, const float *rays_d, const float *z, const float *sdf,
                           uint32_t n_rays, uint32_t T, float inv_s, const float *alpha_in, float *alpha_out,
                           float *z_new, int32_t *bins, float *z_out, int32_t *order, void *stream);
+/* The same round as a product operator (up_sample + cat_z_vals, models/instant_nsr.py:410-475) for the warped path, whose
+ * signed distances between rounds come from warped / un-warped points evaluated by the caller (:166-172, :464-469). */
+int ac_nsr_upsample_round(const float *rays_o, const float *rays_d, const float *z, const float *sdf, uint32_t n_rays,
+                          uint32_t T, float inv_s, float *z_new, int32_t *bins, float *z_out, int32_t *order, void *stream);
 
 /* --------------------------------------------------------------------------------------
  * SMPL-guided inverse warp (utils/ray_utils.py).
