@@ -74,7 +74,8 @@ class NsrRenderArgs(ctypes.Structure):
                 ("normal", ctypes.c_void_p),
                 ("weights", ctypes.c_void_p), ("pts_color", ctypes.c_void_p), ("pts_alpha", ctypes.c_void_p),
                 ("z_vals", ctypes.c_void_p),
-                ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64)]
+                ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64),
+                ("c0_ray_bias", ctypes.c_void_p)]
 
 
 class NsrShadeArgs(ctypes.Structure):
@@ -127,6 +128,8 @@ _SIGNATURES = {
     "ac_nsr_section_points": (_I, [_V, _V, _V, _U32, _U32, _F, _V, _V]),
     "ac_nsr_weight_norm_backward": (_I, [ctypes.POINTER(WeightNormLayer), _U32, _V]),
     "ac_nsr_forward_color": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _U32, _V]),
+    "ac_nsr_forward_color_bias": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _V, _U32, _V]),
+    "ac_nsr_viewdir_bias": (_I, [_V, _V, _U32, _V, _V]),
     "ac_nsr_fd_gradient": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _F, _V]),
     "ac_nsr_render_workspace_bytes": (ctypes.c_uint64, [_U32]),
     "ac_nsr_render": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrRenderArgs), _V]),

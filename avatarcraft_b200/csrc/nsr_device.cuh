@@ -307,12 +307,14 @@ __device__ __forceinline__ void sdf_point(const float2* __restrict__ table, cons
 }
 
 // Colour MLP 21 -> 64 (relu) -> 64 (relu) -> 3 (sigmoid) (models/instant_nsr.py:644-663).
-__device__ __forceinline__ void color_mlp(const float* __restrict__ sw, const float (&in)[kColInPad], float (&rgb)[3]) {
+// bias0: optional [64] added to layer 0's pre-activation (use_viewdirs: the SH-encoded direction's contribution).
+__device__ __forceinline__ void color_mlp(const float* __restrict__ sw, const float (&in)[kColInPad], float (&rgb)[3],
+                                          const float* __restrict__ bias0 = nullptr) {
     float h1[kHidden];
 #pragma unroll
     for (int j = 0; j < kHidden; ++j) {
         const float4* __restrict__ wr = reinterpret_cast<const float4*>(sw + OFF_C0 + j * kColInPad);
-        float a = 0.f;
+        float a = bias0 ? bias0[j] : 0.f;
 #pragma unroll
         for (int q = 0; q < kColInPad / 4; ++q) {
             const float4 w4 = wr[q];

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) fd_gradient_kernel(const float2* __restri
 
 __global__ void __launch_bounds__(256) forward_color_kernel(const float* __restrict__ blob, const float* __restrict__ x,
                                                             const float* __restrict__ n, const float* __restrict__ feat,
-                                                            float* __restrict__ rgb, uint32_t B) {
+                                                            float* __restrict__ rgb, uint32_t B, const float* __restrict__ bias0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sw = reinterpret_cast<float*>(smem_raw);
     const float4* src = reinterpret_cast<const float4*>(blob);
@@ -311,8 +311,24 @@ __global__ void __launch_bounds__(256) forward_color_kernel(const float* __restr
     for (int q = 0; q < 3; ++q) { cin[q] = x[3 * (size_t)b + q]; cin[3 + q] = n[3 * (size_t)b + q]; cin[21 + q] = 0.f; }
 #pragma unroll
     for (int q = 0; q < 15; ++q) cin[6 + q] = feat[15 * (size_t)b + q];
-    color_mlp(sw, cin, c);
+    color_mlp(sw, cin, c, bias0 ? bias0 + 64 * (size_t)b : nullptr);
     rgb[3 * (size_t)b] = c[0]; rgb[3 * (size_t)b + 1] = c[1]; rgb[3 * (size_t)b + 2] = c[2];
+}
+
+// out [n,64] = sh [n,16] w_sh[64,16]^T: the ray direction's contribution to colour layer 0 (use_viewdirs).
+__global__ void __launch_bounds__(256) viewdir_bias_kernel(const float* __restrict__ sh, const float* __restrict__ w_sh, uint32_t n,
+                                                           float* __restrict__ out) {
+    __shared__ float w[64 * 16];
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) w[i] = w_sh[i];
+    __syncthreads();
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * 64) return;
+    const size_t ray = t >> 6;
+    const int j = (int)(t & 63);
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a = fmaf(w[j * 16 + k], sh[ray * 16 + k], a);
+    out[t] = a;
 }
 
 
@@ -573,7 +589,23 @@ int ac_nsr_forward_color(const ac_nsr_model* m, const float* x, const float* nor
     if (!m || !m->mlp_blob || !x || !normal || !geo_feat || !rgb) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
     forward_color_kernel<<<(B + 255) / 256, 256, BLOB_FLOATS * sizeof(float), (cudaStream_t)stream>>>(
-        m->mlp_blob, x, normal, geo_feat, rgb, B);
+        m->mlp_blob, x, normal, geo_feat, rgb, B, nullptr);
+    return acb::launched();
+}
+
+int ac_nsr_forward_color_bias(const ac_nsr_model* m, const float* x, const float* normal, const float* geo_feat, const float* c0_bias, float* rgb,
+                              uint32_t B, void* stream) {
+    if (!m || !m->mlp_blob || !x || !normal || !geo_feat || !c0_bias || !rgb) return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    forward_color_kernel<<<(B + 255) / 256, 256, BLOB_FLOATS * sizeof(float), (cudaStream_t)stream>>>(
+        m->mlp_blob, x, normal, geo_feat, rgb, B, c0_bias);
+    return acb::launched();
+}
+
+int ac_nsr_viewdir_bias(const float* sh, const float* w_sh, uint32_t n, float* out, void* stream) {
+    if (!sh || !w_sh || !out) return AC_E_INVALID_ARG;
+    if (n == 0) return AC_OK;
+    viewdir_bias_kernel<<<(unsigned)(((size_t)n * 64 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sh, w_sh, n, out);
     return acb::launched();
 }
 
@@ -598,7 +630,7 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
         eikonal_reduce_kernel<<<(a->n_rays + seg - 1) / seg, 1024, 0, st>>>(reinterpret_cast<float*>(a->workspace), a->n_rays, seg, a->eikonal);
         return acb::launched();
     }
-    if (a->z_in || a->pts_in || a->near_far_in || sample_only) return AC_E_UNSUPPORTED;   // staged inputs / sampling-only: tensor-core kernel only
+    if (a->z_in || a->pts_in || a->near_far_in || sample_only || a->c0_ray_bias) return AC_E_UNSUPPORTED;   // staged inputs / sampling-only / view directions: tensor-core kernel only
     RenderParams p;
     p.table = reinterpret_cast<const float2*>(m->embeddings);
     p.offsets = m->offsets; p.blob = m->mlp_blob; p.variance = m->variance;

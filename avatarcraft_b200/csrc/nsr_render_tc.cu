@@ -163,13 +163,19 @@ __device__ __forceinline__ void group_sdf_eval(Group& g, const float2* __restric
 
 // Colour MLP 21 -> 64 -> 64 -> 3 (models/instant_nsr.py:644-663) for the group's 128 samples, after layer 0's MMA has
 // been committed: relu -> layer 1 (fp16 activations x (hi, lo) weights) -> relu -> 64 -> 3 head -> sigmoid.
-template <int SLOT>
-__device__ __forceinline__ void group_color_rest(Group& g, float (&rgb)[3]) {
+// VIEW: use_viewdirs=True (:564-569,646-650) -- the 16 SH coefficients of the ray direction enter layer 0 as a per-RAY bias
+// bias[64] = C0[:, sh columns] sh(d) (the direction is the same for every sample of a ray), added before the relu.
+template <int SLOT, bool VIEW = false>
+__device__ __forceinline__ void group_color_rest(Group& g, float (&rgb)[3], const float* __restrict__ bias = nullptr) {
     // relu -> fp16 -> A tile of layer 1 (K = 64 = 8 chunks, fills the whole 16 KB region)
 #pragma unroll
     for (int qtr = 0; qtr < 4; ++qtr) {
         float acc[16];
         tc05::tmem_ld16(g.tmem + qtr * 16, acc);
+        if constexpr (VIEW) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) acc[jj] += __ldg(bias + qtr * 16 + jj);
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint4 pk;
@@ -207,8 +213,8 @@ __device__ __forceinline__ void group_color_rest(Group& g, float (&rgb)[3]) {
 }
 
 // cin = (x, y, z, nx, ny, nz, 15 geometry features); all 128 threads of the group call it together.
-template <int SLOT>
-__device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24], float (&rgb)[3]) {
+template <int SLOT, bool VIEW = false>
+__device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24], float (&rgb)[3], const float* __restrict__ bias = nullptr) {
     // layer 0: K = 32 (21 inputs + zero pad), fp16x3
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -225,10 +231,10 @@ __device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24
         *reinterpret_cast<uint4*>(g.a + 8192 + c * 2048 + g.row * 16) = lo;
     }
     group_mma_round(g, [&] { issue_k32_x3(g.tmem & 0xFFFFu, g.a_s, g.b_s + B_C0_HI, g.b_s + B_C0_LO); });
-    group_color_rest<SLOT>(g, rgb);
+    group_color_rest<SLOT, VIEW>(g, rgb, bias);
 }
 
-template <int SLOT>
+template <int SLOT, bool VIEW = false>
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const RenderParamsTC p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             cin[21] = cin[22] = cin[23] = 0.f;
             __syncwarp();                                // fd[] consumed before the next block overwrites it
             float col[3];
-            group_color_eval<SLOT>(g, cin, col);
+            group_color_eval<SLOT, VIEW>(g, cin, col, VIEW ? p.a.c0_ray_bias + 64 * (size_t)ray : nullptr);
             const float nx = cin[3], ny = cin[4], nz = cin[5];
             const float cosv = r.dx * nx + r.dy * ny + r.dz * nz;
             const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);
@@ -698,7 +704,7 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
     p.eik_partial = reinterpret_cast<float*>(a->workspace);
     // AC_RENDER_IMPL=tc5: the round-1 kernel (one point per lane, no stencil sharing), kept for A/B tests.
     const char* impl = getenv("AC_RENDER_IMPL");          // read per launch so that one process can compare both kernels
-    const bool use_v5 = !(impl && impl[0] == 's' && impl[1] == 't');      // WIP: the stencil kernel is opt-in (AC_RENDER_IMPL=st) until it is the faster one
+    const bool use_v5 = a->c0_ray_bias || !(impl && impl[0] == 's' && impl[1] == 't');      // WIP: the stencil kernel is opt-in (AC_RENDER_IMPL=st) until it is the faster one
     const uint32_t n_quads = (a->n_rays + 3) / 4;
     const uint32_t sms = (uint32_t)acb::sm_count();
     if (!use_v5) {
@@ -726,11 +732,19 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
     SlotLease lease(m->mlp_blob, st);
     if (lease.rc) return lease.rc;
     const uint32_t grid = n_quads < sms ? n_quads : sms;
+    if (a->c0_ray_bias) {                 // use_viewdirs: separate instantiation, the default kernel's registers are untouched
 #define AC_CALL(S)                                                                \
-    ACB_SET_MAX_SMEM(nsr_render_tc_kernel<S>, SM_TOTAL);                          \
-    nsr_render_tc_kernel<S><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
-    AC_SLOT_SWITCH(lease.slot, AC_CALL)
+    ACB_SET_MAX_SMEM((nsr_render_tc_kernel<S, true>), SM_TOTAL);                  \
+    nsr_render_tc_kernel<S, true><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
+        AC_SLOT_SWITCH(lease.slot, AC_CALL)
 #undef AC_CALL
+    } else {
+#define AC_CALL(S)                                                                \
+    ACB_SET_MAX_SMEM((nsr_render_tc_kernel<S, false>), SM_TOTAL);                 \
+    nsr_render_tc_kernel<S, false><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
+        AC_SLOT_SWITCH(lease.slot, AC_CALL)
+#undef AC_CALL
+    }
     const int rc = acb::launched();
     lease.launched();
     return rc;

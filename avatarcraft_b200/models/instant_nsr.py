@@ -280,6 +280,9 @@ class NeRFRenderer(nn.Module):
             return self._run_warped(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
                                     normal_epsilon_ratio, verts, faces, Ts, use_mesh_guide, per_sample_outputs, eikonal_segment)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if getattr(self, "use_viewdirs", False):
+                raise NotImplementedError("use_viewdirs=True is wired for inference (render_canonical / render_warp); the training kernels "
+                                          "take the reference's only trained configuration, use_viewdirs=False (stylize.py never sets it)")
             # eikonal_segment / per_sample_outputs are inference-launch options; one patch = one mean here
             return self._run_with_grad(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
                                        normal_epsilon_ratio, perturb_overwrite, jitter, z_override)
@@ -317,7 +320,9 @@ class NeRFRenderer(nn.Module):
         L = _lib.lib()
         ws_bytes = int(L.ac_nsr_render_workspace_bytes(n))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        ray_bias = self._viewdir_bias(rays_d) if getattr(self, "use_viewdirs", False) else None
         a = _lib.NsrRenderArgs(
+            c0_ray_bias=None if ray_bias is None else ray_bias.data_ptr(),
             rays_o=rays_o.data_ptr(), rays_d=rays_d.data_ptr(),
             bg_color=None if bg_color is None else bg_color.data_ptr(),
             jitter=None if jitter is None else jitter.data_ptr(),
@@ -474,7 +479,8 @@ class NeRFNetwork(NeRFRenderer):
                  weight_norm=True, cuda_ray=False, include_input=True, curvature_loss=False, use_viewdirs=False):
         super().__init__(cuda_ray, curvature_loss)
         if (encoding not in ("hashgrid", "hash") or num_layers != 2 or hidden_dim != 64 or geo_feat_dim != 15
-                or num_layers_color != 3 or hidden_dim_color != 64 or not weight_norm or not include_input or use_viewdirs):
+                or num_layers_color != 3 or hidden_dim_color != 64 or not weight_norm or not include_input
+                or (use_viewdirs and encoding_dir not in ("sphere_harmonics", "sh"))):
             raise NotImplementedError("the fused kernels are specialised for the reference's only configuration "
                                       "(models/instant_nsr.py:479-519)")
         self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
@@ -497,8 +503,14 @@ class NeRFNetwork(NeRFRenderer):
                     nn.init.constant_(lin.weight[:, 3:], 0.0)
             sdf_net.append(nn.utils.weight_norm(lin))
         self.sdf_net = nn.ModuleList(sdf_net)
+        # use_viewdirs (models/instant_nsr.py:564-569): the SH-encoded ray direction (degree 4 -> 16 coefficients) joins the colour
+        # input between x and the normal.  The direction is constant along a ray, so the fused kernels take its contribution
+        # to layer 0 as a per-ray bias (ac_nsr_viewdir_bias) and keep their 21-column layer-0 tile.
         self.encoder_dir = None
         self.in_dim_color = geo_feat_dim + 6
+        if use_viewdirs:
+            self.encoder_dir, dir_dim = get_encoder(encoding_dir, {"in_dim": 3})
+            self.in_dim_color += dir_dim
         cdims = [self.in_dim_color, hidden_dim_color, hidden_dim_color, 3]
         self.color_net = nn.ModuleList([nn.utils.weight_norm(nn.Linear(cdims[l], cdims[l + 1], bias=False)) for l in range(3)])
         self.deviation_net = SingleVarianceNetwork(0.3)
@@ -521,6 +533,16 @@ class NeRFNetwork(NeRFRenderer):
         if self._blob is None or self._blob.device != emb.device or key != self._blob_key:
             if self._blob is None or self._blob.device != emb.device:
                 self._blob = torch.empty(_lib.MLP_BLOB_FLOATS, device=emb.device, dtype=torch.float32)
+            keep = []
+            if self.use_viewdirs:
+                # fold layer 0 (37 columns: x | 16 SH | normal | features) here, hand the kernel's packer the 21 columns it knows
+                # as (g', v') with g' = |v'| (its own fold then returns v' unchanged) and keep the SH block for the per-ray bias
+                with torch.no_grad():
+                    w = torch._weight_norm(self.color_net[0].weight_v.detach(), self.color_net[0].weight_g.detach(), 0)
+                    w21 = torch.cat([w[:, :3], w[:, 19:]], dim=1).contiguous()
+                    self._c0_sh = w[:, 3:19].contiguous()
+                    keep = [w21.norm(dim=1, keepdim=True).contiguous(), w21]
+                ps = ps[:6] + keep + ps[8:]
             args = [_lib.ptr(p.detach().contiguous()) for p in ps]
             _lib.check(_lib.lib().ac_nsr_pack_mlp(*args, _lib.ptr(self._blob), _lib.stream_ptr()), "ac_nsr_pack_mlp")
             self._blob_key = key
@@ -528,6 +550,17 @@ class NeRFNetwork(NeRFRenderer):
                              mlp_blob=self._blob.data_ptr(), variance=self.deviation_net.variance.data_ptr(),
                              log2_per_level_scale=float(np.log2(self.encoder.per_level_scale)),
                              base_resolution=int(self.encoder.base_resolution))
+
+    def _viewdir_bias(self, dirs):
+        """[n,64] layer-0 contribution of SH(dirs) (use_viewdirs): SH op + one small kernel.  Call after _device_model()."""
+        from ..encoder.shencoder.backend import _backend as sh_backend
+        dirs = dirs.reshape(-1, 3).float().contiguous()
+        n = dirs.shape[0]
+        sh = torch.empty(n, 16, device=dirs.device, dtype=torch.float32)
+        sh_backend.sh_encode_forward(dirs, sh, n, 3, 4, False, sh)
+        out = torch.empty(n, 64, device=dirs.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ac_nsr_viewdir_bias(_lib.ptr(sh), _lib.ptr(self._c0_sh), n, _lib.ptr(out), _lib.stream_ptr()), "ac_nsr_viewdir_bias")
+        return out
 
     # ---- point queries (reference: forward_sdf :627, forward_color :644, density :669, gradient :683) ----
     @torch.no_grad()
@@ -544,6 +577,11 @@ class NeRFNetwork(NeRFRenderer):
         x, n, geo_feat = (t.reshape(-1, t.shape[-1]).float().contiguous() for t in (x, n, geo_feat))
         rgb = torch.empty(x.shape[0], 3, device=x.device, dtype=torch.float32)
         m = self._device_model()
+        if self.use_viewdirs:
+            bias = self._viewdir_bias(d)
+            _lib.check(_lib.lib().ac_nsr_forward_color_bias(ctypes.byref(m), _lib.ptr(x), _lib.ptr(n), _lib.ptr(geo_feat), _lib.ptr(bias),
+                                                            _lib.ptr(rgb), x.shape[0], _lib.stream_ptr()), "ac_nsr_forward_color_bias")
+            return rgb
         _lib.check(_lib.lib().ac_nsr_forward_color(ctypes.byref(m), _lib.ptr(x), _lib.ptr(n), _lib.ptr(geo_feat),
                                                    _lib.ptr(rgb), x.shape[0], _lib.stream_ptr()), "ac_nsr_forward_color")
         return rgb

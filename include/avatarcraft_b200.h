@@ -211,8 +211,11 @@ int ac_zero(void *p, uint64_t bytes, void *stream);
 
 /* NeRFNetwork.forward_color (models/instant_nsr.py:644-663, use_viewdirs=False):
  * x [B,3], normal [B,3], geo_feat [B,15] -> rgb [B,3]. */
+/* ac_nsr_forward_color_bias: the same with a per-point layer-0 bias [B,64] (use_viewdirs, see ac_nsr_viewdir_bias). */
 int ac_nsr_forward_color(const ac_nsr_model *model, const float *x, const float *normal,
                          const float *geo_feat, float *rgb, uint32_t B, void *stream);
+int ac_nsr_forward_color_bias(const ac_nsr_model *model, const float *x, const float *normal, const float *geo_feat,
+                              const float *c0_bias, float *rgb, uint32_t B, void *stream);
 /* NeRFNetwork.gradient / finite_difference_normals_approximator (:683-704): [B,3] -> [B,3]. */
 int ac_nsr_fd_gradient(const ac_nsr_model *model, const float *x, float *grad, uint32_t B, float bound,
                        float epsilon, void *stream);
@@ -252,9 +255,15 @@ typedef struct ac_nsr_render_args {
     float *eikonal;
     void *workspace;
     uint64_t workspace_bytes;
+    /* use_viewdirs=True (models/instant_nsr.py:564-569,646-650): NULL, or [n_rays,64] = the contribution of the ray direction's
+     * 16 SH coefficients to colour layer 0 (ac_nsr_viewdir_bias); the packed model then holds the other 21 columns. */
+    const float *c0_ray_bias;
 } ac_nsr_render_args;
 
 uint64_t ac_nsr_render_workspace_bytes(uint32_t n_rays);
+/* out [n,64] = sh [n,16] w_sh^T, w_sh [64,16] = the SH columns of the (weight-norm folded) colour layer 0; sh from
+ * ac_sh_encode_forward(dirs, degree 4). */
+int ac_nsr_viewdir_bias(const float *sh, const float *w_sh, uint32_t n, float *out, void *stream);
 int ac_nsr_render(const ac_nsr_model *model, const ac_nsr_render_args *args, void *stream);
 
 /* Stage-level entry points used by the parity tests to pin the integer paths with
