@@ -278,6 +278,8 @@ def run_ours(args):
         sds = {"metric": "sds_style_steps_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
     torch.set_grad_enabled(False)
     try:
+        if os.environ.get("AC_BENCH_SKIP_WARP"):
+            raise RuntimeError("skipped (AC_BENCH_SKIP_WARP)")
         warp = measure_warp_frame(max(args.steps // 2, 5), dev, world, rank)   # BASELINE.json configs[3]: animate frame through the warp
     except Exception as e:
         warp = {"metric": "warp_frame_rays_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
