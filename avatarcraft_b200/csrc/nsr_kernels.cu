@@ -564,8 +564,7 @@ int ac_nsr_sdf_backward(const ac_nsr_model* m, const float* x, const float* grad
     if (check_model(m) || !x || !grad_out || !grad_table || !delta_a || !hidden || !feats) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
     constexpr size_t smem = kStageBytes + 64 * 32 * sizeof(float);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sdf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    ACB_SET_MAX_SMEM(sdf_backward_kernel, (int)smem);
     sdf_backward_kernel<<<grid_for(B, 256, 2), 256, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
         m->base_resolution, x, grad_out, B, bound, grad_table, delta_a, hidden, feats);
@@ -576,8 +575,7 @@ int ac_nsr_fd_gradient(const ac_nsr_model* m, const float* x, float* grad, uint3
                        void* stream) {
     if (check_model(m) || !x || !grad) return AC_E_INVALID_ARG;
     if (B == 0) return AC_OK;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fd_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes); attr = true; }
+    ACB_SET_MAX_SMEM(fd_gradient_kernel, (int)kStageBytes);
     fd_gradient_kernel<<<grid_for(B, 256, 4), 256, kStageBytes, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(m->embeddings), m->offsets, m->mlp_blob, m->log2_per_level_scale,
         m->base_resolution, x, grad, B, bound, epsilon);
@@ -638,8 +636,7 @@ int ac_nsr_render(const ac_nsr_model* m, const ac_nsr_render_args* a, void* stre
     p.a = *a;
     p.eik_partial = reinterpret_cast<float*>(a->workspace);
     const size_t smem = kStageBytes + (size_t)kWarps * 4 * kMaxT * sizeof(float);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(nsr_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    ACB_SET_MAX_SMEM(nsr_render_kernel, (int)smem);
     nsr_render_kernel<<<(a->n_rays + kWarps - 1) / kWarps, kWarps * 32, smem, st>>>(p);
     int rc = acb::launched();
     if (rc) return rc;

@@ -359,6 +359,12 @@ struct FlashParams {
     float scale;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {       // 2^x, one MUFU.EX2 (2^-inf = 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int KA>           // 64-wide K atoms covering the head dim (1: d <= 64, 2: d <= 128)
 __global__ void __launch_bounds__(128) sd_flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                             const __grid_constant__ CUtensorMap tmVt, const FlashParams p) {
@@ -414,6 +420,7 @@ __global__ void __launch_bounds__(128) sd_flash_attn_kernel(const __grid_constan
         load_k(0, 0);
     }
     // ---- pass 1: row statistics ----
+    const float s2 = p.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < T; ++j) {
         const int st = j & 1;
@@ -428,19 +435,25 @@ __global__ void __launch_bounds__(128) sd_flash_attn_kernel(const __grid_constan
         __syncwarp();                                     // lane 0 of warp 0 rejoins before the warp-collective TMEM loads
         tc05::fence_after_sync();
         const int ncols = min(128, p.Lk - j * 128);
+        // statistics in the log2 domain: exp(scale s - max) = 2^(s2 s - m), s2 = scale log2(e): one FFMA + one MUFU.EX2 per
+        // score; the column mask only exists in the last (partial) key tile
 #pragma unroll 1
         for (int q = 0; q < 8; ++q) {
             float acc[16];
             tc05::tmem_ld16(tS + trow + q * 16, acc);
             if (q * 16 >= ncols) continue;
-            float cm = -INFINITY;
+            if (q * 16 + 16 > ncols) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) if (q * 16 + c < ncols) cm = fmaxf(cm, acc[c] * p.scale);
-            const float mn = fmaxf(m, cm);
+                for (int c = 0; c < 16; ++c) if (q * 16 + c >= ncols) acc[c] = -INFINITY;
+            }
+            float cm = acc[0];
+#pragma unroll
+            for (int c = 1; c < 16; ++c) cm = fmaxf(cm, acc[c]);
+            const float mn = fmaxf(m, cm * s2);              // scale > 0: the maximum commutes with the scaling
             float add = 0.f;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) if (q * 16 + c < ncols) add += __expf(acc[c] * p.scale - mn);
-            l = l * __expf(m - mn) + add;
+            for (int c = 0; c < 16; ++c) add += ex2_approx(fmaf(acc[c], s2, -mn));
+            l = fmaf(l, ex2_approx(m - mn), add);
             m = mn;
         }
         tc05::fence_before_sync();
@@ -469,7 +482,11 @@ __global__ void __launch_bounds__(128) sd_flash_attn_kernel(const __grid_constan
             tc05::tmem_ld16(tS + trow + q * 16, acc);
             float pr[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) pr[c] = (q * 16 + c < ncols) ? __expf(acc[c] * p.scale - m) * inv_l : 0.f;
+            for (int c = 0; c < 16; ++c) pr[c] = ex2_approx(fmaf(acc[c], s2, -m)) * inv_l;
+            if (q * 16 + 16 > ncols) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (q * 16 + c >= ncols) pr[c] = 0.f;
+            }
             // kv columns q*16 .. q*16+15 -> atom (q >> 2), 16-byte chunks 2*(q & 3), +1 of this row, XOR-swizzled by row % 8
             unsigned char* rowp = sP + (q >> 2) * QK_ATOM + (r >> 3) * 1024 + (r & 7) * 128;
             const int ch = 2 * (q & 3);
@@ -852,8 +869,7 @@ int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float*
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return AC_E_INVALID_ARG;
     if (group_bias && rows_per_group <= 0) return AC_E_INVALID_ARG;
     if ((batch_outer > 1 || batch_inner > 1) && (residual || group_bias)) return AC_E_UNSUPPORTED;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; }
+    ACB_SET_MAX_SMEM(sd_gemm_kernel, GEMM_SMEM);
     GemmParams p;
     p.A = reinterpret_cast<const __half*>(A); p.W = reinterpret_cast<const __half*>(W);
     p.bias = bias; p.group_bias = group_bias; p.residual = residual; p.C = C;
@@ -881,8 +897,7 @@ int ac_sd_gemm_f16(const void* A, const void* W, const float* bias, const float*
         sd_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(p);
         return acb::launched();
     }
-    static bool attr2 = false;
-    if (!attr2) { cudaFuncSetAttribute(sd_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr2 = true; }
+    ACB_SET_MAX_SMEM(sd_gemm_tma_kernel, GEMM_SMEM);
     CUtensorMap tmA, tmW;
     int a_zi, a_zo, w_zi, w_zo;
     if (!make_operand_map(&tmA, A, K, M, lda, batch_inner, sAi, batch_outer, sAo, &a_zi, &a_zo) ||
@@ -942,8 +957,7 @@ int ac_sd_conv3x3_f16(const void* act, const void* W, const float* bias, const f
         int zi, zo;
         if (!make_operand_map(&tmW, W, 9 * C, N, 9LL * C, 1, 0, 1, 0, &zi, &zo)) return AC_E_UNSUPPORTED;
     }
-    static bool attr2 = false;
-    if (!attr2) { cudaFuncSetAttribute(sd_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr2 = true; }
+    ACB_SET_MAX_SMEM(sd_gemm_tma_kernel, GEMM_SMEM);
     sd_gemm_tma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p, 0, 0, 0, 0, ConvGeom{9, C / 64, Wd, H});
     return acb::launched();
 }
@@ -972,12 +986,10 @@ int ac_sd_flash_attention_f16(const void* q, const void* k, const void* vt, void
     dim3 grid((Lq + 127) / 128, heads, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (KA == 1) {
-        static bool a1 = false;
-        if (!a1) { cudaFuncSetAttribute(sd_flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); a1 = true; }
+        ACB_SET_MAX_SMEM(sd_flash_attn_kernel<1>, 227 * 1024);
         sd_flash_attn_kernel<1><<<grid, 128, smem, st>>>(tmQ, tmK, tmV, p);
     } else {
-        static bool a2 = false;
-        if (!a2) { cudaFuncSetAttribute(sd_flash_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); a2 = true; }
+        ACB_SET_MAX_SMEM(sd_flash_attn_kernel<2>, 227 * 1024);
         sd_flash_attn_kernel<2><<<grid, 128, smem, st>>>(tmQ, tmK, tmV, p);
     }
     return acb::launched();
