@@ -118,7 +118,9 @@ _SIGNATURES = {
     "ac_nsr_sdf_backward_stencil": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V, _V, _V, _V, _V]),
     "ac_nsr_sdf_backward_workspace_bytes": (ctypes.c_uint64, [_U32]),
     "ac_nsr_sdf_backward_fused_ws": (_I, [ctypes.POINTER(NsrModel), _V, _V, _U32, _F, _V, _V, _V, _V, _V, ctypes.c_uint64, _V]),
-    "ac_nsr_sdf_backward_stencil_ws": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V, _V, _V, _V, _V, ctypes.c_uint64, _V]),
+    "ac_nsr_sdf_backward_stencil_ws": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V, _V, _V, _V, _V, ctypes.c_uint64, _V, _V]),
+    "ac_nsr_sdf_feature_cache_bytes": (ctypes.c_uint64, [_U32]),
+    "ac_nsr_forward_sdf_stencil_cache": (_I, [ctypes.POINTER(NsrModel), _V, _U32, _F, _F, _V, _V, _V, ctypes.c_uint64, _V]),
     "ac_nsr_shade_forward": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrShadeArgs), _V, _V]),
     "ac_nsr_shade_backward": (_I, [ctypes.POINTER(NsrModel), ctypes.POINTER(NsrShadeArgs), ctypes.POINTER(NsrShadeGrads), _V]),
     "ac_absmax_scale": (_I, [_V, _U32, _F, _V, _V]),

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __rest
 namespace acb {
 int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStream_t st);
 int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st, uint32_t stencil_M = 0,
-                          float eps = 0.f, float* out_fd = nullptr);
+                          float eps = 0.f, float* out_fd = nullptr, void* feat_cache = nullptr);
 }
 namespace {
 
@@ -557,6 +557,16 @@ int ac_nsr_forward_sdf_stencil(const ac_nsr_model* m, const float* P, uint32_t M
     if (check_model(m) || !P || !out_centre || !out_fd || !(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
     if (M == 0) return AC_OK;
     return acb::launch_forward_sdf_tc(m, P, out_centre, 7u * M, bound, (cudaStream_t)stream, M, eps, out_fd);
+}
+
+uint64_t ac_nsr_sdf_feature_cache_bytes(uint32_t n_points) { return (uint64_t)((n_points + 127u) / 128u) * 16384u; }
+
+int ac_nsr_forward_sdf_stencil_cache(const ac_nsr_model* m, const float* P, uint32_t M, float bound, float eps, float* out_centre, float* out_fd,
+                                     void* feature_cache, uint64_t cache_bytes, void* stream) {
+    if (check_model(m) || !P || !out_centre || !out_fd || !(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
+    if (!feature_cache || cache_bytes < ac_nsr_sdf_feature_cache_bytes(7u * M) || ((uintptr_t)feature_cache & 15)) return AC_E_WORKSPACE;
+    if (M == 0) return AC_OK;
+    return acb::launch_forward_sdf_tc(m, P, out_centre, 7u * M, bound, (cudaStream_t)stream, M, eps, out_fd, feature_cache);
 }
 
 int ac_nsr_sdf_backward(const ac_nsr_model* m, const float* x, const float* grad_out, uint32_t B, float bound,

@@ -509,7 +509,11 @@ template <int SLOT>
 __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const float2* __restrict__ table, const int32_t* __restrict__ offsets,
                                                                           const float* __restrict__ blob, float S, uint32_t H,
                                                                           const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound,
-                                                                          const uint32_t stencil_M, const float eps, float* __restrict__ out_fd) {
+                                                                          const uint32_t stencil_M, const float eps, float* __restrict__ out_fd,
+                                                                          unsigned char* __restrict__ feat_cache) {
+    // feat_cache (optional): every 128-point tile's encoded A operand (32 features as fp16 hi | lo chunks, 16 KB, the layout the
+    // MMA reads) is also written to feat_cache + tile * 16 KB, so the backward of the same points loads it back with
+    // coalesced 16-byte accesses instead of repeating the 128 gathers per point.
     // stencil_M > 0: x holds M section points and the B = 7 M evaluated points are generated here -- block 0 the points
     // themselves (16 outputs -> out [M,16]), blocks 1..6 their +-eps neighbours along x, y, z re-clamped to the bound
     // (signed distance only -> out_fd [6,M]): the finite-difference stencil of NeRFNetwork.gradient (:683-704).
@@ -584,6 +588,12 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const 
             float o1[1];
             group_sdf_eval<SLOT, false>(g, table, lv, bound, px, py, pz, o1);
             if (valid) out_fd[(size_t)(blk - 1) * stencil_M + smp] = o1[0];
+        }
+        if (feat_cache && g_first < B) {                  // this thread's row of the tile: 8 chunks of 16 bytes, 2 KB apart
+            unsigned char* dst = feat_cache + (size_t)(g_first >> 7) * 16384 + g.row * 16;
+            const unsigned char* src = g.a + g.row * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 2048) = *reinterpret_cast<const uint4*>(src + c * 2048);
         }
     }
     tc05::fence_before_sync();
@@ -751,7 +761,7 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
 }
 
 int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st, uint32_t stencil_M,
-                          float eps, float* out_fd) {
+                          float eps, float* out_fd, void* feat_cache) {
     const uint32_t per_cta = kGroups * 128;
     const uint32_t want = (B + per_cta - 1) / per_cta;
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
@@ -760,7 +770,8 @@ int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uin
 #define AC_CALL(S)                                                                                                              \
     ACB_SET_MAX_SMEM(forward_sdf_tc_kernel<S>, SM_TOTAL);                                                                       \
     forward_sdf_tc_kernel<S><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(reinterpret_cast<const float2*>(m->embeddings), m->offsets, \
-        m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, out, B, bound, stencil_M, eps, out_fd)
+        m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, out, B, bound, stencil_M, eps, out_fd,           \
+        reinterpret_cast<unsigned char*>(feat_cache))
     AC_SLOT_SWITCH(lease.slot, AC_CALL)
 #undef AC_CALL
     const int rc = acb::launched();

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const fl
                                                                         const float* __restrict__ x, const float* __restrict__ gout, uint32_t B,
                                                                         float bound, const float* __restrict__ scales, float* __restrict__ grad_table,
                                                                         float* __restrict__ grad_w0b, float* __restrict__ grad_w1, const uint32_t stencil_M,
-                                                                        const float eps, const float* __restrict__ gout_fd, float* __restrict__ din_t) {
+                                                                        const float eps, const float* __restrict__ gout_fd, float* __restrict__ din_t,
+                                                                        const unsigned char* __restrict__ feat_cache) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float4* xb = reinterpret_cast<float4*>(smem + M_XB);
     float* w1t = reinterpret_cast<float*>(smem + M_W1T);
@@ -361,7 +362,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const fl
         }
         const bool sd_only = __all_sync(0xffffffffu, blk != 0u || !valid);   // warp-uniform: only d/d(signed distance) is non-zero
         // ---- IN tile: features (hi | lo), then (x y z 1 0 0 0 0), zeros, grad_out * s_g ----
-        encode_to_tile<G_LO>(row_ptr + G_IN, table, lv, bound, px, py, pz, g.std_layout);
+        if (feat_cache) {        // the forward of the same points left this tile's encoded features (hi | lo chunks): no gathers
+            const uint32_t g_first = base + (uint32_t)group * 128u;         // a trailing group past the last point has no tile
+            const unsigned char* src = feat_cache + (size_t)(g_first >> 7) * 16384 + g.row * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(row_ptr + G_IN + c * 2048) = g_first < B ? __ldg(reinterpret_cast<const uint4*>(src + c * 2048)) : z4;
+                *reinterpret_cast<uint4*>(row_ptr + G_LO + c * 2048) = g_first < B ? __ldg(reinterpret_cast<const uint4*>(src + 8192 + c * 2048)) : z4;
+            }
+        } else {
+            encode_to_tile<G_LO>(row_ptr + G_IN, table, lv, bound, px, py, pz, g.std_layout);
+        }
         {
             uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
             if (valid) { c4.x = tc05::pack_f16x2(px, py); c4.y = tc05::pack_f16x2(pz, 1.0f); }
@@ -610,7 +622,7 @@ bool use_v1_backward() {
 
 int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout, uint32_t B, float bound, const float* scales, float* grad_table,
                         float* grad_w0b, float* grad_w1, uint32_t stencil_M, float eps, const float* gout_fd, cudaStream_t st,
-                        void* workspace = nullptr, uint64_t workspace_bytes = 0) {
+                        void* workspace = nullptr, uint64_t workspace_bytes = 0, const void* feature_cache = nullptr) {
     const float2* table = reinterpret_cast<const float2*>(m->embeddings);
     if (use_v1_backward()) {
         ACB_SET_MAX_SMEM(sdf_backward_tc_kernel, T_TOTAL);
@@ -627,7 +639,7 @@ int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout
             ACB_SET_MAX_SMEM(sdf_backward_mma_kernel<true>, M_TOTAL);
             sdf_backward_mma_kernel<true><<<grid, kThreadsB, M_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x,
                                                                             gout, B, bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd,
-                                                                            din_t);
+                                                                            din_t, reinterpret_cast<const unsigned char*>(feature_cache));
             if (int rc = acb::launched()) return rc;
             const uint32_t blocks = (B + 255u) / 256u, cap = (uint32_t)acb::sm_count() * 8u;
             sdf_scatter_kernel<<<blocks < cap ? blocks : cap, 256, 0, st>>>(m->offsets, m->log2_per_level_scale, m->base_resolution, x, B, bound, stencil_M,
@@ -637,7 +649,7 @@ int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout
         ACB_SET_MAX_SMEM(sdf_backward_mma_kernel<false>, M_TOTAL);
         sdf_backward_mma_kernel<false><<<grid, kThreadsB, M_TOTAL, st>>>(table, m->offsets, m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x,
                                                                          gout, B, bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd,
-                                                                         nullptr);
+                                                                         nullptr, reinterpret_cast<const unsigned char*>(feature_cache));
     }
     return acb::launched();
 }
@@ -676,11 +688,12 @@ extern "C" int ac_nsr_sdf_backward_fused_ws(const ac_nsr_model* m, const float* 
 
 extern "C" int ac_nsr_sdf_backward_stencil_ws(const ac_nsr_model* m, const float* P, uint32_t M, float bound, float eps, const float* grad_centre,
                                               const float* grad_fd, const float* scales, float* grad_table, float* grad_w0b, float* grad_w1,
-                                              void* workspace, uint64_t workspace_bytes, void* stream) {
+                                              void* workspace, uint64_t workspace_bytes, const void* feature_cache, void* stream) {
     if (!m || !m->embeddings || !m->offsets || !m->mlp_blob || !P || !grad_centre || !grad_fd || !scales || !grad_table || !grad_w0b || !grad_w1)
         return AC_E_INVALID_ARG;
     if (!(eps > 0.f) || M > 0xFFFFFFFFu / 7u) return AC_E_INVALID_ARG;
     if (M == 0) return AC_OK;
+    if (feature_cache && ((uintptr_t)feature_cache & 15)) return AC_E_INVALID_ARG;
     return launch_sdf_backward(m, P, grad_centre, 7u * M, bound, scales, grad_table, grad_w0b, grad_w1, M, eps, grad_fd, (cudaStream_t)stream, workspace,
-                               workspace_bytes);
+                               workspace_bytes, feature_cache);
 }

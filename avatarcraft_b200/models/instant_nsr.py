@@ -97,6 +97,15 @@ def _backward_workspace(net, n_points, dev):
     return ws
 
 
+def _feature_cache(net, n_points, dev):
+    """Encoded features of the stencil forward's points, kept for its backward (16 KB per 128 points)."""
+    need = int(_lib.lib().ac_nsr_sdf_feature_cache_bytes(int(n_points)))
+    fc = getattr(net, "_sdf_feat_cache", None)
+    if fc is None or fc.numel() < need or fc.device != dev:
+        fc = net._sdf_feat_cache = torch.empty(need, device=dev, dtype=torch.uint8)
+    return fc
+
+
 def _fp16_scales(gmax, net):
     """Device-side power-of-two factors (s_d, s_g) that bring delta / grad_out into the fp16 range of the tensor-core
     operands of the fused backward (include/avatarcraft_b200.h); no host synchronisation."""
@@ -121,8 +130,13 @@ class _SdfStencil(torch.autograd.Function):
         centre = torch.empty(M, 16, device=P.device, dtype=torch.float32)
         fd = torch.empty(6, M, device=P.device, dtype=torch.float32)
         m = net._device_model()
-        _lib.check(_lib.lib().ac_nsr_forward_sdf_stencil(ctypes.byref(m), _lib.ptr(P), M, float(bound), float(eps), _lib.ptr(centre), _lib.ptr(fd),
-                                                         _lib.stream_ptr()), "ac_nsr_forward_sdf_stencil")
+        # the encoded features are cached for the backward; autograd may run several graphs before their backward, so the
+        # cache is only trusted when this forward was the model's latest (token), else the backward re-encodes
+        fc = _feature_cache(net, 7 * M, P.device)
+        net._sdf_feat_token = ctx.token = object()
+        _lib.check(_lib.lib().ac_nsr_forward_sdf_stencil_cache(ctypes.byref(m), _lib.ptr(P), M, float(bound), float(eps), _lib.ptr(centre),
+                                                               _lib.ptr(fd), _lib.ptr(fc), fc.numel(), _lib.stream_ptr()),
+                   "ac_nsr_forward_sdf_stencil_cache")
         ctx.save_for_backward(P)
         ctx.net, ctx.bound, ctx.eps, ctx.emb_shape = net, float(bound), float(eps), embeddings.shape
         return centre, fd
@@ -139,9 +153,11 @@ class _SdfStencil(torch.autograd.Function):
         acc0 = torch.zeros(64, 36, **f32); acc1 = torch.zeros(16, 64, **f32)
         m = net._device_model()
         ws = _backward_workspace(net, 7 * M, dev)
+        fc = net._sdf_feat_cache if getattr(net, "_sdf_feat_token", None) is ctx.token else None
         _lib.check(_lib.lib().ac_nsr_sdf_backward_stencil_ws(ctypes.byref(m), _lib.ptr(P), M, ctx.bound, ctx.eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
                                                              _lib.ptr(scales), _lib.ptr(grad_table), _lib.ptr(acc0), _lib.ptr(acc1), _lib.ptr(ws),
-                                                             ws.numel(), _lib.stream_ptr()), "ac_nsr_sdf_backward_stencil_ws")
+                                                             ws.numel(), None if fc is None else _lib.ptr(fc), _lib.stream_ptr()),
+                   "ac_nsr_sdf_backward_stencil_ws")
         gw0b = acc0 / scales[0]
         gw1 = acc1 / scales[1]
         gb1 = g_centre.sum(0)

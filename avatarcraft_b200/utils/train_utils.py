@@ -169,8 +169,9 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
         centre = torch.empty(Mp, 16, device=dev, dtype=torch.float32)
         fd = torch.empty(6, Mp, device=dev, dtype=torch.float32)
         model = net_style._device_model()
-        _lib.check(L.ac_nsr_forward_sdf_stencil(ctypes.byref(model), _lib.ptr(P), Mp, bound, eps, _lib.ptr(centre), _lib.ptr(fd), sp()),
-                   "ac_nsr_forward_sdf_stencil")
+        fc = M._feature_cache(net_style, 7 * Mp, dev)          # encoded features of the 7 Mp points, reused by the backward below
+        _lib.check(L.ac_nsr_forward_sdf_stencil_cache(ctypes.byref(model), _lib.ptr(P), Mp, bound, eps, _lib.ptr(centre), _lib.ptr(fd),
+                                                      _lib.ptr(fc), fc.numel(), sp()), "ac_nsr_forward_sdf_stencil_cache")
         bg = None if bkg_key % 4 == WHITE_BKG else torch.zeros(m, 3, device=dev)
         bufs = M._shade_forward(net_style, o, d, z, P, centre, fd, bg, num_steps, bound, eps, car)
         g_eik = None
@@ -199,7 +200,7 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
         ws = M._backward_workspace(net_style, 7 * Mp, dev)
         _lib.check(L.ac_nsr_sdf_backward_stencil_ws(ctypes.byref(model), _lib.ptr(P), Mp, bound, eps, _lib.ptr(g_centre), _lib.ptr(g_fd),
                                                     _lib.ptr(st.scales), _lib.ptr(G["encoder.embeddings"]), _lib.ptr(acc0), _lib.ptr(acc1),
-                                                    _lib.ptr(ws), ws.numel(), sp()), "ac_nsr_sdf_backward_stencil_ws")
+                                                    _lib.ptr(ws), ws.numel(), _lib.ptr(fc), sp()), "ac_nsr_sdf_backward_stencil_ws")
         sdf, col, P_ = net_style.sdf_net, net_style.color_net, _lib.ptr
         s0, s1 = st.scales[0:1], st.scales[1:2]
 

@@ -143,7 +143,15 @@ int ac_nsr_sdf_backward_fused_ws(const ac_nsr_model *model, const float *x, cons
                                  uint64_t workspace_bytes, void *stream);
 int ac_nsr_sdf_backward_stencil_ws(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
                                    const float *grad_centre, const float *grad_fd, const float *scales, float *grad_table,
-                                   float *grad_w0b, float *grad_w1, void *workspace, uint64_t workspace_bytes, void *stream);
+                                   float *grad_w0b, float *grad_w1, void *workspace, uint64_t workspace_bytes,
+                                   const void *feature_cache, void *stream);
+/* Feature cache between the stencil forward and its backward: ac_nsr_forward_sdf_stencil_cache also writes every 128-point
+ * tile's encoded operand (32 hash features as fp16 hi | lo, 16 KB per tile; ac_nsr_sdf_feature_cache_bytes(7 M) bytes, 16-byte
+ * aligned) and ac_nsr_sdf_backward_stencil_ws(feature_cache = that buffer, same P / M / model) loads it back instead of
+ * repeating the 128 table gathers per point.  feature_cache = NULL recomputes the encoding. */
+uint64_t ac_nsr_sdf_feature_cache_bytes(uint32_t n_points);
+int ac_nsr_forward_sdf_stencil_cache(const ac_nsr_model *model, const float *P, uint32_t M, float bound, float eps,
+                                     float *out_centre, float *out_fd, void *feature_cache, uint64_t cache_bytes, void *stream);
 /* --------------------------------------------------------------------------------------
  * The differentiable half of NeRFRenderer.run on the training path, after the SDF stencil
  * (models/instant_nsr.py:210-299; driven by stylize.py:153-193): finite-difference normal, colour MLP, NeuS alpha,

@@ -369,3 +369,39 @@ def test_native_patch_step_equals_autograd_patch_step():
     assert abs(res["native"][3] - res["autograd"][3]) < 1e-4 * max(1.0, abs(res["autograd"][3]))
     assert res["autograd"][3] > 0
     assert rel_l2(res["native"][1].cpu().numpy(), res["autograd"][1].cpu().numpy()) < 1e-5
+
+
+def test_stencil_backward_with_feature_cache_equals_recomputed_encoding():
+    """ac_nsr_forward_sdf_stencil_cache keeps every tile's encoded features for ac_nsr_sdf_backward_stencil_ws: same outputs as the
+    forward without a cache (bit for bit) and the same gradients as the backward that re-gathers (atomics order only)."""
+    import ctypes
+    from avatarcraft_b200 import _lib
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    gen = torch.Generator().manual_seed(14)
+    M, bound, eps = 30011, 1.6, 0.005
+    P = ((torch.rand(M, 3, generator=gen) * 2 - 1) * 1.6).cuda()
+    m = net._device_model()
+    L = _lib.lib()
+    c0 = torch.empty(M, 16, device="cuda"); f0 = torch.empty(6, M, device="cuda")
+    c1 = torch.empty_like(c0); f1 = torch.empty_like(f0)
+    _lib.check(L.ac_nsr_forward_sdf_stencil(ctypes.byref(m), _lib.ptr(P), M, bound, eps, _lib.ptr(c0), _lib.ptr(f0), _lib.stream_ptr()), "fwd")
+    fc = torch.empty(int(L.ac_nsr_sdf_feature_cache_bytes(7 * M)), device="cuda", dtype=torch.uint8)
+    _lib.check(L.ac_nsr_forward_sdf_stencil_cache(ctypes.byref(m), _lib.ptr(P), M, bound, eps, _lib.ptr(c1), _lib.ptr(f1), _lib.ptr(fc), fc.numel(),
+                                                  _lib.stream_ptr()), "fwd cache")
+    assert torch.equal(c0, c1) and torch.equal(f0, f1)
+    g_c = torch.randn(M, 16, generator=gen).cuda(); g_f = torch.randn(6, M, generator=gen).cuda()
+    scales = torch.tensor([256.0, 1024.0], device="cuda")
+    ws = torch.empty(int(L.ac_nsr_sdf_backward_workspace_bytes(7 * M)), device="cuda", dtype=torch.uint8)
+    outs = []
+    for cache in (None, fc):
+        gt = torch.zeros_like(net.encoder.embeddings); a0 = torch.zeros(64, 36, device="cuda"); a1 = torch.zeros(16, 64, device="cuda")
+        _lib.check(L.ac_nsr_sdf_backward_stencil_ws(ctypes.byref(m), _lib.ptr(P), M, bound, eps, _lib.ptr(g_c), _lib.ptr(g_f), _lib.ptr(scales),
+                                                    _lib.ptr(gt), _lib.ptr(a0), _lib.ptr(a1), _lib.ptr(ws), ws.numel(),
+                                                    None if cache is None else _lib.ptr(cache), _lib.stream_ptr()), "bwd")
+        outs.append((gt, a0, a1))
+    for a, b in zip(outs[0], outs[1]):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+    small = torch.empty(64, device="cuda", dtype=torch.uint8)
+    assert L.ac_nsr_forward_sdf_stencil_cache(ctypes.byref(m), _lib.ptr(P), M, bound, eps, _lib.ptr(c1), _lib.ptr(f1), _lib.ptr(small), 64,
+                                              _lib.stream_ptr()) == _lib.AC_E_WORKSPACE
