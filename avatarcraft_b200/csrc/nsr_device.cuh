@@ -71,6 +71,9 @@ __device__ __forceinline__ uint32_t wrap_slot(uint32_t h, const LevelMeta& m) {
 
 // Level bodies with the level kind known at compile time (used when the offsets table has the reference layout:
 // leading dense levels, then power-of-two hashed levels).  Bit-identical to grid_level_3d.
+#ifndef AC_PAIR_LOADS
+#define AC_PAIR_LOADS 0     // measured (profiles/r02_gather_experiments.md): bit-identical, but 14.8 ms/frame vs 14.1 ms -- off
+#endif
 template <bool HASHED>
 __device__ __forceinline__ float2 grid_level_3d_k(const float2* __restrict__ table, const LevelMeta m, float x, float y, float z) {
     float px = fmaf(x, m.scale, 0.5f), py = fmaf(y, m.scale, 0.5f), pz = fmaf(z, m.scale, 0.5f);
@@ -120,8 +123,31 @@ __device__ __forceinline__ float2 grid_level_3d_k(const float2* __restrict__ tab
     } else
 #endif
     {
+#if AC_PAIR_LOADS
+        // The two x-corners of a cell are neighbours in memory more often than not: slot, slot + 1 on a dense level, and
+        // s, s ^ 1 on a hashed level whenever ix is even (the hash leaves x un-multiplied).  One 16-byte load of the aligned
+        // entry pair that holds the first corner also delivers the second one when both sit in the same pair -- which, for
+        // the reference's offsets table (hashed levels start at odd entries), happens for every even ix iff the table starts
+        // 8 bytes past a 16-byte boundary (the host keeps such a copy).  Otherwise a second 8-byte load fetches it.  Same
+        // table entries either way: results are bit-identical; the L1 data pipe sees up to 25 % fewer wavefronts.  MEASURED
+        // SLOWER than eight 8-byte loads (the selects and the predicated second load cost more issue slots than the saved
+        // wavefronts return: 14.8 vs 14.1 ms per frame with a shifted table, 15.4 ms without), so it is compiled out.
+        const uint32_t b8 = (uint32_t)(reinterpret_cast<uintptr_t>(table) >> 3) & 1u;
+        const float4* __restrict__ t16 = reinterpret_cast<const float4*>(table - b8);
+        const uint32_t e_base = m.offset + b8;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const uint32_t e0 = e_base + s[k], e1 = e_base + s[k + 1];
+            const float4 q = __ldg(t16 + (e0 >> 1));
+            const float2 lo = make_float2(q.x, q.y), hi = make_float2(q.z, q.w);
+            v[k] = (e0 & 1u) ? hi : lo;
+            if ((e1 >> 1) == (e0 >> 1)) v[k + 1] = (e1 & 1u) ? hi : lo;
+            else v[k + 1] = __ldg(t + s[k + 1]);
+        }
+#else
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+#endif
     }
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
@@ -167,8 +193,31 @@ __device__ __forceinline__ float2 grid_level_3d(const float2* __restrict__ table
     } else
 #endif
     {
+#if AC_PAIR_LOADS
+        // The two x-corners of a cell are neighbours in memory more often than not: slot, slot + 1 on a dense level, and
+        // s, s ^ 1 on a hashed level whenever ix is even (the hash leaves x un-multiplied).  One 16-byte load of the aligned
+        // entry pair that holds the first corner also delivers the second one when both sit in the same pair -- which, for
+        // the reference's offsets table (hashed levels start at odd entries), happens for every even ix iff the table starts
+        // 8 bytes past a 16-byte boundary (the host keeps such a copy).  Otherwise a second 8-byte load fetches it.  Same
+        // table entries either way: results are bit-identical; the L1 data pipe sees up to 25 % fewer wavefronts.  MEASURED
+        // SLOWER than eight 8-byte loads (the selects and the predicated second load cost more issue slots than the saved
+        // wavefronts return: 14.8 vs 14.1 ms per frame with a shifted table, 15.4 ms without), so it is compiled out.
+        const uint32_t b8 = (uint32_t)(reinterpret_cast<uintptr_t>(table) >> 3) & 1u;
+        const float4* __restrict__ t16 = reinterpret_cast<const float4*>(table - b8);
+        const uint32_t e_base = m.offset + b8;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const uint32_t e0 = e_base + s[k], e1 = e_base + s[k + 1];
+            const float4 q = __ldg(t16 + (e0 >> 1));
+            const float2 lo = make_float2(q.x, q.y), hi = make_float2(q.z, q.w);
+            v[k] = (e0 & 1u) ? hi : lo;
+            if ((e1 >> 1) == (e0 >> 1)) v[k + 1] = (e1 & 1u) ? hi : lo;
+            else v[k + 1] = __ldg(t + s[k + 1]);
+        }
+#else
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = __ldg(t + s[k]);
+#endif
     }
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
