@@ -138,6 +138,7 @@ _SIGNATURES = {
     "ac_warp_mesh_bytes": (ctypes.c_uint64, [_U32]),
     "ac_warp_prepare_mesh": (_I, [_V, _V, _U32, _U32, _V, _V]),
     "ac_warp_samples_to_canonical": (_I, [_V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
+    "ac_warp_samples_to_canonical_rays": (_I, [_V, _U32, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
     "ac_warp_samples_to_canonical_ordered": (_I, [_V, _V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
     "ac_warp_query_keys": (_I, [_V, _U32, _V, _U32, _F, _V, _V]),
     "ac_mesh_guided_near_far": (_I, [_V, _V, _U32, _V, _U32, _F, _F, _V, _V]),

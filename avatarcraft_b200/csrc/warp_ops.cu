@@ -198,26 +198,9 @@ __device__ __forceinline__ uint32_t nearest_box(const Box* __restrict__ b, uint3
     return arg;
 }
 
-// pts [n,3] -> can_pts [n,3], mask [n] (dist^2 < threshold), optional closest [n,3], face_id [n], dist2 [n].
-// T [n_T,4,4] row-major per-vertex transforms whose last row is (0,0,0,c).
-__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, const int32_t* __restrict__ order, uint32_t n,
-                                                                const MeshView m, const float* __restrict__ T, float threshold,
-                                                                float* __restrict__ can_pts, float* __restrict__ mask,
-                                                                float* __restrict__ closest, int32_t* __restrict__ face_id,
-                                                                float* __restrict__ dist2_out) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n) return;
-    const uint32_t i = order ? (uint32_t)order[slot] : slot;      // spatially sorted queries keep a warp on the same boxes
-    const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
-    const TriRec* __restrict__ tris = m.tris;
-    const uint32_t n_faces = m.n_faces;
-    // 1. greedy descent to the nearest leaf box -> a tight first bound
-    const uint32_t s0 = nearest_box(m.l2, 0, m.n2, px, py, pz);
-    const uint32_t g0 = nearest_box(m.l1, s0 * kFan, min(m.n1, (s0 + 1) * kFan), px, py, pz);
-    const uint32_t c0 = nearest_box(m.l0, g0 * kFan, min(m.n0, (g0 + 1) * kFan), px, py, pz);
-    Best best; best.d2 = INFINITY; best.d = INFINITY; best.b1 = 0.f; best.b2 = 0.f; best.f = 0xFFFFFFFFu;
-    scan_cluster(tris, c0 * kCluster, min(n_faces, (c0 + 1) * kCluster), px, py, pz, best);
-    // 2. exact branch and bound: every box that can still hold a closer (or equally close) triangle
+// Exact branch and bound from whatever `best` holds (a real candidate, or just an upper bound with f = none): every box
+// that can still hold a closer (or equally close) triangle is visited; `skip_leaf` was scanned by the caller.
+__device__ __forceinline__ void search_boxes(const MeshView& m, float px, float py, float pz, uint32_t skip_leaf, Best& best) {
     for (uint32_t s = 0; s < m.n2; ++s) {
         if (box_dist2(m.l2 + s, px, py, pz) > best.d2) continue;
         const uint32_t g_hi = min(m.n1, (s + 1) * kFan);
@@ -225,17 +208,32 @@ __global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __r
             if (box_dist2(m.l1 + g, px, py, pz) > best.d2) continue;
             const uint32_t c_hi = min(m.n0, (g + 1) * kFan);
             for (uint32_t c = g * kFan; c < c_hi; ++c) {
-                if (c == c0 || box_dist2(m.l0 + c, px, py, pz) > best.d2) continue;
-                scan_cluster(tris, c * kCluster, min(n_faces, (c + 1) * kCluster), px, py, pz, best);
+                if (c == skip_leaf || box_dist2(m.l0 + c, px, py, pz) > best.d2) continue;
+                scan_cluster(m.tris, c * kCluster, min(m.n_faces, (c + 1) * kCluster), px, py, pz, best);
             }
         }
     }
+}
+
+// Full query: greedy descent to the nearest leaf box for a tight first bound, then the exact search.
+__device__ __forceinline__ void closest_full(const MeshView& m, float px, float py, float pz, Best& best) {
+    const uint32_t s0 = nearest_box(m.l2, 0, m.n2, px, py, pz);
+    const uint32_t g0 = nearest_box(m.l1, s0 * kFan, min(m.n1, (s0 + 1) * kFan), px, py, pz);
+    const uint32_t c0 = nearest_box(m.l0, g0 * kFan, min(m.n0, (g0 + 1) * kFan), px, py, pz);
+    best.d2 = INFINITY; best.d = INFINITY; best.b1 = 0.f; best.b2 = 0.f; best.f = 0xFFFFFFFFu;
+    scan_cluster(m.tris, c0 * kCluster, min(m.n_faces, (c0 + 1) * kCluster), px, py, pz, best);
+    search_boxes(m, px, py, pz, c0, best);
+}
+
+// T_interp = sum_k b_k T[v_k] (utils/ray_utils.py:80), its inverse applied to (p, 1), xyz kept un-normalised (:84); outputs.
+__device__ __forceinline__ void warp_outputs(const MeshView& m, const float* __restrict__ T, float threshold, uint32_t i, float px, float py, float pz,
+                                             const Best& best, float* __restrict__ can_pts, float* __restrict__ mask, float* __restrict__ closest,
+                                             int32_t* __restrict__ face_id, float* __restrict__ dist2_out) {
     const uint32_t best_f = best.f;
     const float bb1 = best.b1, bb2 = best.b2;
     const float bestd2 = best.d2;
-    const TriRec t = tris[best_f];
+    const TriRec t = m.tris[best_f];
     const float b0 = 1.0f - bb1 - bb2;
-    // T_interp = sum_k b_k T[v_k]  (utils/ray_utils.py:80), then inverse applied to (p,1), xyz kept un-normalised (:84)
     float M[12], c = 0.f;
 #pragma unroll
     for (int q = 0; q < 12; ++q) M[q] = 0.f;
@@ -268,6 +266,58 @@ __global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __r
     }
     if (face_id) face_id[i] = (int32_t)best_f;
     if (dist2_out) dist2_out[i] = bestd2;
+}
+
+// pts [n,3] -> can_pts [n,3], mask [n] (dist^2 < threshold), optional closest [n,3], face_id [n], dist2 [n].
+// T [n_T,4,4] row-major per-vertex transforms whose last row is (0,0,0,c).
+__global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __restrict__ pts, const int32_t* __restrict__ order, uint32_t n,
+                                                                const MeshView m, const float* __restrict__ T, float threshold,
+                                                                float* __restrict__ can_pts, float* __restrict__ mask,
+                                                                float* __restrict__ closest, int32_t* __restrict__ face_id,
+                                                                float* __restrict__ dist2_out) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const uint32_t i = order ? (uint32_t)order[slot] : slot;      // spatially sorted queries keep a warp on the same boxes
+    const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
+    Best best;
+    closest_full(m, px, py, pz, best);
+    warp_outputs(m, T, threshold, i, px, py, pz, best, can_pts, mask, closest, face_id, dist2_out);
+}
+
+// Samples along a ray are neighbours: a thread walks G consecutive samples of one ray; after the first (full) query each
+// next one starts from the triangle-inequality bound dist(p) <= dist(p_prev) + |p - p_prev| and from the leaf that held
+// the previous closest triangle, so the exact search only opens the few boxes inside that radius.  Same search, same
+// tie rule (smallest triangle index among equals): results are bit-identical to the per-point kernel.
+template <int G>
+__global__ void __launch_bounds__(256) warp_to_canonical_rays_kernel(const float* __restrict__ pts, uint32_t n_rays, uint32_t n_samples,
+                                                                     const MeshView m, const float* __restrict__ T, float threshold,
+                                                                     float* __restrict__ can_pts, float* __restrict__ mask,
+                                                                     float* __restrict__ closest, int32_t* __restrict__ face_id,
+                                                                     float* __restrict__ dist2_out) {
+    const uint32_t chunks = (n_samples + G - 1) / G;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rays * chunks) return;
+    // chunk-major: the 32 lanes of a warp take the SAME chunk of 32 neighbouring rays (adjacent pixels, same depth range)
+    const uint32_t chunk = t / n_rays, ray = t - chunk * n_rays;
+    const uint32_t k0 = chunk * G, k1 = min(n_samples, k0 + G);
+    Best best;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t i = ray * n_samples + k;
+        const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
+        if (k == k0) {
+            closest_full(m, px, py, pz, best);
+        } else {
+            const float dx = px - qx, dy = py - qy, dz = pz - qz;
+            const float bound = (best.d + sqrtf(dx * dx + dy * dy + dz * dz)) * 1.000001f + 1e-7f;
+            const uint32_t leaf = best.f / kCluster;
+            best.d = bound; best.d2 = bound * bound; best.f = 0xFFFFFFFFu; best.b1 = 0.f; best.b2 = 0.f;
+            scan_cluster(m.tris, leaf * kCluster, min(m.n_faces, (leaf + 1) * kCluster), px, py, pz, best);
+            search_boxes(m, px, py, pz, leaf, best);
+        }
+        qx = px; qy = py; qz = pz;
+        warp_outputs(m, T, threshold, i, px, py, pz, best, can_pts, mask, closest, face_id, dist2_out);
+    }
 }
 
 // One warp per ray: near = min_v(z0 - dz), far = max_v(z0 + dz) over the vertex spheres the ray pierces
@@ -346,6 +396,18 @@ int ac_warp_samples_to_canonical_ordered(const float* pts, const int32_t* order,
     if (n_pts == 0) return AC_OK;
     warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, order, n_pts, mesh_view(mesh, n_faces), T, threshold,
                                                                                    can_pts, mask, closest, face_id, dist2);
+    return acb::launched();
+}
+
+int ac_warp_samples_to_canonical_rays(const float* pts, uint32_t n_rays, uint32_t n_samples, const void* mesh, uint32_t n_faces, const float* T,
+                                      float threshold, float* can_pts, float* mask, float* closest, int32_t* face_id, float* dist2, void* stream) {
+    if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0 || n_samples == 0) return AC_E_INVALID_ARG;
+    if (n_rays == 0) return AC_OK;
+    if ((uint64_t)n_rays * n_samples > 0xFFFFFFFFull) return AC_E_INVALID_ARG;
+    constexpr int G = 8;
+    const uint32_t threads = n_rays * ((n_samples + G - 1) / G);
+    warp_to_canonical_rays_kernel<G><<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, n_rays, n_samples, mesh_view(mesh, n_faces), T,
+                                                                                             threshold, can_pts, mask, closest, face_id, dist2);
     return acb::launched();
 }
 

@@ -197,3 +197,23 @@ def test_stylize_resume_is_step_accurate_inside_an_epoch(tmp_path):
         assert float((wa[k].float() - wb[k].float()).abs().max()) <= 2e-3, k
     # constant learning rate by default: the reference never steps its StepLR (stylize.py:214)
     assert end_b["optimizer"]["lr"] == 5e-3
+
+
+def test_ray_coherent_warp_equals_per_point_search(body):
+    """ac_warp_samples_to_canonical_rays (a thread walks 8 consecutive samples of a ray, each search seeded by the previous
+    result) must reproduce the per-point search bit for bit: same faces, distances, closest and canonical points, mask."""
+    from avatarcraft_b200.utils import ray_utils as ru
+    o, d = syn.pinhole_rays(syn.orbit_pose(10.0), 96, 96)
+    z = torch.linspace(0.6, 2.8, 44)                              # 44 samples: the last chunk of 8 is ragged
+    pts = (o[:, None, :] + d[:, None, :] * z[None, :, None]).cuda().contiguous()
+    mesh = ru.PosedMesh(body["world_verts"], body["faces"], body["Ts"], "cuda")
+    b = ru.warp_samples_to_canonical(pts, None, None, None, 0.05, mesh=mesh, return_query=True)
+    old, ru.RAY_COHERENT = ru.RAY_COHERENT, True
+    try:
+        a = ru.warp_samples_to_canonical(pts, None, None, None, 0.05, mesh=mesh, return_query=True)
+    finally:
+        ru.RAY_COHERENT = old
+    for name, x, y in zip(("can", "dirs", "closest", "mask", "face", "dist2"), a, b):
+        same = torch.equal(x, y) or ((torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y)))
+        assert same, name
+    assert 0.02 < float(a[3].float().mean()) < 0.9
