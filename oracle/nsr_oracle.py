@@ -207,7 +207,7 @@ class OracleNSR:
                 far = torch.where(torch.isinf(gf)[:, None], far, gf[:, None])
 
             def warp(p):                           # float64 numpy round trip, then .float() like the reference
-                can, mask, *_ = _wo.warp_samples_to_canonical(p.numpy(), verts, faces, Ts, 0.05)
+                can, mask, *_ = _wo.warp_samples_to_canonical(p.numpy(), verts, faces, Ts, 0.05, device=getattr(self, 'warp_device', None))
                 return torch.from_numpy(can), torch.from_numpy(mask)
         z = near + (far - near) * torch.linspace(0.0, 1.0, num_steps).unsqueeze(0).expand(N, num_steps)
         sample_dist = (far - near) / num_steps

@@ -217,3 +217,28 @@ def test_ray_coherent_warp_equals_per_point_search(body):
         same = torch.equal(x, y) or ((torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y)))
         assert same, name
     assert 0.02 < float(a[3].float().mean()) < 0.9
+
+
+def test_warped_render_against_oracle_4096_rays(body):
+    """render_can=False on a whole 64x64 frame (4096 rays, 32+32 samples = 393 216 closest-point queries against 13 776
+    triangles): the oracle's exhaustive float64 closest-point scan runs in torch on the GPU (oracle/warp_oracle.py), everything
+    else of the oracle on the CPU as usual."""
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    o, d = syn.pinhole_rays(syn.orbit_pose(10.0), 64, 64)
+    orc = OracleNSR(sd)
+    orc.warp_device = "cuda"
+    ref = orc.run(o, d, 32, 1.6, 32, verts=body["world_verts"], faces=body["faces"], Ts=body["Ts"])
+    out = net.run(o.cuda()[None], d.cuda()[None], 32, 1.6, 32, None, 1.0, 0.0, render_can=False, verts=body["world_verts"],
+                  faces=body["faces"], Ts=body["Ts"])
+    torch.cuda.synchronize()
+    rgb, rgb_o = out[3].reshape(-1, 3).cpu().numpy(), ref[3].reshape(-1, 3).numpy()
+    dz = (out[9].cpu() - ref[9]).abs().max(1)[0].numpy()
+    hit = ref[2].reshape(-1).numpy() > 0.5
+    print(f"warped render, 4096 rays: PSNR {psnr(rgb, rgb_o):.1f} dB, depth coincidence (1e-4) {(dz <= 1e-4).mean():.4f}, "
+          f"{int(hit.sum())} rays hit the canonical body")
+    assert psnr(rgb, rgb_o) >= 40.0
+    assert (dz <= 1e-4).mean() >= 0.9
+    ok = dz <= 1e-5
+    np.testing.assert_allclose(out[2].reshape(-1).cpu().numpy()[ok], ref[2].reshape(-1).numpy()[ok], atol=3e-3)
+    assert hit.sum() >= 200
