@@ -615,6 +615,96 @@ __global__ void __launch_bounds__(256) sdf_scatter_kernel(const int32_t* __restr
     }
 }
 
+// Stencil variant of the scatter: the seven points of a sample's finite-difference stencil (centre, +-0.005 along x, y, z) lie in
+// one grid cell on the coarse levels, and so do the stencils of the next samples of the ray.  Lanes are laid out as
+// (sample, stencil point) -- 4 consecutive samples x 8 lanes (7 points + a zero-weight copy of the centre) -- so a run of
+// equal cells now spans whole stencils: one reduction packet per (run, corner) where the point-ordered kernel above
+// needs one per stencil block.  Same arithmetic, different summation order.
+__global__ void __launch_bounds__(256) sdf_scatter_stencil_kernel(const int32_t* __restrict__ offsets, float S, uint32_t H, const float* __restrict__ x,
+                                                                  uint32_t M, float bound, float eps, const float* __restrict__ din_t,
+                                                                  float* __restrict__ grad_table) {
+    __shared__ LevelMeta lv[kLevels];
+    if (threadIdx.x < kLevels) lv[threadIdx.x] = make_level_meta(offsets, threadIdx.x, S, H, 3);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const float two_b = 2.0f * bound;
+    const size_t B = (size_t)7 * M;
+    const uint32_t sub = (uint32_t)lane >> 3, st = (uint32_t)lane & 7u;
+    const uint32_t blk = st == 7u ? 0u : st;                     // lane 7 of a sample: a copy of the centre that carries no gradient
+    for (uint32_t base = blockIdx.x * 32u; base < M; base += gridDim.x * 32u) {
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t smp = base + it * 4 + sub;
+            bool inr = smp < M;
+            float u = 0.f, v = 0.f, w = 0.f;
+            if (inr) {
+                float px = x[3 * (size_t)smp], py = x[3 * (size_t)smp + 1], pz = x[3 * (size_t)smp + 2];
+                if (blk) {
+                    const float e = (blk & 1) ? eps : -eps;
+                    const uint32_t ax = (blk - 1) >> 1;
+                    if (ax == 0) px = clampf(px + e, -bound, bound);
+                    else if (ax == 1) py = clampf(py + e, -bound, bound);
+                    else pz = clampf(pz + e, -bound, bound);
+                }
+                u = (px + bound) / two_b; v = (py + bound) / two_b; w = (pz + bound) / two_b;
+                inr = !((u < 0.f) | (u > 1.f) | (v < 0.f) | (v > 1.f) | (w < 0.f) | (w > 1.f));
+            }
+            if (!__any_sync(full, inr)) continue;
+            const size_t b = (size_t)blk * M + smp;
+#pragma unroll 1
+            for (int ll = 0; ll < 2; ++ll) {
+                const int l = 2 * warp + ll;
+                const LevelMeta m = lv[l];
+                float gx = 0.f, gy = 0.f;
+                if (inr && st != 7u) { gx = din_t[(size_t)(2 * l) * B + b]; gy = din_t[(size_t)(2 * l + 1) * B + b]; }
+                float fx = fmaf(u, m.scale, 0.5f), fy = fmaf(v, m.scale, 0.5f), fz = fmaf(w, m.scale, 0.5f);
+                const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+                const uint32_t ix = (uint32_t)flx, iy = (uint32_t)fly, iz = (uint32_t)flz;
+                fx -= flx; fy -= fly; fz -= flz;
+                float val[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float wgt = (((c & 1) ? fx : 1.0f - fx) * ((c & 2) ? fy : 1.0f - fy)) * ((c & 4) ? fz : 1.0f - fz);
+                    val[2 * c] = wgt * gx; val[2 * c + 1] = wgt * gy;
+                }
+                const uint32_t k1 = inr ? (ix | (iy << 16)) : 0xFFFFFFFFu, k2 = inr ? iz : (0x80000000u | (uint32_t)lane);
+                const uint32_t p1 = __shfl_up_sync(full, k1, 1), p2 = __shfl_up_sync(full, k2, 1);
+                const bool head = lane == 0 || k1 != p1 || k2 != p2;
+                const unsigned heads = __ballot_sync(full, head);
+                bool emit = inr;
+                if (heads != full) {
+                    const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+                    emit = inr && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        float a = val[q];
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const float t = __shfl_up_sync(full, a, d);
+                            if (lane - d >= start) a += t;
+                        }
+                        val[q] = a;
+                    }
+                    if (st == 7u && head) emit = false;          // a zero-weight copy that is a run of its own has nothing to add
+                } else if (st == 7u) {
+                    emit = false;
+                }
+                if (!emit) continue;
+                float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t cx = ix + (c & 1), cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
+                    uint32_t slot;
+                    if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
+                    else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
+                    atomicAdd(dst + slot, make_float2(val[2 * c], val[2 * c + 1]));
+                }
+            }
+        }
+    }
+}
+
 bool use_v1_backward() {
     static const bool v1 = [] { const char* e = getenv("AC_SDF_BWD_IMPL"); return e && e[0] == 'v' && e[1] == '1'; }();
     return v1;
@@ -641,9 +731,17 @@ int launch_sdf_backward(const ac_nsr_model* m, const float* x, const float* gout
                                                                             gout, B, bound, scales, grad_table, grad_w0b, grad_w1, stencil_M, eps, gout_fd,
                                                                             din_t, reinterpret_cast<const unsigned char*>(feature_cache));
             if (int rc = acb::launched()) return rc;
-            const uint32_t blocks = (B + 255u) / 256u, cap = (uint32_t)acb::sm_count() * 8u;
-            sdf_scatter_kernel<<<blocks < cap ? blocks : cap, 256, 0, st>>>(m->offsets, m->log2_per_level_scale, m->base_resolution, x, B, bound, stencil_M,
-                                                                           eps, din_t, grad_table);
+            const uint32_t cap = (uint32_t)acb::sm_count() * 8u;
+            static const bool point_order = [] { const char* e = getenv("AC_SCATTER_ORDER"); return e && e[0] == 'p'; }();   // A/B
+            if (stencil_M && !point_order) {
+                const uint32_t blocks = (stencil_M + 31u) / 32u;
+                sdf_scatter_stencil_kernel<<<blocks < cap ? blocks : cap, 256, 0, st>>>(m->offsets, m->log2_per_level_scale, m->base_resolution, x,
+                                                                                       stencil_M, bound, eps, din_t, grad_table);
+            } else {
+                const uint32_t blocks = (B + 255u) / 256u;
+                sdf_scatter_kernel<<<blocks < cap ? blocks : cap, 256, 0, st>>>(m->offsets, m->log2_per_level_scale, m->base_resolution, x, B, bound,
+                                                                               stencil_M, eps, din_t, grad_table);
+            }
             return acb::launched();
         }
         ACB_SET_MAX_SMEM(sdf_backward_mma_kernel<false>, M_TOTAL);
