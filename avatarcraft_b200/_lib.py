@@ -128,6 +128,10 @@ _SIGNATURES = {
     "ac_fill_uniform": (_I, [_V, ctypes.c_uint64, ctypes.c_uint64, _V]),
     "ac_zero": (_I, [_V, ctypes.c_uint64, _V]),
     "ac_nsr_section_points": (_I, [_V, _V, _V, _U32, _U32, _F, _V, _V]),
+    "ac_nsr_ray_points": (_I, [_V, _V, _V, _V, _U32, _U32, _F, _V, _V, _V]),
+    "ac_nsr_merge_gather": (_I, [_V, _V, _V, _U32, _U32, _V, _V]),
+    "ac_clamp_inplace": (_I, [_V, ctypes.c_uint64, _F, _V]),
+    "ac_nsr_take_sdf": (_I, [_V, ctypes.c_uint64, _V, _V]),
     "ac_nsr_weight_norm_backward": (_I, [ctypes.POINTER(WeightNormLayer), _U32, _V]),
     "ac_nsr_forward_color": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _U32, _V]),
     "ac_nsr_forward_color_bias": (_I, [ctypes.POINTER(NsrModel), _V, _V, _V, _V, _V, _U32, _V]),

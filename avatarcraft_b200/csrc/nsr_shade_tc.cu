@@ -628,6 +628,51 @@ __global__ void __launch_bounds__(256) section_points_kernel(const float* __rest
     P[3 * i] = clampf(x, -bound, bound); P[3 * i + 1] = clampf(y, -bound, bound); P[3 * i + 2] = clampf(zz, -bound, bound);
 }
 
+// Stage kernels of the warped (render_can=False) path, whose points go through the SMPL warp between the stages
+// (models/instant_nsr.py:155-172, :461-475):
+//   ray_points_kernel   z [n,T] (or, z == NULL, the coarse depths near + (far - near) * linspace(0, 1, T) written to z_out) ->
+//                       points o + d z, optionally clamped to +-bound
+//   merge_gather_kernel sdf [n,T] and s_new [n,16] gathered by the merge permutation `order` [n,T+16] (cat_z_vals :466-470)
+__global__ void __launch_bounds__(256) ray_points_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z,
+                                                         const float* __restrict__ near_far, uint32_t n, uint32_t T, float bound,
+                                                         float* __restrict__ z_out, float* __restrict__ P) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * T) return;
+    const uint32_t ray = (uint32_t)(i / T), k = (uint32_t)(i - (size_t)ray * T);
+    float zk;
+    if (z) {
+        zk = z[i];
+    } else {
+        const float near = near_far[2 * ray], far = near_far[2 * ray + 1];
+        zk = near + (far - near) * linspace01((int)k, (int)T);
+        z_out[i] = zk;
+    }
+    Ray r;
+    r.ox = rays_o[3 * ray]; r.oy = rays_o[3 * ray + 1]; r.oz = rays_o[3 * ray + 2];
+    r.dx = rays_d[3 * ray]; r.dy = rays_d[3 * ray + 1]; r.dz = rays_d[3 * ray + 2];
+    float x, y, zz;
+    ray_point(r, zk, x, y, zz);
+    if (bound > 0.f) { x = clampf(x, -bound, bound); y = clampf(y, -bound, bound); zz = clampf(zz, -bound, bound); }
+    P[3 * i] = x; P[3 * i + 1] = y; P[3 * i + 2] = zz;
+}
+__global__ void __launch_bounds__(256) merge_gather_kernel(const float* __restrict__ sdf, const float* __restrict__ s_new, const int32_t* __restrict__ order,
+                                                           uint32_t n, uint32_t T, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t To = T + 16;
+    if (i >= (size_t)n * To) return;
+    const uint32_t ray = (uint32_t)(i / To);
+    const int32_t src = order[i];
+    out[i] = src < (int32_t)T ? sdf[(size_t)ray * T + src] : s_new[(size_t)ray * 16 + (src - (int32_t)T)];
+}
+
+// x[i] = clamp(x[i], -bound, bound) in place (points after the warp, :172) ; sdf[b] = out16[b][0] (the signed distance column)
+__global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ x, size_t n, float bound) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = clampf(x[i], -bound, bound);
+}
+__global__ void __launch_bounds__(256) take_sdf_kernel(const float* __restrict__ out16, size_t B, float* __restrict__ sdf) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (size_t)gridDim.x * blockDim.x) sdf[i] = out16[16 * i];
+}
+
 // Weight-norm backward for one layer: W = g * v / |v|_row  ->  dg = (dW . v) / |v|,  dv = g / |v| * (dW - (dW . v) v / |v|^2).
 // One warp per row; gradients are ADDED to dv / dg (the flat gradient buffer of the optimiser).
 struct WnLayer { const float* dW; const float* v; const float* g; float* dv; float* dg; int rows, cols, ldw; const float* scale; float* db; int db_col; };
@@ -776,6 +821,39 @@ int ac_nsr_section_points(const float* rays_o, const float* rays_d, const float*
     if (n_rays == 0) return AC_OK;
     const size_t total = (size_t)n_rays * n_samples;
     section_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z_vals, n_rays, n_samples, bound, points);
+    return acb::launched();
+}
+
+int ac_nsr_ray_points(const float* rays_o, const float* rays_d, const float* z, const float* near_far, uint32_t n_rays, uint32_t n_samples, float bound,
+                      float* z_out, float* points, void* stream) {
+    if (!rays_o || !rays_d || !points || n_samples < 2 || (!z && (!near_far || !z_out))) return AC_E_INVALID_ARG;
+    if (n_rays == 0) return AC_OK;
+    const size_t total = (size_t)n_rays * n_samples;
+    ray_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, near_far, n_rays, n_samples, bound, z_out, points);
+    return acb::launched();
+}
+
+int ac_clamp_inplace(float* x, uint64_t n, float bound, void* stream) {
+    if (!x || !(bound > 0.f)) return AC_E_INVALID_ARG;
+    if (n == 0) return AC_OK;
+    uint64_t want = (n + 255) / 256, cap = (uint64_t)acb::sm_count() * 16;
+    clamp_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, bound);
+    return acb::launched();
+}
+
+int ac_nsr_take_sdf(const float* out16, uint64_t B, float* sdf, void* stream) {
+    if (!out16 || !sdf) return AC_E_INVALID_ARG;
+    if (B == 0) return AC_OK;
+    uint64_t want = (B + 255) / 256, cap = (uint64_t)acb::sm_count() * 16;
+    take_sdf_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(out16, (size_t)B, sdf);
+    return acb::launched();
+}
+
+int ac_nsr_merge_gather(const float* sdf, const float* s_new, const int32_t* order, uint32_t n_rays, uint32_t T, float* out, void* stream) {
+    if (!sdf || !s_new || !order || !out || T < 1) return AC_E_INVALID_ARG;
+    if (n_rays == 0) return AC_OK;
+    const size_t total = (size_t)n_rays * (T + 16);
+    merge_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sdf, s_new, order, n_rays, T, out);
     return acb::launched();
 }
 

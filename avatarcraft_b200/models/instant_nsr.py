@@ -401,34 +401,55 @@ class NeRFRenderer(nn.Module):
         else:
             near, far = near_far_from_bound(o, d, bound)
             nf = torch.cat([near, far], -1).contiguous()
-        near, far = nf[:, :1], nf[:, 1:]
-        z = (near + (far - near) * torch.linspace(0.0, 1.0, num_steps, device=dev)[None]).contiguous()
+        nf = nf.contiguous()
+        f32 = dict(device=dev, dtype=torch.float32)
+        sp = _lib.stream_ptr
+
+        def ray_points(z_in, T_, clamp):
+            """o + d z as one launch (coarse depths generated in the kernel when z_in is None)."""
+            P_ = torch.empty(n, T_, 3, **f32)
+            z_o = torch.empty(n, T_, **f32) if z_in is None else None
+            _lib.check(L.ac_nsr_ray_points(_lib.ptr(o), _lib.ptr(d), None if z_in is None else _lib.ptr(z_in), _lib.ptr(nf), n, T_,
+                                           float(bound) if clamp else 0.0, None if z_o is None else _lib.ptr(z_o), _lib.ptr(P_), sp()),
+                       "ac_nsr_ray_points")
+            return P_, z_o
+
+        def sdf_of(points, T_):
+            """signed distance [n, T_] of a flat point list: forward_sdf + its first column, both native."""
+            out16 = self.forward_sdf(points.reshape(-1, 3), bound)
+            sd = torch.empty(n, T_, **f32)
+            _lib.check(L.ac_nsr_take_sdf(_lib.ptr(out16), n * T_, _lib.ptr(sd), sp()), "ac_nsr_take_sdf")
+            return sd
         T = num_steps
+        P0, z = ray_points(None, T, False)                                       # coarse depths + un-clamped points (:155-166)
         if upsample_steps > 0:
-            can, _, _, _ = warp_samples_to_canonical(o[:, None] + d[:, None] * z[..., None], None, None, None,
-                                                     DEFAULT_GEO_THRESH, mesh=mesh)
-            sdf = self.forward_sdf(can.clamp(-bound, bound).reshape(-1, 3), bound)[:, 0].reshape(n, T).contiguous()
+            can = warp_samples_to_canonical(P0, None, None, None, DEFAULT_GEO_THRESH, mesh=mesh, product=True)[0]
+            _lib.check(L.ac_clamp_inplace(_lib.ptr(can), can.numel(), float(bound), sp()), "ac_clamp_inplace")
+            sdf = sdf_of(can, T)
             rounds = upsample_steps // 16
             for i in range(rounds):
-                z_new = torch.empty(n, 16, device=dev); bins = torch.empty(n, 16, 2, dtype=torch.int32, device=dev)
-                z_out = torch.empty(n, T + 16, device=dev); order = torch.empty(n, T + 16, dtype=torch.int32, device=dev)
+                z_new = torch.empty(n, 16, **f32); bins = torch.empty(n, 16, 2, dtype=torch.int32, device=dev)
+                z_out = torch.empty(n, T + 16, **f32); order = torch.empty(n, T + 16, dtype=torch.int32, device=dev)
                 _lib.check(L.ac_nsr_upsample_round(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), _lib.ptr(sdf), n, T, float(64 * 2 ** i),
-                                                   _lib.ptr(z_new), _lib.ptr(bins), _lib.ptr(z_out), _lib.ptr(order),
-                                                   _lib.stream_ptr()), "ac_nsr_upsample_round")
+                                                   _lib.ptr(z_new), _lib.ptr(bins), _lib.ptr(z_out), _lib.ptr(order), sp()),
+                           "ac_nsr_upsample_round")
                 if i + 1 < rounds:
-                    p_new = (o[:, None] + d[:, None] * z_new[..., None]).clamp(-bound, bound)        # un-warped (:464-465)
-                    s_new = self.forward_sdf(p_new.reshape(-1, 3), bound)[:, 0].reshape(n, 16)
-                    sdf = torch.gather(torch.cat([sdf, s_new], -1), 1, order.long()).contiguous()
+                    p_new, _ = ray_points(z_new, 16, True)                                           # un-warped, clamped (:464-465)
+                    s_new = sdf_of(p_new, 16)
+                    merged = torch.empty(n, T + 16, **f32)
+                    _lib.check(L.ac_nsr_merge_gather(_lib.ptr(sdf), _lib.ptr(s_new), _lib.ptr(order), n, T, _lib.ptr(merged), sp()),
+                               "ac_nsr_merge_gather")
+                    sdf = merged
                 z, T = z_out, T + 16
-        gaps = torch.cat([z[:, 1:] - z[:, :-1], (far - near) / num_steps], -1)
-        z_mid = torch.cat([z[:, :-1] + 0.5 * gaps[:, :-1], z[:, -1:]], -1)
-        P, _, _, mask = warp_samples_to_canonical(o[:, None] + d[:, None] * z_mid[..., None], None, None, None,
-                                                  DEFAULT_GEO_THRESH, mesh=mesh)
+        # section mid-points, un-clamped (the warp comes first, :198-203): ac_nsr_section_points with an unreachable bound
+        Pm = torch.empty(n * T, 3, **f32)
+        _lib.check(L.ac_nsr_section_points(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), n, T, 3.0e38, _lib.ptr(Pm), sp()), "ac_nsr_section_points")
+        P, mask = warp_samples_to_canonical(Pm.reshape(n, T, 3), None, None, None, DEFAULT_GEO_THRESH, mesh=mesh, product=True)
         if bg_color is not None:
             bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
         return self._launch_render(B, N, o, d, num_steps, upsample_steps, bound, bg_color, None, cos_anneal_ratio,
                                    normal_epsilon_ratio, per_sample_outputs, eikonal_segment,
-                                   alpha_mask=mask.float().contiguous(), z_in=z.contiguous(), pts_in=P.contiguous(),
+                                   alpha_mask=mask, z_in=z.contiguous(), pts_in=P.contiguous(),
                                    near_far_in=nf.contiguous())
 
     def _run_with_grad(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,

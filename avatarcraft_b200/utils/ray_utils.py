@@ -48,10 +48,11 @@ class PosedMesh:
                                           _lib.ptr(self.records), _lib.stream_ptr()), "ac_warp_prepare_mesh")
 
 
-def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMesh = None, return_query=False):
+def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMesh = None, return_query=False, product=False):
     """pts [num_rays, num_samples, 3] (CUDA) -> can_pts, can_dirs, closest, mask -- the reference's return tuple
     (utils/ray_utils.py:62-90).  `can_dirs` is computed like the reference does although nothing downstream
-    reads it (models/instant_nsr.py:203,208)."""
+    reads it (models/instant_nsr.py:203,208).  `product=True` (the render path): only what `run` consumes -- (can_pts
+    [R,S,3], mask [R,S] as the kernel's 0/1 floats) -- and no torch arithmetic."""
     assert pts.dim() == 3 and pts.shape[-1] == 3, 'pts should have shape [num_rays, num_samples, 3]'
     if mesh is None:
         mesh = PosedMesh(verts, faces, T, pts.device)
@@ -83,6 +84,8 @@ def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMe
                                                                    _lib.ptr(closest), _lib.ptr(face), _lib.ptr(dist2), _lib.stream_ptr()),
                    "ac_warp_samples_to_canonical")
     can = can.reshape(R, S, 3)
+    if product:
+        return can, mask.reshape(R, S)
     dirs = can[:, 1:] - can[:, :-1]
     dirs = torch.cat([dirs, dirs[:, -1:]], dim=1)
     dirs = dirs / torch.linalg.norm(dirs, dim=2, keepdim=True)

@@ -197,6 +197,17 @@ int ac_absmax_scale(const float *x, uint32_t n, float target, float *scale_out, 
 /* points [n*T,3] = clamp(o + d * z_mid, +-bound), z_mid = z + (z_next - z) / 2, last sample at its own depth (:186-206). */
 int ac_nsr_section_points(const float *rays_o, const float *rays_d, const float *z_vals, uint32_t n_rays,
                           uint32_t n_samples, float bound, float *points, void *stream);
+/* Stage operators of the warped path (points travel through the SMPL warp between them, models/instant_nsr.py:155-172,461-475):
+ * ac_nsr_ray_points: points [n*T,3] = o + d z (clamped to +-bound when bound > 0); z == NULL generates the coarse depths
+ *   near + (far - near) * linspace(0, 1, T) from near_far [n,2] and also writes them to z_out [n,T].
+ * ac_nsr_merge_gather: out [n,T+16] = cat(sdf [n,T], s_new [n,16]) gathered by the merge permutation `order` (:466-470). */
+int ac_nsr_ray_points(const float *rays_o, const float *rays_d, const float *z, const float *near_far, uint32_t n_rays,
+                      uint32_t n_samples, float bound, float *z_out, float *points, void *stream);
+int ac_nsr_merge_gather(const float *sdf, const float *s_new, const int32_t *order, uint32_t n_rays, uint32_t T, float *out,
+                        void *stream);
+/* x = clamp(x, -bound, bound) in place over n floats (warped points, :172); sdf [B] = column 0 of forward_sdf's [B,16]. */
+int ac_clamp_inplace(float *x, uint64_t n, float bound, void *stream);
+int ac_nsr_take_sdf(const float *out16, uint64_t B, float *sdf, void *stream);
 /* Backward of the weight-norm fold W = g * v / |v|_row (models/instant_nsr.py:555-556,585-586) for up to 5 layers in one
  * launch: dv += ..., dg += ... from dW [rows, ldw] * dW_scale (gradients of the folded weights). */
 typedef struct {
