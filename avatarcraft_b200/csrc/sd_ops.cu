@@ -575,6 +575,33 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     }
 }
 
+// Vectorised variant for C % 4 == 0, (C / G) % 4 == 0 and 256 % (C / 4) == 0 (every Stable-Diffusion shape): a thread owns FOUR
+// consecutive channels (one 16-byte load per pixel, all in one group) and every (C / 4)-th ... pixel of the block's chunk, so
+// all 256 threads are busy whatever C is; partials fold through shared memory into fp64 atomics per (batch, group).
+__global__ void __launch_bounds__(256) gn_stats_vec_kernel(const float* __restrict__ x, int HW, int C, int G, int px_per_block, double* __restrict__ sums) {
+    __shared__ float sh[256][2];
+    const int q = C >> 2, cq = threadIdx.x % q, pr = threadIdx.x / q, rows = 256 / q;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
+    float s = 0.f, ss = 0.f;
+    for (int p = p0 + pr; p < p1; p += rows) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((long long)b * HW + p) * C) + cq);
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+    }
+    sh[threadIdx.x][0] = s; sh[threadIdx.x][1] = ss;
+    __syncthreads();
+    // thread g < G sums the (cpg / 4) quads of its group over the `rows` pixel rows
+    const int qpg = (C / G) >> 2;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double a = 0.0, a2 = 0.0;
+        for (int r = 0; r < rows; ++r)
+            for (int k = 0; k < qpg; ++k) { a += (double)sh[r * q + g * qpg + k][0]; a2 += (double)sh[r * q + g * qpg + k][1]; }
+        atomicAdd(&sums[((long long)b * G + g) * 2], a);
+        atomicAdd(&sums[((long long)b * G + g) * 2 + 1], a2);
+    }
+}
+
 // (sum, sumsq) -> (mean, rstd), in place as floats: stats[b][g] = (mean, rstd).
 __global__ void gn_finalize_kernel(const double* __restrict__ sums, int n, double count, float eps, float* __restrict__ stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -595,6 +622,21 @@ struct NormArgs {          // optional GroupNorm(+SiLU) applied while reading th
 __device__ __forceinline__ void norm8(float (&v)[8], const NormArgs& nm, int b, int c0, int C) {
     if (!nm.stats) return;
     const int cpg = C / nm.G;
+    if ((cpg & 3) == 0) {           // channels c0..c0+3 and c0+4..c0+7 each lie in one group: two statistics, 16-byte parameter loads
+        const float* st = nm.stats + (long long)b * nm.G * 2;
+        const int g0 = c0 / cpg, g1 = (c0 + 4) / cpg;
+        const float m0 = st[2 * g0], r0 = st[2 * g0 + 1], m1 = st[2 * g1], r1 = st[2 * g1 + 1];
+        const float4 ga0 = __ldg(reinterpret_cast<const float4*>(nm.gamma + c0)), ga1 = __ldg(reinterpret_cast<const float4*>(nm.gamma + c0 + 4));
+        const float4 be0 = __ldg(reinterpret_cast<const float4*>(nm.beta + c0)), be1 = __ldg(reinterpret_cast<const float4*>(nm.beta + c0 + 4));
+        const float ga[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+        const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float y = (v[j] - (j < 4 ? m0 : m1)) * (j < 4 ? r0 : r1) * ga[j] + be[j];
+            v[j] = nm.act ? silu(y) : y;
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c0 + j, g = c / cpg;
@@ -797,6 +839,64 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
     }
 }
 
+// Vectorised variants (same shape conditions as gn_stats_vec_kernel): four channels of one group per thread, 16-byte accesses.
+__global__ void __launch_bounds__(256) gn_bwd_reduce_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int act, int HW, int C,
+                                                                int G, int px_per_block, double* __restrict__ sums) {
+    __shared__ float sh[256][2];
+    const int q = C >> 2, cq = threadIdx.x % q, pr = threadIdx.x / q, rows = 256 / q;
+    const int b = blockIdx.y, g = (4 * cq) / (C / G);
+    const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
+    const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq), be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = p0 + pr; p < p1; p += rows) {
+        const long long at = ((long long)b * HW + p) * (long long)q + cq;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + at), dv = __ldg(reinterpret_cast<const float4*>(dy) + at);
+        float xh, dz;
+        dz = gn_dz(xv.x, dv.x, mean, rstd, ga.x, be.x, act, xh) * ga.x; s1 += dz; s2 = fmaf(dz, xh, s2);
+        dz = gn_dz(xv.y, dv.y, mean, rstd, ga.y, be.y, act, xh) * ga.y; s1 += dz; s2 = fmaf(dz, xh, s2);
+        dz = gn_dz(xv.z, dv.z, mean, rstd, ga.z, be.z, act, xh) * ga.z; s1 += dz; s2 = fmaf(dz, xh, s2);
+        dz = gn_dz(xv.w, dv.w, mean, rstd, ga.w, be.w, act, xh) * ga.w; s1 += dz; s2 = fmaf(dz, xh, s2);
+    }
+    sh[threadIdx.x][0] = s1; sh[threadIdx.x][1] = s2;
+    __syncthreads();
+    const int qpg = (C / G) >> 2;
+    for (int gg = threadIdx.x; gg < G; gg += blockDim.x) {
+        double a = 0.0, a2 = 0.0;
+        for (int r = 0; r < rows; ++r)
+            for (int k = 0; k < qpg; ++k) { a += (double)sh[r * q + gg * qpg + k][0]; a2 += (double)sh[r * q + gg * qpg + k][1]; }
+        atomicAdd(&sums[((long long)b * G + gg) * 2], a);
+        atomicAdd(&sums[((long long)b * G + gg) * 2 + 1], a2);
+    }
+}
+__global__ void __launch_bounds__(256) gn_bwd_apply_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int act, long long total4,
+                                                               int HW, int C, int G, const double* __restrict__ sums, const float* __restrict__ add,
+                                                               float* __restrict__ dx32, __half* __restrict__ dx16) {
+    const int q = C >> 2, cpg = C / G;
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    const long long per_image = (long long)HW * q;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_image);
+        const int cq = (int)((t - (long long)b * per_image) % q);
+        const long long sg = ((long long)b * G + (4 * cq) / cpg) * 2;
+        const float mean = stats[sg], rstd = stats[sg + 1];
+        const float m1 = (float)sums[sg] * inv_n, m2 = (float)sums[sg + 1] * inv_n;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq), be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + t), dv = __ldg(reinterpret_cast<const float4*>(dy) + t);
+        float4 o;
+        float xh, dz;
+        dz = gn_dz(xv.x, dv.x, mean, rstd, ga.x, be.x, act, xh) * ga.x; o.x = rstd * (dz - m1 - xh * m2);
+        dz = gn_dz(xv.y, dv.y, mean, rstd, ga.y, be.y, act, xh) * ga.y; o.y = rstd * (dz - m1 - xh * m2);
+        dz = gn_dz(xv.z, dv.z, mean, rstd, ga.z, be.z, act, xh) * ga.z; o.z = rstd * (dz - m1 - xh * m2);
+        dz = gn_dz(xv.w, dv.w, mean, rstd, ga.w, be.w, act, xh) * ga.w; o.w = rstd * (dz - m1 - xh * m2);
+        if (add) { const float4 av = __ldg(reinterpret_cast<const float4*>(add) + t); o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w; }
+        if (dx32) reinterpret_cast<float4*>(dx32)[t] = o;
+        if (dx16) { uint2 h; h.x = tc05::pack_f16x2(o.x, o.y); h.y = tc05::pack_f16x2(o.z, o.w); reinterpret_cast<uint2*>(dx16)[t] = h; }
+    }
+}
+
 // softmax backward: dS = P (dP - sum_row(P dP)) * scale.  One warp per row; P fp16 [rows, ld], dP fp32 [rows, ld] -> dS fp16.
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __half* __restrict__ P, const float* __restrict__ dP, long long rows, int L, long long ld,
                                                           float scale, __half* __restrict__ dS) {
@@ -850,6 +950,9 @@ __global__ void __launch_bounds__(256) conv_s2_dgrad_operand_kernel(const float*
         reinterpret_cast<uint4*>(out)[t] = pack8(v);
     }
 }
+
+// shapes the vectorised GroupNorm kernels take: four channels per thread inside one group, C / 4 lanes dividing the block
+inline bool gn_vec_ok(int C, int G) { return C % 4 == 0 && (C / G) % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
 
 inline int grid_for(long long work, int block, int per_sm) {
     const long long want = (work + block - 1) / block;
@@ -1001,7 +1104,12 @@ int ac_sd_group_norm_stats(const float* x, int B, int HW, int C, int G, float ep
     if (cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * B * G, st) != cudaSuccess) return acb::cuda_fail();
     const int px = HW >= 2048 ? 32 : (HW >= 256 ? 8 : 2);     // enough blocks to fill the machine at every resolution
     dim3 grid((HW + px - 1) / px, B);
-    gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(x, HW, C, G, px, sums_workspace);
+    if (gn_vec_ok(C, G) && ((uintptr_t)x & 15) == 0) {
+        const int pxv = HW >= 16384 ? 128 : (HW >= 2048 ? 64 : (HW >= 256 ? 16 : 4));
+        gn_stats_vec_kernel<<<dim3((HW + pxv - 1) / pxv, B), 256, 0, st>>>(x, HW, C, G, pxv, sums_workspace);
+    } else {
+        gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(x, HW, C, G, px, sums_workspace);
+    }
     int rc = acb::launched();
     if (rc) return rc;
     gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(sums_workspace, B * G, (double)HW * (C / G), eps, stats);
@@ -1053,11 +1161,20 @@ int ac_sd_group_norm_backward(const float* x, const float* dy, int B, int HW, in
         return AC_E_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(sums_workspace, 0, sizeof(double) * 2 * B * G, st) != cudaSuccess) return acb::cuda_fail();
+    const long long total = (long long)B * HW * C;
+    const uintptr_t al = (uintptr_t)x | (uintptr_t)dy | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)add | (uintptr_t)dx32 | ((uintptr_t)dx16 << 1);
+    if (gn_vec_ok(C, G) && (al & 15) == 0) {
+        const int pxv = HW >= 16384 ? 128 : (HW >= 2048 ? 64 : (HW >= 256 ? 16 : 4));
+        gn_bwd_reduce_vec_kernel<<<dim3((HW + pxv - 1) / pxv, B), 256, 0, st>>>(x, dy, stats, gamma, beta, silu_act, HW, C, G, pxv, sums_workspace);
+        if (int rc = acb::launched()) return rc;
+        gn_bwd_apply_vec_kernel<<<grid_for(total / 4, 256, 16), 256, 0, st>>>(x, dy, stats, gamma, beta, silu_act, total / 4, HW, C, G, sums_workspace,
+                                                                               add, dx32, reinterpret_cast<__half*>(dx16));
+        return acb::launched();
+    }
     const int px = HW >= 2048 ? 32 : (HW >= 256 ? 8 : 2);
     dim3 grid((HW + px - 1) / px, B);
     gn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(x, dy, stats, gamma, beta, silu_act, HW, C, G, px, sums_workspace);
     if (int rc = acb::launched()) return rc;
-    const long long total = (long long)B * HW * C;
     gn_bwd_apply_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(x, dy, stats, gamma, beta, silu_act, total, HW, C, G, sums_workspace, add, dx32,
                                                                    reinterpret_cast<__half*>(dx16));
     return acb::launched();
