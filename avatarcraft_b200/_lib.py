@@ -75,7 +75,7 @@ class NsrRenderArgs(ctypes.Structure):
                 ("weights", ctypes.c_void_p), ("pts_color", ctypes.c_void_p), ("pts_alpha", ctypes.c_void_p),
                 ("z_vals", ctypes.c_void_p),
                 ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64),
-                ("c0_ray_bias", ctypes.c_void_p)]
+                ("c0_ray_bias", ctypes.c_void_p), ("opacity_only", ctypes.c_uint32)]
 
 
 class NsrShadeArgs(ctypes.Structure):

@@ -445,8 +445,9 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             cin[0] = px; cin[1] = py; cin[2] = pz;
             cin[21] = cin[22] = cin[23] = 0.f;
             __syncwarp();                                // fd[] consumed before the next block overwrites it
-            float col[3];
-            group_color_eval<SLOT, VIEW>(g, cin, col, VIEW ? p.a.c0_ray_bias + 64 * (size_t)ray : nullptr);
+            float col[3] = {0.f, 0.f, 0.f};
+            if (!p.a.opacity_only)                       // launch-uniform: the trainer's frozen-net pass only reads weight_sum
+                group_color_eval<SLOT, VIEW>(g, cin, col, VIEW ? p.a.c0_ray_bias + 64 * (size_t)ray : nullptr);
             const float nx = cin[3], ny = cin[4], nz = cin[5];
             const float cosv = r.dx * nx + r.dy * ny + r.dz * nz;
             const float it = -(softplus100(-cosv * 0.5f + 0.5f) * (1.0f - car) + softplus100(-cosv) * car);

@@ -284,14 +284,15 @@ class NeRFRenderer(nn.Module):
     def run(self, rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio=1.0,
             normal_epsilon_ratio=1.0, render_can=True, verts=None, faces=None, Ts=None,
             perturb_overwrite: bool = False, use_mesh_guide: bool = True, jitter=None, per_sample_outputs=True,
-            eikonal_segment=0, z_override=None):
+            eikonal_segment=0, z_override=None, opacity_only=False):
         """Same contract as the reference (models/instant_nsr.py:133-299): rays [B=1,N,3] ->
         (depth [1,N], weights [N,T], weights_sum [N,1], image [1,N,3], normal_map [N,3],
          gradient_error, curvature_error, color [N,T,3], alpha [N,T], z_vals [N,T]).
         `jitter` ([N,num_steps] in [0,1)) overrides the training-time torch.rand draw (:162);
         `per_sample_outputs=False` skips the four [N,T,...] stores (they are then None);
         `eikonal_segment=k` returns one eikonal mean per k consecutive rays (a [ceil(N/k)] tensor);
-        `z_override` ([N,T], autograd path only) replaces the sampled depths (parity tests)."""
+        `z_override` ([N,T], autograd path only) replaces the sampled depths (parity tests);
+        `opacity_only=True` (inference launch) skips the colour network: image / pts_color are then meaningless."""
         if not render_can:
             return self._run_warped(rays_o, rays_d, num_steps, bound, upsample_steps, bg_color, cos_anneal_ratio,
                                     normal_epsilon_ratio, verts, faces, Ts, use_mesh_guide, per_sample_outputs, eikonal_segment)
@@ -315,11 +316,11 @@ class NeRFRenderer(nn.Module):
         if bg_color is not None:
             bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
         return self._launch_render(B, N, rays_o, rays_d, num_steps, upsample_steps, bound, bg_color, jitter, cos_anneal_ratio,
-                                   normal_epsilon_ratio, per_sample_outputs, eikonal_segment)
+                                   normal_epsilon_ratio, per_sample_outputs, eikonal_segment, opacity_only=opacity_only)
 
     def _launch_render(self, B, N, rays_o, rays_d, num_steps, upsample_steps, bound, bg_color, jitter, cos_anneal_ratio,
                        normal_epsilon_ratio, per_sample_outputs, eikonal_segment, alpha_mask=None, z_in=None, pts_in=None,
-                       near_far_in=None):
+                       near_far_in=None, opacity_only=False):
         """One ac_nsr_render launch; returns the reference's 10-tuple."""
         n, dev = rays_o.shape[0], rays_o.device
         T = num_steps + upsample_steps
@@ -336,9 +337,9 @@ class NeRFRenderer(nn.Module):
         L = _lib.lib()
         ws_bytes = int(L.ac_nsr_render_workspace_bytes(n))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        ray_bias = self._viewdir_bias(rays_d) if getattr(self, "use_viewdirs", False) else None
+        ray_bias = self._viewdir_bias(rays_d) if getattr(self, "use_viewdirs", False) and not opacity_only else None
         a = _lib.NsrRenderArgs(
-            c0_ray_bias=None if ray_bias is None else ray_bias.data_ptr(),
+            c0_ray_bias=None if ray_bias is None else ray_bias.data_ptr(), opacity_only=int(bool(opacity_only)),
             rays_o=rays_o.data_ptr(), rays_d=rays_d.data_ptr(),
             bg_color=None if bg_color is None else bg_color.data_ptr(),
             jitter=None if jitter is None else jitter.data_ptr(),

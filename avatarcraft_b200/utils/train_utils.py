@@ -136,6 +136,10 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
     # parameters only change at optimizer.step(), so the sampled depths of every patch (and the frozen net's opacities) are
     # the same whether computed patch by patch (the reference, stylize.py:153-181) or in one launch -- and a 4096-ray
     # sampling launch is latency bound (one ray per warp), 16 of them cost 8x one 65 536-ray launch.
+    if not patches:                       # more ranks than rays: this rank only joins the collectives
+        optimizer.all_reduce()
+        optimizer.step()
+        return _LazyStats(stats)
     if len(patches) == 1:
         idx = None
         o_all, d_all = rays_o[patches[0][0]:patches[0][1]].float().contiguous(), rays_d[patches[0][0]:patches[0][1]].float().contiguous()
@@ -157,7 +161,8 @@ def native_patch_step(net_style, net_gt, optimizer, rays_o, rays_d, pixel_grad, 
     wsum_gt_all = None
     if use_opacity and net_gt is not None:
         with torch.no_grad():
-            wsum_gt_all = net_gt.run(o_all[None], d_all[None], num_steps, bound, upsample_steps, None, 1.0, 0.0, per_sample_outputs=False)[2].reshape(-1)
+            wsum_gt_all = net_gt.run(o_all[None], d_all[None], num_steps, bound, upsample_steps, None, 1.0, 0.0, per_sample_outputs=False,
+                                     opacity_only=True)[2].reshape(-1)
     at = 0
     for ip, (s, e, scale) in enumerate(patches):
         m = e - s

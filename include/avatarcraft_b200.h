@@ -277,6 +277,9 @@ typedef struct ac_nsr_render_args {
     /* use_viewdirs=True (models/instant_nsr.py:564-569,646-650): NULL, or [n_rays,64] = the contribution of the ray direction's
      * 16 SH coefficients to colour layer 0 (ac_nsr_viewdir_bias); the packed model then holds the other 21 columns. */
     const float *c0_ray_bias;
+    /* non-zero: skip the colour network (rgb / pts_color are then meaningless; depth, weight_sum, normal, weights, alpha,
+     * eikonal are unchanged) -- the opacity target of the trainer's frozen net only needs weight_sum (stylize.py:177-181). */
+    uint32_t opacity_only;
 } ac_nsr_render_args;
 
 uint64_t ac_nsr_render_workspace_bytes(uint32_t n_rays);

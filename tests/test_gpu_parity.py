@@ -432,3 +432,16 @@ def test_use_viewdirs_render_against_reference_fixture():
     h = torch.cat([x, sh, n, feat[:, 1:]], -1)
     c_ref = torch.sigmoid(torch.relu(torch.relu(h @ w[0].t()) @ w[1].t()) @ w[2].t())
     np.testing.assert_allclose(c_dev.cpu().numpy(), c_ref.cpu().numpy(), atol=5e-6)
+
+
+def test_opacity_only_launch_keeps_everything_but_the_colour():
+    """ac_nsr_render_args.opacity_only skips the colour network (the trainer's frozen-net pass reads weight_sum only): depth,
+    weight_sum, normal map, depths and eikonal are bit-identical to the full launch."""
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    o, d = syn.pinhole_rays(syn.orbit_pose(30.0), 64, 64)
+    full = _render(net, o, d, 64, 64)
+    fast = _render(net, o, d, 64, 64, opacity_only=True)
+    for i in (0, 1, 2, 4, 8, 9):                       # depth, weights, weight_sum, normal map, alpha, z
+        assert torch.equal(full[i], fast[i]), i
+    assert float(full[5]) == float(fast[5])
