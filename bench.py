@@ -317,8 +317,8 @@ def run_ours(args):
                          "note": "algorithmic gather bytes (no reuse) per SURVEY.md 8(d); gathers are served from L1/L2, "
                                  "so frac may exceed 1 -- see traffic (ncu dram bytes) and profiles/",
                          "mlp_tflops": tflops, "mlp_frac_of_bf16_peak": tflops / pk["bf16_tflops"],
-                         "measured_limiter": "L1 data pipe: l1tex__throughput 77 % of peak, issue slots 56 %, DRAM 0.06 % "
-                                             "(ncu, profiles/r01f_render_kernel_tc_v5b.md)"},
+                         "measured_limiter": "L1 data pipe: l1tex__throughput 76 % of peak, data-stage wavefronts 71 %, issue slots 51 %, "
+                                             "tensor pipe 3.7 %, DRAM 79 MB per launch (ncu, profiles/r02p_render_kernel_tc.md)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": cpu_threads(), "kind": cpu_reference_kind(),
                              "sample": f"{CPU_SAMPLE_RAYS}-ray batch (central rows) of the same frame, {cpu_dt:.1f} s"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 2 * RAYS_PER_FRAME * 12,
