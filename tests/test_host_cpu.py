@@ -86,3 +86,27 @@ def test_models_neus_matches_reference_fixture():
                           "inside_sphere"}
         for k in ("color_fine", "weight_sum", "weights", "gradient_error", "cdf_fine", "s_val"):
             np.testing.assert_allclose(r[k].detach().numpy(), g[f"{tag}.{k}"], atol=2e-5, rtol=1e-4, err_msg=f"{tag}.{k}")
+
+
+def test_reference_import_paths_resolve_to_the_package():
+    """The reference's entry points import `models.instant_nsr`, `models.neus`, `encoder`, `raymarching`, `utils.render_utils`
+    (render_canonical.py:22, stylize.py:26, encoder/__init__.py): with the repo root on sys.path the same statements load this
+    package's modules (alias modules at the repo root)."""
+    import importlib
+    import subprocess
+    import sys
+    from tests.util import ROOT
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from models.instant_nsr import NeRFNetwork, NeRFRenderer\n"
+            "from models.neus import build_neus, NeuSRenderer\n"
+            "from models.diffusion import StableDiffusion\n"
+            "from encoder import get_encoder\n"
+            "from encoder.hashencoder import HashEncoder\n"
+            "from encoder.shencoder import SHEncoder\n"
+            "import raymarching, utils.render_utils as ru, utils.ray_utils as rays, utils.constant as c\n"
+            "import avatarcraft_b200.models.instant_nsr as impl\n"
+            "assert NeRFNetwork is impl.NeRFNetwork and sys.modules['models.instant_nsr'] is impl\n"
+            "assert hasattr(ru, 'render_instantnsr_naive') and hasattr(rays, 'warp_samples_to_canonical') and hasattr(raymarching, 'march_rays_train')\n"
+            "print('ok')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
