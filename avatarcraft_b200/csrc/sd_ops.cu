@@ -697,6 +697,22 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
     }
 }
 
+// The ks = 1 case of im2col_kernel on its own (the producer of every implicit-GEMM convolution and projection: GroupNorm(+SiLU)
+// on the fly, fp32 NHWC -> fp16 NHWC) for C % 8 == 0: one 8-channel chunk per thread, no tap / stride / padding index math.
+__global__ void __launch_bounds__(256) norm_cast_kernel(const float* __restrict__ x, long long total_chunks, int HW, int C, const NormArgs nm,
+                                                        __half* __restrict__ out) {
+    const int chunks = C >> 3;
+    const long long per_image = (long long)HW * chunks;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total_chunks; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_image);
+        const int ch = (int)((t - (long long)b * per_image) % chunks);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * t), c4 = __ldg(reinterpret_cast<const float4*>(x) + 2 * t + 1);
+        float v[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
+        norm8(v, nm, b, ch * 8, C);
+        reinterpret_cast<uint4*>(out)[t] = pack8(v);
+    }
+}
+
 // LayerNorm over the last axis, fp32 [M,C] -> fp16 [M,C]; one warp per row, two passes over registers/L1.
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, __half* __restrict__ out) {
@@ -954,6 +970,10 @@ __global__ void __launch_bounds__(256) conv_s2_dgrad_operand_kernel(const float*
 // shapes the vectorised GroupNorm kernels take: four channels per thread inside one group, C / 4 lanes dividing the block
 inline bool gn_vec_ok(int C, int G) { return C % 4 == 0 && (C / G) % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
 
+// pixels per block of the vectorised GroupNorm reductions: ~512 blocks per image whatever the resolution -- enough to fill the
+// machine, few enough that the fp64 atomics onto the 2 G group sums (one pair per block and group) do not queue up
+inline int gn_vec_pixels(int HW) { const int p = HW / 512; return p < 16 ? 16 : (p > 512 ? 512 : p); }
+
 inline int grid_for(long long work, int block, int per_sm) {
     const long long want = (work + block - 1) / block;
     const long long cap = (long long)acb::sm_count() * per_sm;
@@ -1105,7 +1125,7 @@ int ac_sd_group_norm_stats(const float* x, int B, int HW, int C, int G, float ep
     const int px = HW >= 2048 ? 32 : (HW >= 256 ? 8 : 2);     // enough blocks to fill the machine at every resolution
     dim3 grid((HW + px - 1) / px, B);
     if (gn_vec_ok(C, G) && ((uintptr_t)x & 15) == 0) {
-        const int pxv = HW >= 16384 ? 128 : (HW >= 2048 ? 64 : (HW >= 256 ? 16 : 4));
+        const int pxv = gn_vec_pixels(HW);
         gn_stats_vec_kernel<<<dim3((HW + pxv - 1) / pxv, B), 256, 0, st>>>(x, HW, C, G, pxv, sums_workspace);
     } else {
         gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * C, st>>>(x, HW, C, G, px, sums_workspace);
@@ -1124,6 +1144,11 @@ int ac_sd_im2col_f16(const float* x, int B, int Hs, int Ws, int C, int ksize, in
     NormArgs nm; nm.stats = gn_stats; nm.gamma = gn_gamma; nm.beta = gn_beta; nm.G = gn_groups > 0 ? gn_groups : 1; nm.act = gn_silu;
     const int Cp = (C + 7) / 8 * 8;
     const long long total = (long long)B * Ho * Wo * ksize * ksize * (Cp / 8);
+    if (ksize == 1 && stride == 1 && pad == 0 && !upsample2x && Ho == Hs && Wo == Ws && (C & 7) == 0 && ((uintptr_t)x & 15) == 0 &&
+        (!gn_stats || (((uintptr_t)gn_gamma | (uintptr_t)gn_beta) & 15) == 0)) {
+        norm_cast_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, total, Hs * Ws, C, nm, reinterpret_cast<__half*>(out));
+        return acb::launched();
+    }
     im2col_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, B, Hs, Ws, C, Cp, ksize, stride, pad, upsample2x, Ho, Wo, nm,
                                                                              reinterpret_cast<__half*>(out));
     return acb::launched();
@@ -1164,7 +1189,7 @@ int ac_sd_group_norm_backward(const float* x, const float* dy, int B, int HW, in
     const long long total = (long long)B * HW * C;
     const uintptr_t al = (uintptr_t)x | (uintptr_t)dy | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)add | (uintptr_t)dx32 | ((uintptr_t)dx16 << 1);
     if (gn_vec_ok(C, G) && (al & 15) == 0) {
-        const int pxv = HW >= 16384 ? 128 : (HW >= 2048 ? 64 : (HW >= 256 ? 16 : 4));
+        const int pxv = gn_vec_pixels(HW);
         gn_bwd_reduce_vec_kernel<<<dim3((HW + pxv - 1) / pxv, B), 256, 0, st>>>(x, dy, stats, gamma, beta, silu_act, HW, C, G, pxv, sums_workspace);
         if (int rc = acb::launched()) return rc;
         gn_bwd_apply_vec_kernel<<<grid_for(total / 4, 256, 16), 256, 0, st>>>(x, dy, stats, gamma, beta, silu_act, total / 4, HW, C, G, sums_workspace,

@@ -31,4 +31,4 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    main()               # no sys.exit: __graft_entry__.build() runs this file through runpy
