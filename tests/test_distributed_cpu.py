@@ -30,6 +30,12 @@ def _loss(model, x, start, end, scale):
     return (y * torch.arange(start, end, dtype=torch.float32)[:, None]).sum() + scale * 7.0 * (y ** 2).mean()
 
 
+def _free_port():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, n, bs, ref_grads, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -60,7 +66,7 @@ def test_two_rank_patch_step_equals_single_process(n, bs):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n, bs, ref, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -91,7 +97,7 @@ def _cfg_worker(rank, world, port, q):
         refused = True
     assert refused
     g = sd.pixel_gradient(emb, rgb, 16, 16, guidance_scale=100, seed=11)
-    q.put((rank, g))
+    q.put((rank, g.numpy()))              # by value: a tensor's shared-memory handle dies with this process
     dist.destroy_process_group()
 
 
@@ -109,10 +115,11 @@ def test_cfg_pair_split_over_two_ranks_equals_single_process():
     want = sd.pixel_gradient(emb, rgb, 16, 16, guidance_scale=100, seed=11)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_cfg_worker, args=(r, 2, 29571, q)) for r in range(2)]
+    port = _free_port()
+    ps = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(2))
+    got = {r: torch.from_numpy(g) for r, g in (q.get(timeout=300) for _ in range(2))}
     for p in ps:
         p.join(timeout=60)
     assert torch.equal(got[0], got[1]) and torch.allclose(got[0], want, atol=1e-7) and float(want.abs().max()) > 0
@@ -135,7 +142,7 @@ def _shard_render_worker(rank, world, port, q):
     full = render_rays_sharded(fake_render, o, d, rank, world)
     odd = render_rays_sharded(fake_render, o[:7], d[:7], rank, world)        # 7 rays on 2 ranks: padded, gathered, trimmed
     assert torch.equal(odd, o[:7] * 2.0 + 1.0)
-    q.put((rank, full, calls[:1]))
+    q.put((rank, full.numpy(), calls[:1]))
     dist.destroy_process_group()
 
 
@@ -145,10 +152,11 @@ def test_pass1_ray_sharding_reassembles_the_whole_image():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_shard_render_worker, args=(r, 2, 29573, q)) for r in range(2)]
+    port = _free_port()
+    ps = [ctx.Process(target=_shard_render_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    got = {r: (img, calls) for r, img, calls in (q.get(timeout=120) for _ in range(2))}
+    got = {r: (torch.from_numpy(img), calls) for r, img, calls in (q.get(timeout=300) for _ in range(2))}
     for p in ps:
         p.join(timeout=60)
     want = torch.arange(24.0).reshape(8, 3) * 2.0 + 1.0
@@ -174,7 +182,7 @@ def _masked_mean_worker(rank, world, port, q):
     (eik * masked_mean_share(relax.sum())).backward()
     g = w.grad.clone()
     dist.all_reduce(g)
-    q.put((rank, g, float(relax.sum())))
+    q.put((rank, g.numpy(), float(relax.sum())))
     dist.destroy_process_group()
 
 
@@ -190,10 +198,11 @@ def test_split_patch_masked_eikonal_equals_single_process():
     ((relax * (w * 3.0 - 1.0) ** 2).sum() / (relax.sum() + 1e-5)).backward()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_masked_mean_worker, args=(r, 2, 29577, q)) for r in range(2)]
+    port = _free_port()
+    ps = [ctx.Process(target=_masked_mean_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    got = {r: (g, c) for r, g, c in (q.get(timeout=120) for _ in range(2))}
+    got = {r: (torch.from_numpy(g), c) for r, g, c in (q.get(timeout=300) for _ in range(2))}
     for p in ps:
         p.join(timeout=60)
     assert got[0][1] != got[1][1]                                               # the two halves do have different mask counts
