@@ -528,6 +528,23 @@ __global__ void __launch_bounds__(kThreadsB, 1) sdf_backward_mma_kernel(const fl
     if (warp == 0) tc05::tmem_dealloc<512>(tmem_base);
 }
 
+// The two x-corners of a cell are neighbouring table entries more often than not (slot, slot + 1 on a dense level; s, s ^ 1 on
+// a hashed level whenever the cell's x index is even): when the pair also starts on a 16-byte boundary, ONE
+// red.global.add.v4.f32 carries both corners' contributions -- one packet on the SM's reduction path instead of two.  (With the
+// reference's offsets table the hashed-level pairs are aligned iff the gradient table starts 8 bytes past a 16-byte boundary,
+// which is where utils/optim.FlatAdam places it; any other placement just takes the two-packet path more often.)
+__device__ __forceinline__ void red_corner_pair(float2* __restrict__ dst, uint32_t slot0, uint32_t slot1, float ax, float ay, float bx, float by) {
+    const uint32_t lo = slot0 < slot1 ? slot0 : slot1;
+    float2* p = dst + lo;
+    if ((slot0 ^ slot1) == 1u && (reinterpret_cast<uintptr_t>(p) & 15u) == 0u) {
+        const bool first = lo == slot0;
+        atomicAdd(reinterpret_cast<float4*>(p), first ? make_float4(ax, ay, bx, by) : make_float4(bx, by, ax, ay));
+    } else {
+        atomicAdd(dst + slot0, make_float2(ax, ay));
+        atomicAdd(dst + slot1, make_float2(bx, by));
+    }
+}
+
 // The table scatter of the split backward: grad_table[corner] += w_corner * din (hashencoder.cu:223-308) for every point and
 // level.  A block takes 256 consecutive points; warp w handles levels 2w and 2w+1 of all of them, 32 consecutive points per
 // instruction (consecutive samples of a ray: the din_t reads are coalesced).  No shared-memory tiles, full occupancy: this
@@ -589,26 +606,31 @@ __global__ void __launch_bounds__(256) sdf_scatter_kernel(const int32_t* __restr
                 if (heads != full) {
                     const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
                     emit = inr && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+                    // shuffles share the L1 data pipe with the reductions (ncu: half of its wavefronts): run only the scan
+                    // steps the warp's longest run needs -- one or two at the fine levels instead of five
+                    const int longest = (int)__reduce_max_sync(full, (unsigned)(lane - start));
+#pragma unroll 1
+                    for (int d = 1; d <= longest; d <<= 1) {
+                        const bool take = lane - d >= start;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        float a = val[q];
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const float t = __shfl_up_sync(full, a, d);
-                            if (lane - d >= start) a += t;
+                        for (int q = 0; q < 16; ++q) {
+                            const float t = __shfl_up_sync(full, val[q], d);
+                            if (take) val[q] += t;
                         }
-                        val[q] = a;
                     }
                 }
                 if (!emit) continue;
                 float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t cx = ix + (c & 1), cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
-                    uint32_t slot;
-                    if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
-                    else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
-                    atomicAdd(dst + slot, make_float2(val[2 * c], val[2 * c + 1]));
+                for (int c = 0; c < 8; c += 2) {                 // corner pairs (x, x + 1) at fixed (y, z)
+                    const uint32_t cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
+                    uint32_t s0, s1;
+                    if (m.hashed == 0u) { s0 = ix + cy * m.res1 + cz * m.res1 * m.res1; s1 = s0 + 1u; }
+                    else {
+                        const uint32_t hyz = (cy * 2654435761u) ^ (cz * 805459861u);
+                        s0 = wrap_slot(ix ^ hyz, m); s1 = wrap_slot((ix + 1u) ^ hyz, m);
+                    }
+                    red_corner_pair(dst, s0, s1, val[2 * c], val[2 * c + 1], val[2 * c + 2], val[2 * c + 3]);
                 }
             }
         }
@@ -676,15 +698,17 @@ __global__ void __launch_bounds__(256) sdf_scatter_stencil_kernel(const int32_t*
                 if (heads != full) {
                     const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
                     emit = inr && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+                    // shuffles share the L1 data pipe with the reductions (ncu: half of its wavefronts): run only the scan
+                    // steps the warp's longest run needs -- one or two at the fine levels instead of five
+                    const int longest = (int)__reduce_max_sync(full, (unsigned)(lane - start));
+#pragma unroll 1
+                    for (int d = 1; d <= longest; d <<= 1) {
+                        const bool take = lane - d >= start;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        float a = val[q];
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const float t = __shfl_up_sync(full, a, d);
-                            if (lane - d >= start) a += t;
+                        for (int q = 0; q < 16; ++q) {
+                            const float t = __shfl_up_sync(full, val[q], d);
+                            if (take) val[q] += t;
                         }
-                        val[q] = a;
                     }
                     if (st == 7u && head) emit = false;          // a zero-weight copy that is a run of its own has nothing to add
                 } else if (st == 7u) {
@@ -693,12 +717,15 @@ __global__ void __launch_bounds__(256) sdf_scatter_stencil_kernel(const int32_t*
                 if (!emit) continue;
                 float2* __restrict__ dst = reinterpret_cast<float2*>(grad_table) + m.offset;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t cx = ix + (c & 1), cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
-                    uint32_t slot;
-                    if (m.hashed == 0u) slot = cx + cy * m.res1 + cz * m.res1 * m.res1;
-                    else slot = wrap_slot(cx ^ (cy * 2654435761u) ^ (cz * 805459861u), m);
-                    atomicAdd(dst + slot, make_float2(val[2 * c], val[2 * c + 1]));
+                for (int c = 0; c < 8; c += 2) {                 // corner pairs (x, x + 1) at fixed (y, z)
+                    const uint32_t cy = iy + ((c >> 1) & 1), cz = iz + ((c >> 2) & 1);
+                    uint32_t s0, s1;
+                    if (m.hashed == 0u) { s0 = ix + cy * m.res1 + cz * m.res1 * m.res1; s1 = s0 + 1u; }
+                    else {
+                        const uint32_t hyz = (cy * 2654435761u) ^ (cz * 805459861u);
+                        s0 = wrap_slot(ix ^ hyz, m); s1 = wrap_slot((ix + 1u) ^ hyz, m);
+                    }
+                    red_corner_pair(dst, s0, s1, val[2 * c], val[2 * c + 1], val[2 * c + 2], val[2 * c + 3]);
                 }
             }
         }

@@ -34,10 +34,17 @@ class FlatAdam:
         if any(p.dtype != torch.float32 or p.device != dev for p in self.params):
             raise RuntimeError("FlatAdam needs fp32 parameters on one device")
         # every parameter starts on a 16 B boundary so views stay vector-aligned
+        # ... except tables of float2 entries (the hash grid): they start 8 bytes past a 16-byte boundary, where neighbouring
+        # corner entries of the reference's offsets table pair up into aligned 16-byte blocks, so the training scatter can
+        # merge two reductions into one red.global.add.v4.f32 (csrc/nsr_train_tc.cu: red_corner_pair)
         self._spans, at = [], 0
         for p in self.params:
+            at = (at + 3) // 4 * 4
+            if p.dim() == 2 and p.shape[1] == 2 and p.numel() >= (1 << 16):
+                at += 2
             self._spans.append((at, p.numel()))
-            at += (p.numel() + 3) // 4 * 4
+            at += p.numel()
+        at = (at + 3) // 4 * 4
         self.numel = at
         self.flat_param = torch.zeros(at, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(at, device=dev, dtype=torch.float32)
