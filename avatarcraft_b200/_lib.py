@@ -75,7 +75,7 @@ class NsrRenderArgs(ctypes.Structure):
                 ("weights", ctypes.c_void_p), ("pts_color", ctypes.c_void_p), ("pts_alpha", ctypes.c_void_p),
                 ("z_vals", ctypes.c_void_p),
                 ("eikonal", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64),
-                ("c0_ray_bias", ctypes.c_void_p), ("opacity_only", ctypes.c_uint32)]
+                ("c0_ray_bias", ctypes.c_void_p), ("opacity_only", ctypes.c_uint32), ("skip_masked", ctypes.c_uint32)]
 
 
 class NsrShadeArgs(ctypes.Structure):
@@ -144,6 +144,7 @@ _SIGNATURES = {
     "ac_warp_samples_to_canonical": (_I, [_V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
     "ac_warp_samples_to_canonical_rays": (_I, [_V, _U32, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
     "ac_warp_samples_to_canonical_ordered": (_I, [_V, _V, _U32, _V, _U32, _V, _F, _V, _V, _V, _V, _V, _V]),
+    "ac_warp_samples_to_canonical_masked": (_I, [_V, _V, _U32, _V, _U32, _V, _F, _V, _V, _V]),
     "ac_warp_query_keys": (_I, [_V, _U32, _V, _U32, _F, _V, _V]),
     "ac_mesh_guided_near_far": (_I, [_V, _V, _U32, _V, _U32, _F, _F, _V, _V]),
     "ac_march_rays_train": (_I, [_V, _V, _V, _F, _I, _F, _U32, _U32, _U32, _V, _V, _V, _V, _V, _U32, _V]),

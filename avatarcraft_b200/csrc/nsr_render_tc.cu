@@ -390,7 +390,14 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
         float acc_w = 0.f, acc_d = 0.f, eik_num = 0.f, eik_den = 0.f;
         for (int k0 = 0; k0 < Ttot; k0 += 32) {
             const int nS = min(32, Ttot - k0);
-            for (int q0 = 0; q0 < 6 * nS; q0 += 32) {
+            // skip_masked: when the warp's mask is zero on all 32 samples of this block for all four rays of the group (one
+            // barrier with an OR reduction), nothing is evaluated -- every alpha of the block is zero anyway
+            bool dead = false;
+            if (p.a.skip_masked && p.a.alpha_mask) {
+                const bool on = k0 + lane < Ttot && p.a.alpha_mask[(size_t)ray * Ttot + k0 + lane] != 0.0f;
+                dead = !tc05::named_bar_or(g.bar_id, 128, on);
+            }
+            for (int q0 = 0; !dead && q0 < 6 * nS; q0 += 32) {
                 const int q = min(q0 + lane, 6 * nS - 1);
                 const int sI = q / 6, dir = q - 6 * sI;
                 const int k = k0 + sI;
@@ -427,15 +434,17 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
                 ray_point(r, k < Ttot - 1 ? zk + 0.5f * delta : zk, px, py, pz);
             }
             px = clampf(px, -bound, bound); py = clampf(py, -bound, bound); pz = clampf(pz, -bound, bound);
-            float cin[24], sdf0, gn;
-            {
+            float cin[24], sdf0 = 0.f, gn = 1.0f;
+            if (!dead) {
                 float o16[16];
                 group_sdf_eval<SLOT, true>(g, table, lv, bound, px, py, pz, o16);
                 sdf0 = o16[0];
 #pragma unroll
                 for (int q = 0; q < 15; ++q) cin[6 + q] = o16[1 + q];
             }
-            {
+            if (dead) {
+                cin[3] = cin[4] = cin[5] = 0.f;
+            } else {
                 const float* f6 = fd + 6 * (k - k0);
                 const float gx = 0.5f * (f6[0] - f6[1]) / eps, gy = 0.5f * (f6[2] - f6[3]) / eps, gz = 0.5f * (f6[4] - f6[5]) / eps;
                 gn = sqrtf(gx * gx + gy * gy + gz * gz);
@@ -446,7 +455,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             cin[21] = cin[22] = cin[23] = 0.f;
             __syncwarp();                                // fd[] consumed before the next block overwrites it
             float col[3] = {0.f, 0.f, 0.f};
-            if (!p.a.opacity_only)                       // launch-uniform: the trainer's frozen-net pass only reads weight_sum
+            if (!p.a.opacity_only && !dead)              // launch-uniform: the trainer's frozen-net pass only reads weight_sum
                 group_color_eval<SLOT, VIEW>(g, cin, col, VIEW ? p.a.c0_ray_bias + 64 * (size_t)ray : nullptr);
             const float nx = cin[3], ny = cin[4], nz = cin[5];
             const float cosv = r.dx * nx + r.dy * ny + r.dz * nz;
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             if (p.a.alpha_mask) alpha = alpha * p.a.alpha_mask[(size_t)ray * Ttot + k];
             if (!live) alpha = 0.0f;
             const float pn = sqrtf(px * px + py * py + pz * pz);
-            if (live && pn < 1.2f) { eik_num += (gn - 1.0f) * (gn - 1.0f); eik_den += 1.0f; }
+            if (live && !dead && pn < 1.2f) { eik_num += (gn - 1.0f) * (gn - 1.0f); eik_den += 1.0f; }
 
             float blk;
             const float tr = warp_excl_prod(live ? (1.0f - alpha + 1e-7f) : 1.0f, lane, blk) * carry;

@@ -37,6 +37,14 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// barrier + OR of a predicate over the `threads` participants (every one of them gets the result)
+__device__ __forceinline__ bool named_bar_or(uint32_t id, uint32_t threads, bool pred) {
+    uint32_t out;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(out) : "r"((uint32_t)pred), "r"(id), "r"(threads) : "memory");
+    return out != 0u;
+}
+
 // ---- TMEM allocation (one full warp executes these) ---------------------------------------
 template <uint32_t COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {

@@ -216,11 +216,16 @@ __device__ __forceinline__ void search_boxes(const MeshView& m, float px, float 
 }
 
 // Full query: greedy descent to the nearest leaf box for a tight first bound, then the exact search.
-__device__ __forceinline__ void closest_full(const MeshView& m, float px, float py, float pz, Best& best) {
+// `limit2` < inf: only triangles closer than sqrt(limit2) are of interest (the caller masks everything else out): the bound
+// starts there, and a point with nothing inside it comes back with best.f = none after a handful of box tests -- these far
+// points are the expensive ones of the unbounded search.  Points inside the limit get the unbounded search's answer (same
+// candidate set, same tie rule).
+__device__ __forceinline__ void closest_full(const MeshView& m, float px, float py, float pz, Best& best, float limit2 = INFINITY) {
     const uint32_t s0 = nearest_box(m.l2, 0, m.n2, px, py, pz);
+    best.d2 = limit2; best.d = limit2 < INFINITY ? sqrtf(limit2) * 1.000001f : INFINITY; best.b1 = 0.f; best.b2 = 0.f; best.f = 0xFFFFFFFFu;
+    if (box_dist2(m.l2 + s0, px, py, pz) > limit2) return;                       // nothing of the mesh within the limit
     const uint32_t g0 = nearest_box(m.l1, s0 * kFan, min(m.n1, (s0 + 1) * kFan), px, py, pz);
     const uint32_t c0 = nearest_box(m.l0, g0 * kFan, min(m.n0, (g0 + 1) * kFan), px, py, pz);
-    best.d2 = INFINITY; best.d = INFINITY; best.b1 = 0.f; best.b2 = 0.f; best.f = 0xFFFFFFFFu;
     scan_cluster(m.tris, c0 * kCluster, min(m.n_faces, (c0 + 1) * kCluster), px, py, pz, best);
     search_boxes(m, px, py, pz, c0, best);
 }
@@ -232,6 +237,14 @@ __device__ __forceinline__ void warp_outputs(const MeshView& m, const float* __r
     const uint32_t best_f = best.f;
     const float bb1 = best.b1, bb2 = best.b2;
     const float bestd2 = best.d2;
+    if (best_f == 0xFFFFFFFFu) {         // bounded search, nothing within the limit: masked out, the point itself stands in
+        can_pts[3 * (size_t)i] = px; can_pts[3 * (size_t)i + 1] = py; can_pts[3 * (size_t)i + 2] = pz;
+        mask[i] = 0.0f;
+        if (closest) { closest[3 * (size_t)i] = px; closest[3 * (size_t)i + 1] = py; closest[3 * (size_t)i + 2] = pz; }
+        if (face_id) face_id[i] = -1;
+        if (dist2_out) dist2_out[i] = bestd2;
+        return;
+    }
     const TriRec t = m.tris[best_f];
     const float b0 = 1.0f - bb1 - bb2;
     float M[12], c = 0.f;
@@ -274,13 +287,13 @@ __global__ void __launch_bounds__(256) warp_to_canonical_kernel(const float* __r
                                                                 const MeshView m, const float* __restrict__ T, float threshold,
                                                                 float* __restrict__ can_pts, float* __restrict__ mask,
                                                                 float* __restrict__ closest, int32_t* __restrict__ face_id,
-                                                                float* __restrict__ dist2_out) {
+                                                                float* __restrict__ dist2_out, const float limit2) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n) return;
     const uint32_t i = order ? (uint32_t)order[slot] : slot;      // spatially sorted queries keep a warp on the same boxes
     const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
     Best best;
-    closest_full(m, px, py, pz, best);
+    closest_full(m, px, py, pz, best, limit2);
     warp_outputs(m, T, threshold, i, px, py, pz, best, can_pts, mask, closest, face_id, dist2_out);
 }
 
@@ -395,7 +408,16 @@ int ac_warp_samples_to_canonical_ordered(const float* pts, const int32_t* order,
     if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0) return AC_E_INVALID_ARG;
     if (n_pts == 0) return AC_OK;
     warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, order, n_pts, mesh_view(mesh, n_faces), T, threshold,
-                                                                                   can_pts, mask, closest, face_id, dist2);
+                                                                                   can_pts, mask, closest, face_id, dist2, INFINITY);
+    return acb::launched();
+}
+
+int ac_warp_samples_to_canonical_masked(const float* pts, const int32_t* order, uint32_t n_pts, const void* mesh, uint32_t n_faces,
+                                        const float* T, float threshold, float* can_pts, float* mask, void* stream) {
+    if (!pts || !mesh || !T || !can_pts || !mask || n_faces == 0 || !(threshold > 0.f)) return AC_E_INVALID_ARG;
+    if (n_pts == 0) return AC_OK;
+    warp_to_canonical_kernel<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, order, n_pts, mesh_view(mesh, n_faces), T, threshold,
+                                                                                   can_pts, mask, nullptr, nullptr, nullptr, threshold);
     return acb::launched();
 }
 

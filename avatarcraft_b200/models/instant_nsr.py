@@ -270,6 +270,13 @@ class SingleVarianceNetwork(nn.Module):
 
 
 class NeRFRenderer(nn.Module):
+    # Warped renders (render_can=False) multiply alpha by the mask "closest surface point within sqrt(0.05)"
+    # (models/instant_nsr.py:245-248), so samples outside it cannot reach the image.  True: the section-point warp stops
+    # searching at that distance and the render launch skips sample blocks that are masked out entirely.  image, depth,
+    # weights_sum, normal_map, weights and alpha stay bit-identical; pts_color of skipped samples is 0 and the eikonal
+    # statistic no longer counts them -- which is why this is opt-in: render_warp.py (:88 discards that statistic) turns it on.
+    warp_skip_masked = False
+
     def __init__(self, cuda_ray=False, curvature_loss=False):
         super().__init__()
         if cuda_ray:
@@ -340,6 +347,7 @@ class NeRFRenderer(nn.Module):
         ray_bias = self._viewdir_bias(rays_d) if getattr(self, "use_viewdirs", False) and not opacity_only else None
         a = _lib.NsrRenderArgs(
             c0_ray_bias=None if ray_bias is None else ray_bias.data_ptr(), opacity_only=int(bool(opacity_only)),
+            skip_masked=int(alpha_mask is not None and bool(getattr(self, "warp_skip_masked", False))),
             rays_o=rays_o.data_ptr(), rays_d=rays_d.data_ptr(),
             bg_color=None if bg_color is None else bg_color.data_ptr(),
             jitter=None if jitter is None else jitter.data_ptr(),
@@ -445,7 +453,8 @@ class NeRFRenderer(nn.Module):
         # section mid-points, un-clamped (the warp comes first, :198-203): ac_nsr_section_points with an unreachable bound
         Pm = torch.empty(n * T, 3, **f32)
         _lib.check(L.ac_nsr_section_points(_lib.ptr(o), _lib.ptr(d), _lib.ptr(z), n, T, 3.0e38, _lib.ptr(Pm), sp()), "ac_nsr_section_points")
-        P, mask = warp_samples_to_canonical(Pm.reshape(n, T, 3), None, None, None, DEFAULT_GEO_THRESH, mesh=mesh, product=True)
+        P, mask = warp_samples_to_canonical(Pm.reshape(n, T, 3), None, None, None, DEFAULT_GEO_THRESH, mesh=mesh, product=True,
+                                            masked_only=bool(getattr(self, "warp_skip_masked", False)))
         if bg_color is not None:
             bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).expand(n, 3).contiguous()
         return self._launch_render(B, N, o, d, num_steps, upsample_steps, bound, bg_color, None, cos_anneal_ratio,

@@ -48,11 +48,14 @@ class PosedMesh:
                                           _lib.ptr(self.records), _lib.stream_ptr()), "ac_warp_prepare_mesh")
 
 
-def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMesh = None, return_query=False, product=False):
+def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMesh = None, return_query=False, product=False,
+                              masked_only=False):
     """pts [num_rays, num_samples, 3] (CUDA) -> can_pts, can_dirs, closest, mask -- the reference's return tuple
     (utils/ray_utils.py:62-90).  `can_dirs` is computed like the reference does although nothing downstream
     reads it (models/instant_nsr.py:203,208).  `product=True` (the render path): only what `run` consumes -- (can_pts
-    [R,S,3], mask [R,S] as the kernel's 0/1 floats) -- and no torch arithmetic."""
+    [R,S,3], mask [R,S] as the kernel's 0/1 floats) -- and no torch arithmetic.  `masked_only` (with `product`): the caller
+    multiplies alpha by the mask, so samples farther than sqrt(threshold) from the surface need no closest point -- the search
+    is bounded by the threshold, those samples return mask 0 and can_pts = pts; everything inside is unchanged."""
     assert pts.dim() == 3 and pts.shape[-1] == 3, 'pts should have shape [num_rays, num_samples, 3]'
     if mesh is None:
         mesh = PosedMesh(verts, faces, T, pts.device)
@@ -79,6 +82,11 @@ def warp_samples_to_canonical(pts, verts, faces, T, threshold=0.2, mesh: PosedMe
             _lib.check(_lib.lib().ac_warp_query_keys(_lib.ptr(flat), n, _lib.ptr(mesh.records), mesh.n_faces, 0.25, _lib.ptr(keys),
                                                      _lib.stream_ptr()), "ac_warp_query_keys")
             order = torch.sort(keys)[1].to(torch.int32)
+        if product and masked_only:
+            _lib.check(_lib.lib().ac_warp_samples_to_canonical_masked(_lib.ptr(flat), _lib.ptr(order), n, _lib.ptr(mesh.records), mesh.n_faces,
+                                                                      _lib.ptr(mesh.Ts), float(threshold), _lib.ptr(can), _lib.ptr(mask),
+                                                                      _lib.stream_ptr()), "ac_warp_samples_to_canonical_masked")
+            return can.reshape(R, S, 3), mask.reshape(R, S)
         _lib.check(_lib.lib().ac_warp_samples_to_canonical_ordered(_lib.ptr(flat), _lib.ptr(order), n, _lib.ptr(mesh.records), mesh.n_faces,
                                                                    _lib.ptr(mesh.Ts), float(threshold), _lib.ptr(can), _lib.ptr(mask),
                                                                    _lib.ptr(closest), _lib.ptr(face), _lib.ptr(dist2), _lib.stream_ptr()),

@@ -515,6 +515,7 @@ def measure_warp_frame(steps, dev, world, rank):
     from avatarcraft_b200.utils import synthetic as syn
     from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
     net = NeRFNetwork(); net.load_state_dict(syn.synthetic_state_dict("trained", 43)); net = net.to(dev).eval()
+    net.warp_skip_masked = os.environ.get("AC_WARP_EXACT_ALL", "") == ""       # what render_warp.py sets (it keeps only the image)
     body = syn.synthetic_body()
     o, d = syn.pinhole_rays(syn.orbit_pose(10.0 + 3.0 * rank), W_IMG, H_IMG)
     o, d = o.to(dev), d.to(dev)
@@ -541,7 +542,8 @@ def measure_warp_frame(steps, dev, world, rank):
             "closest_point_queries_per_sec": world * RAYS_PER_FRAME * 96 / per * 1e3, "gpu_launches": int(_lib.lib().ac_launch_count() - l0),
             "config": {"workload": "render_warp.py animate frame 256x256, 32+32 samples/ray, batch 8192, synthetic SMPL-shaped body "
                                    "(6890 verts / 13 776 faces), mesh prep + near/far + warp (96 closest-point queries/ray) + render",
-                       "sdf_evals_per_ray": 496, "color_evals_per_ray": 64}}
+                       "sdf_evals_per_ray": 496, "color_evals_per_ray": 64,
+                       "warp_skip_masked": bool(net.warp_skip_masked)}}
 
 
 def run_train(args):

@@ -280,6 +280,11 @@ typedef struct ac_nsr_render_args {
     /* non-zero: skip the colour network (rgb / pts_color are then meaningless; depth, weight_sum, normal, weights, alpha,
      * eikonal are unchanged) -- the opacity target of the trainer's frozen net only needs weight_sum (stylize.py:177-181). */
     uint32_t opacity_only;
+    /* non-zero (with alpha_mask): a block of 32 consecutive samples whose mask is all zero on the four rays evaluated
+     * together is not evaluated at all -- its alpha is zero whatever the networks say (models/instant_nsr.py:245-248), so rgb,
+     * depth, weight_sum, normal, weights and alpha are bit-identical; pts_color of such samples is 0 and they drop out of the
+     * eikonal statistic (which the inference entry point, render_warp.py:88, discards). */
+    uint32_t skip_masked;
 } ac_nsr_render_args;
 
 uint64_t ac_nsr_render_workspace_bytes(uint32_t n_rays);
@@ -331,6 +336,13 @@ int ac_warp_samples_to_canonical_rays(const float *pts, uint32_t n_rays, uint32_
 int ac_warp_samples_to_canonical_ordered(const float *pts, const int32_t *order, uint32_t n_pts, const void *mesh,
                                          uint32_t n_faces, const float *T, float threshold, float *can_pts,
                                          float *mask, float *closest, int32_t *face_id, float *dist2, void *stream);
+/* The section-point warp of the render path (models/instant_nsr.py:198-203,245-248): the caller multiplies alpha by `mask`,
+ * so a sample with no triangle within sqrt(threshold) needs no closest point.  The search is bounded by the threshold;
+ * such samples come back with mask 0 and can_pts = pts (a finite stand-in that never reaches the image); samples inside
+ * the threshold get exactly what ac_warp_samples_to_canonical_ordered returns. */
+int ac_warp_samples_to_canonical_masked(const float *pts, const int32_t *order, uint32_t n_pts, const void *mesh,
+                                        uint32_t n_faces, const float *T, float threshold, float *can_pts,
+                                        float *mask, void *stream);
 int ac_warp_query_keys(const float *pts, uint32_t n_pts, const void *mesh, uint32_t n_faces, float margin,
                        int32_t *keys, void *stream);
 int ac_mesh_guided_near_far(const float *rays_o, const float *rays_d, uint32_t n_rays, const float *verts,

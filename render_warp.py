@@ -46,6 +46,7 @@ def main():
         poses = np.load(opt.poseseq_path).astype(np.float32).reshape(-1, 72) if opt.poseseq_path else None
         faces = np.concatenate([body.faces, body.faces], 1)
     net = net.cuda().eval()
+    net.warp_skip_masked = True          # only img is kept below (as render_warp.py:88): masked-out samples need no search / evaluation
     shape_from, shape_to = np.zeros((1, 10), np.float32), np.zeros((1, 10), np.float32)
     shape_from[0, 1], shape_to[0, 1] = 2.0, -2.0                      # render_warp.py:37-45 defaults
     world_verts, Ts, n_frames = calc_local_trans(body, poses=poses, shape_from=shape_from, shape_to=shape_to,

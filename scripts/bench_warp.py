@@ -8,6 +8,7 @@ from avatarcraft_b200.utils import synthetic as syn
 from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
 torch.set_grad_enabled(False)
 net = NeRFNetwork(); net.load_state_dict(syn.synthetic_state_dict("trained", 43)); net = net.cuda().eval()
+net.warp_skip_masked = "--exact-all" not in sys.argv
 body = syn.synthetic_body()
 o, d = syn.pinhole_rays(syn.orbit_pose(10.0), 256, 256)
 o, d = o.cuda(), d.cuda()

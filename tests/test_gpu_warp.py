@@ -109,6 +109,44 @@ def test_warped_render_against_oracle(body):
     assert hit.sum() >= 5                                                  # the warp actually lands samples inside the canonical body
 
 
+def test_warp_skip_masked_leaves_the_image_bit_identical(body):
+    """NeRFNetwork.warp_skip_masked (what render_warp.py turns on): the section-point warp stops at the mask distance and
+    fully masked sample blocks are not evaluated.  Everything that reaches the image must be bit-identical to the exact path;
+    inside the mask distance the bounded search must return the unbounded search's canonical points."""
+    from avatarcraft_b200.utils.ray_utils import PosedMesh, warp_samples_to_canonical
+    from avatarcraft_b200.utils.constant import DEFAULT_GEO_THRESH
+    sd = state_dict("trained", 43)
+    net = gpu_model(sd)
+    o, d = syn.pinhole_rays(syn.orbit_pose(10.0), 64, 64)
+    o, d = o.cuda().contiguous(), d.cuda().contiguous()
+    kw = dict(render_can=False, verts=body["world_verts"], faces=body["faces"], Ts=body["Ts"])
+    exact = net.run(o[None], d[None], 32, 1.6, 32, None, 1.0, 0.0, **kw)
+    net.warp_skip_masked = True
+    try:
+        fast = net.run(o[None], d[None], 32, 1.6, 32, None, 1.0, 0.0, **kw)
+    finally:
+        net.warp_skip_masked = False
+    torch.cuda.synchronize()
+    for i, name in ((0, "depth"), (1, "weights"), (2, "weights_sum"), (3, "image"), (4, "normal_map"), (8, "alpha"), (9, "z_vals")):
+        assert torch.equal(exact[i], fast[i]), name
+    wsum = exact[2].reshape(-1)
+    assert int((wsum > 0.5).sum()) >= 200 and int((wsum == 0).sum()) >= 1000          # body rays and empty rays both present
+    # the bounded search itself: mask identical everywhere, canonical points identical wherever the mask is set
+    mesh = PosedMesh(body["world_verts"], body["faces"], body["Ts"], "cuda")
+    g = torch.Generator().manual_seed(3)
+    v = torch.as_tensor(body["world_verts"], dtype=torch.float32)
+    pts = torch.cat([v[torch.randint(0, v.shape[0], (20000,), generator=g)] + 0.15 * torch.randn(20000, 3, generator=g),
+                     torch.rand(20000, 3, generator=g) * 3.2 - 1.6]).cuda().reshape(40, 1000, 3)
+    can_a, mask_a = warp_samples_to_canonical(pts, None, None, None, DEFAULT_GEO_THRESH, mesh=mesh, product=True)
+    can_b, mask_b = warp_samples_to_canonical(pts, None, None, None, DEFAULT_GEO_THRESH, mesh=mesh, product=True, masked_only=True)
+    torch.cuda.synchronize()
+    assert torch.equal(mask_a, mask_b)
+    on = mask_a > 0.5
+    assert 5000 < int(on.sum()) < 35000
+    assert torch.equal(can_a[on], can_b[on])
+    assert torch.equal(can_b[~on], pts[~on])
+
+
 def test_render_driver_passes_warp_arguments(body):
     from avatarcraft_b200.utils.render_utils import render_instantnsr_naive
     sd = state_dict("trained", 43)
