@@ -35,7 +35,10 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------------
 // GEMM
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+#ifndef AC_GEMM_STAGES
+#define AC_GEMM_STAGES 3          // 3 x 32 KB: two CTAs per SM.  2 stages (three CTAs per SM) measure the same (11.57 vs 11.48 ms of GEMM
+#endif                            // per guidance call): the 128 x 128 tile's 64 flop per operand byte is capped by the L2 slices, not by occupancy
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = AC_GEMM_STAGES;
 constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand per stage
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 128;   // + barriers + TMEM slot
@@ -80,69 +83,76 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const __half* __restrict
     }
 }
 
-// Epilogue shared by both main loops.  TMEM lane = output row.  Rows are parked in shared memory (the operand ring is
-// idle now; 132-float pitch keeps the 16-byte stores of a quarter-warp on distinct banks) so that the global side is
-// row-contiguous: one warp instruction reads/writes 512 B of one output row (bias, per-row-group bias, residual and the
-// store / split-K reduction).
+// Epilogue shared by both main loops.  TMEM lane = output row.  The tile is parked in shared memory (the operand ring is
+// idle now) in two halves of 64 columns (68-float pitch: the 16-byte stores of a quarter-warp land on distinct banks; 34 KB, so
+// it fits the two-stage ring) so that the global side is row-contiguous: one warp instruction reads/writes 256 B of each of
+// two output rows (bias, per-row-group bias, residual and the store / split-K reduction).
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, unsigned char* smem, uint32_t tmem, int m0, int n0, long long c_off, int split,
                                               int warp, int lane) {
     float* stage = reinterpret_cast<float*>(smem);
-    constexpr int PITCH = BN + 4;
-    {
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        float* srow = stage + (warp * 32 + lane) * PITCH;
-#pragma unroll 2
-        for (int q = 0; q < BN / 16; ++q) {
-            float acc[16];
-            tc05::tmem_ld16(trow + q * 16, acc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(srow + q * 16)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-    }
-    __syncthreads();
+    constexpr int HALF = BN / 2, PITCH = HALF + 4;
+    static_assert(BM * PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit the operand ring");
     const bool lead = split == 0;                        // split-K: the first slice carries bias / residual
-    const int n = n0 + lane * 4;
-    const int nv = p.N - n < 4 ? p.N - n : 4;            // valid columns of this lane's float4 (<= 0: none)
-    const bool vec_ok = nv == 4 && (p.ldc & 3) == 0 && (c_off & 3) == 0;
-    float bz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.bias && lead)
-        for (int j = 0; j < 4; ++j) if (j < nv) bz[j] = p.bias[n + j];
+    const int sub = lane >> 4, l16 = lane & 15;          // a warp instruction covers two rows x 64 columns
 #pragma unroll 1
-    for (int r = warp; r < BM; r += GEMM_THREADS / 32) {
-        const int row = m0 + r;
-        if (row >= p.M || nv <= 0) continue;
-        const float4 a4 = *reinterpret_cast<const float4*>(stage + r * PITCH + lane * 4);
-        float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
-        if (lead && p.group_bias) {
-            const float* gb = p.group_bias + (long long)(row / p.rows_per_group) * p.N + n;
-            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += gb[j];
-        }
-        if (lead && p.residual) {
-            const float* rs = p.residual + (long long)row * p.ldr + n;
-            if (nv == 4 && (p.ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rs);
-                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-            } else {
-                for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rs[j];
+    for (int h = 0; h < 2; ++h) {
+        if (n0 + h * HALF >= p.N) break;                 // CTA-uniform: nothing of this half is inside the matrix
+        {
+            const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * HALF);
+            float* srow = stage + (warp * 32 + lane) * PITCH;
+#pragma unroll 2
+            for (int q = 0; q < HALF / 16; ++q) {
+                float acc[16];
+                tc05::tmem_ld16(trow + q * 16, acc);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(srow + q * 16)[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             }
         }
-        const long long at = c_off + (long long)row * p.ldc + n;
-        if (p.splits > 1) {
-            float* dst = reinterpret_cast<float*>(p.C) + at;
-            for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
-        } else if (p.out_f16) {
-            __half* dst = reinterpret_cast<__half*>(p.C) + at;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-                uint2 o; o.x = tc05::pack_f16x2(v[0], v[1]); o.y = tc05::pack_f16x2(v[2], v[3]);
-                *reinterpret_cast<uint2*>(dst) = o;
-            } else {
-                for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = __float2half_rn(v[j]);
+        __syncthreads();
+        const int n = n0 + h * HALF + l16 * 4;
+        const int nv = p.N - n < 4 ? p.N - n : 4;            // valid columns of this lane's float4 (<= 0: none)
+        const bool vec_ok = nv == 4 && (p.ldc & 3) == 0 && (c_off & 3) == 0;
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias && lead)
+            for (int j = 0; j < 4; ++j) if (j < nv) bz[j] = p.bias[n + j];
+#pragma unroll 1
+        for (int r = warp * 2 + sub; r < BM; r += GEMM_THREADS / 16) {
+            const int row = m0 + r;
+            if (row >= p.M || nv <= 0) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + r * PITCH + l16 * 4);
+            float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
+            if (lead && p.group_bias) {
+                const float* gb = p.group_bias + (long long)(row / p.rows_per_group) * p.N + n;
+                for (int j = 0; j < 4; ++j) if (j < nv) v[j] += gb[j];
             }
-        } else {
-            float* dst = reinterpret_cast<float*>(p.C) + at;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            else for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = v[j];
+            if (lead && p.residual) {
+                const float* rs = p.residual + (long long)row * p.ldr + n;
+                if (nv == 4 && (p.ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(rs);
+                    v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (j < nv) v[j] += rs[j];
+                }
+            }
+            const long long at = c_off + (long long)row * p.ldc + n;
+            if (p.splits > 1) {
+                float* dst = reinterpret_cast<float*>(p.C) + at;
+                for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, v[j]);
+            } else if (p.out_f16) {
+                __half* dst = reinterpret_cast<__half*>(p.C) + at;
+                if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                    uint2 o; o.x = tc05::pack_f16x2(v[0], v[1]); o.y = tc05::pack_f16x2(v[2], v[3]);
+                    *reinterpret_cast<uint2*>(dst) = o;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = __float2half_rn(v[j]);
+                }
+            } else {
+                float* dst = reinterpret_cast<float*>(p.C) + at;
+                if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                else for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = v[j];
+            }
         }
+        __syncthreads();                                 // the staging rows are rewritten by the second half
     }
 }
 
