@@ -103,6 +103,7 @@ _SIGNATURES = {
     "ac_version": (ctypes.c_char_p, []),
     "ac_last_cuda_error": (ctypes.c_char_p, []),
     "ac_launch_count": (ctypes.c_uint64, []),
+    "ac_launch_count_add": (None, [ctypes.c_uint64]),
     "ac_hash_encode_forward": (_I, [_V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
     "ac_hash_encode_backward": (_I, [_V, _V, _V, _V, _V, _U32, _U32, _U32, _U32, _F, _U32, _I, _V, _V, _V]),
     "ac_sh_encode_forward": (_I, [_V, _V, _U32, _U32, _U32, _I, _V, _V]),

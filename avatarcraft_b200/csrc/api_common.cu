@@ -42,4 +42,5 @@ extern "C" {
 const char* ac_version(void) { return "avatarcraft_b200 0.1 (sm_100a)"; }
 const char* ac_last_cuda_error(void) { return g_err; }
 uint64_t ac_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void ac_launch_count_add(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }

@@ -7,6 +7,7 @@ Layout: activations are contiguous fp32 [B, H, W, C] (== the [B*H*W, C] token ma
 (conv kernels permuted to [N, ky, kx, C]) are cached per parameter and refreshed when the parameter's version changes.
 No fallback: every op raises if libavatarcraft_b200.so is missing or a tensor is not on a CUDA device."""
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -227,11 +228,78 @@ def resnet(x, mod, temb_act16):
     return conv(h, mod.conv2, norm=mod.norm2, residual=sc)
 
 
-@torch.no_grad()
+GRAPH = os.environ.get("AC_SD_GRAPH", "1") != "0"     # replay the UNet forward as one CUDA graph (same kernels, no launch gaps)
+GRAPH_WARMUP = 2                                      # eager calls per input shape before the capture
+
+
+class _UNetGraph:
+    """One captured forward for one input signature: static input / output buffers + the graph."""
+
+    def __init__(self, unet, sample, timestep, ctx):
+        self.sample = sample.detach().clone()
+        self.t = torch.as_tensor(timestep, device=sample.device).reshape(-1).clone()
+        self.ctx = ctx.detach().clone()
+        self.graph = torch.cuda.CUDAGraph()
+        count = _lib.lib().ac_launch_count
+        torch.cuda.synchronize(sample.device)
+        n0 = count()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):    # other threads (NCCL watchdog) may touch CUDA meanwhile
+            self.out = _unet_forward_eager(unet, self.sample, self.t, self.ctx)
+        self.launches = int(count() - n0)             # kernels of this library inside the graph (ac_launch_count bookkeeping)
+
+    def __call__(self, sample, timestep, ctx):
+        self.sample.copy_(sample)
+        self.t.copy_(torch.as_tensor(timestep, device=self.sample.device).reshape(-1))
+        self.ctx.copy_(ctx)
+        self.graph.replay()
+        _lib.lib().ac_launch_count_add(self.launches)
+        return self.out
+
+
+def _weights_stamp(unet):
+    """Changes whenever a parameter is re-assigned or written in place (the graph holds fp16 copies of the weights)."""
+    s = 0
+    for p in unet.parameters():
+        s += p._version + (p.data_ptr() & 0xFFFFFF)
+    return s
+
+
 def unet_forward(unet, sample, timestep, encoder_hidden_states):
-    """UNet2DConditionModel.forward on the native kernels: sample [B,Cin,H,W] -> [B,Cout,H,W] fp32."""
+    """UNet2DConditionModel.forward on the native kernels: sample [B,Cin,H,W] -> [B,Cout,H,W] fp32.
+    After GRAPH_WARMUP eager calls with one input signature the launch sequence (~700 kernels of this library and a few torch
+    copies) is captured once and replayed: the kernels are identical, the CPU launch cost and the gaps between the small
+    kernels go away.  The returned tensor is the graph's output buffer: it is overwritten by the next call with the same
+    signature.  AC_SD_GRAPH=0 keeps every call eager."""
     if not sample.is_cuda:
         raise RuntimeError("sd_native.unet_forward needs CUDA tensors (no CPU path)")
+    if not GRAPH or torch.cuda.is_current_stream_capturing():
+        return _unet_forward_eager(unet, sample, timestep, encoder_hidden_states)
+    t = torch.as_tensor(timestep, device=sample.device)
+    key = (tuple(sample.shape), sample.dtype, int(t.numel()), t.dtype, tuple(encoder_hidden_states.shape), encoder_hidden_states.dtype,
+           sample.device.index)
+    cache = unet.__dict__.setdefault("_native_graphs", {})
+    stamp = _weights_stamp(unet)
+    if cache.get("stamp") != stamp:
+        cache.clear(); cache["stamp"] = stamp
+    slot = cache.get(key)
+    if isinstance(slot, _UNetGraph):
+        return slot(sample, timestep, encoder_hidden_states)
+    seen = 0 if slot is None else slot
+    if seen >= GRAPH_WARMUP:
+        try:
+            g = cache[key] = _UNetGraph(unet, sample, timestep, encoder_hidden_states)
+            return g(sample, timestep, encoder_hidden_states)
+        except Exception as e:                        # capture refused (e.g. an allocation inside it): stay eager, say so once
+            import warnings
+            warnings.warn(f"sd_native: CUDA graph capture of the UNet forward failed ({type(e).__name__}: {e}); running eagerly")
+            cache[key] = -(1 << 30)
+            return _unet_forward_eager(unet, sample, timestep, encoder_hidden_states)
+    cache[key] = seen + 1
+    return _unet_forward_eager(unet, sample, timestep, encoder_hidden_states)
+
+
+@torch.no_grad()
+def _unet_forward_eager(unet, sample, timestep, encoder_hidden_states):
     cfg = unet.config
     B = sample.shape[0]
     with torch.cuda.device(sample.device):

@@ -30,6 +30,8 @@ const char *ac_version(void);
 const char *ac_last_cuda_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t ac_launch_count(void);
+/* A caller that replays a captured CUDA graph of this library's launches adds the graph's kernel count per replay. */
+void ac_launch_count_add(uint64_t n);
 
 /* --------------------------------------------------------------------------------------
  * Multi-resolution hash-grid encoder.  Replaces the pybind ops

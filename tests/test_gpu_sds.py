@@ -159,6 +159,43 @@ def test_native_unet_matches_torch_ops_on_identical_weights(linear_proj):
     assert rel(y, ref) < 1e-2, rel(y, ref)
 
 
+def test_native_unet_graph_replay_equals_eager_launches():
+    """After two eager calls per input signature the native forward is captured into a CUDA graph and replayed: same kernels,
+    so replays on NEW inputs (sample, timestep, context all changed) must agree with the eager launches to the forward's own
+    run-to-run noise (two eager runs of this net differ by 0 .. 7e-4 relative L2: the split-K GEMMs reduce with atomics and a
+    last-bit difference flips fp16 roundings downstream; a stale input would show up as O(0.1)), the launch counter must keep
+    counting, and a weight change must drop the graph."""
+    from avatarcraft_b200.models import sd_native
+    torch.manual_seed(0)
+    unet = sd_unet.UNet2DConditionModel(sd_unet.UNetConfig.tiny()).cuda().eval()
+    assert sd_native.GRAPH
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    outs, ins = [], []
+    with torch.no_grad():
+        for i in range(5):
+            x = torch.randn(2, 4, 32, 32, device="cuda", generator=gen)
+            ctx = torch.randn(2, 77, unet.config.cross_attention_dim, device="cuda", generator=gen)
+            t = torch.tensor([100 + 150 * i], device="cuda")
+            before = _lib.lib().ac_launch_count()
+            outs.append(unet(x, t, encoder_hidden_states=ctx).sample.clone())
+            assert _lib.lib().ac_launch_count() - before > 100
+            ins.append((x, t, ctx))
+        graphs = [v for v in unet._native_graphs.values() if isinstance(v, sd_native._UNetGraph)]
+        assert len(graphs) == 1                                   # calls 3..5 were replays
+        sd_native.GRAPH = False
+        try:
+            for (x, t, ctx), y in zip(ins, outs):
+                ref = unet(x, t, encoder_hidden_states=ctx).sample
+                assert rel(y, ref) < 3e-3, rel(y, ref)
+        finally:
+            sd_native.GRAPH = True
+        unet.conv_out.bias.add_(1.0)                              # in-place weight change: the stale graph must not be used
+        x, t, ctx = ins[-1]
+        y = unet(x, t, encoder_hidden_states=ctx).sample
+        assert rel(y, outs[-1] + 1.0) < 3e-3
+        assert not any(isinstance(v, sd_native._UNetGraph) for v in unet._native_graphs.values())
+
+
 def test_sds_step_runs_end_to_end_with_native_unet():
     torch.manual_seed(0)
     sd = diffusion.StableDiffusion("cuda", "1.5", unet_config=sd_unet.UNetConfig.tiny(), vae=sd_vae.AutoencoderKL.tiny())
