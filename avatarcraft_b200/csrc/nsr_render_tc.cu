@@ -234,8 +234,8 @@ __device__ __forceinline__ void group_color_eval(Group& g, const float (&cin)[24
     group_color_rest<SLOT, VIEW>(g, rgb, bias);
 }
 
-template <int SLOT, bool VIEW = false>
-__global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const RenderParamsTC p) {
+template <int SLOT, bool VIEW = false, bool SKIP = false>      // SKIP: ac_nsr_render_args.skip_masked (its own instantiation: the
+__global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const RenderParamsTC p) {   // default kernel's code is untouched)
     extern __shared__ __align__(1024) unsigned char smem[];
     LevelMeta* lv = reinterpret_cast<LevelMeta*>(smem + SM_LEVELS);
     unsigned char* bt = smem + SM_B;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) nsr_render_tc_kernel(const R
             // skip_masked: when the warp's mask is zero on all 32 samples of this block for all four rays of the group (one
             // barrier with an OR reduction), nothing is evaluated -- every alpha of the block is zero anyway
             bool dead = false;
-            if (p.a.skip_masked && p.a.alpha_mask) {
+            if constexpr (SKIP) {
                 const bool on = k0 + lane < Ttot && p.a.alpha_mask[(size_t)ray * Ttot + k0 + lane] != 0.0f;
                 dead = !tc05::named_bar_or(g.bar_id, 128, on);
             }
@@ -756,6 +756,12 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
 #define AC_CALL(S)                                                                \
     ACB_SET_MAX_SMEM((nsr_render_tc_kernel<S, true>), SM_TOTAL);                  \
     nsr_render_tc_kernel<S, true><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
+        AC_SLOT_SWITCH(lease.slot, AC_CALL)
+#undef AC_CALL
+    } else if (a->skip_masked && a->alpha_mask && a->rgb) {      // warped inference that keeps only the image
+#define AC_CALL(S)                                                                \
+    ACB_SET_MAX_SMEM((nsr_render_tc_kernel<S, false, true>), SM_TOTAL);           \
+    nsr_render_tc_kernel<S, false, true><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(p)
         AC_SLOT_SWITCH(lease.slot, AC_CALL)
 #undef AC_CALL
     } else {
