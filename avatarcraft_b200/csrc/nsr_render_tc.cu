@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const 
                                                                           const float* __restrict__ blob, float S, uint32_t H,
                                                                           const float* __restrict__ x, float* __restrict__ out, uint32_t B, float bound,
                                                                           const uint32_t stencil_M, const float eps, float* __restrict__ out_fd,
-                                                                          unsigned char* __restrict__ feat_cache) {
+                                                                          unsigned char* __restrict__ feat_cache, const uint32_t packed) {
     // feat_cache (optional): every 128-point tile's encoded A operand (32 features as fp16 hi | lo chunks, 16 KB, the layout the
     // MMA reads) is also written to feat_cache + tile * 16 KB, so the backward of the same points loads it back with
     // coalesced 16-byte accesses instead of repeating the 128 gathers per point.
@@ -561,6 +561,52 @@ __global__ void __launch_bounds__(kWarpsTC * 32, 1) forward_sdf_tc_kernel(const 
         g.std_layout = ok;
     }
     const uint32_t per_cta = kGroups * 128;
+    if (packed) {
+        // Stencil mode, M a multiple of 128: a group takes 128 section points and evaluates their 7 x 128 stencil points in seven
+        // rounds.  Rounds 0..5 are the neighbours with a warp's lanes packed as (sample, direction) -- the six +-eps neighbours of a
+        // sample sit within 0.01 of each other, so on every level coarser than ~10 they share a grid cell and the warp's gather
+        // collapses to a few cache lines (the render kernel's arrangement, :687-704) -- round 6 the points themselves.  Outputs and
+        // feature-cache rows go where the point-major numbering b = block * M + sample puts them, so the backward is unchanged.
+        const int wq = warp & 3;
+        // 128-sample blocks are dealt to CTAs first, then to a CTA's groups: a small launch still spreads over every SM
+        for (uint32_t u = blockIdx.x + gridDim.x * (uint32_t)group; u < (stencil_M >> 7); u += gridDim.x * kGroups) {    // group-uniform
+            const uint32_t s0 = (u << 7) + 32u * (uint32_t)wq;
+#pragma unroll 1
+            for (int k = 0; k < 7; ++k) {
+                uint32_t blk = 0, smp = s0 + (uint32_t)lane;
+                if (k < 6) {
+                    const uint32_t q = 32u * (uint32_t)k + (uint32_t)lane;
+                    smp = s0 + q / 6u; blk = q % 6u + 1u;
+                }
+                float px = x[3 * (size_t)smp], py = x[3 * (size_t)smp + 1], pz = x[3 * (size_t)smp + 2];
+                if (blk) {
+                    const float e = (blk & 1) ? eps : -eps;  // blocks 1,3,5 = +eps, 2,4,6 = -eps
+                    const uint32_t ax = (blk - 1) >> 1;
+                    if (ax == 0) px = clampf(px + e, -bound, bound);
+                    else if (ax == 1) py = clampf(py + e, -bound, bound);
+                    else pz = clampf(pz + e, -bound, bound);
+                }
+                if (k == 6) {
+                    float o16[16];
+                    group_sdf_eval<SLOT, true>(g, table, lv, bound, px, py, pz, o16);
+                    float4* dst = reinterpret_cast<float4*>(out + 16 * (size_t)smp);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+                } else {
+                    float o1[1];
+                    group_sdf_eval<SLOT, false>(g, table, lv, bound, px, py, pz, o1);
+                    out_fd[(size_t)(blk - 1) * stencil_M + smp] = o1[0];
+                }
+                if (feat_cache) {
+                    const size_t b = (size_t)blk * stencil_M + smp;
+                    unsigned char* dst = feat_cache + (b >> 7) * 16384 + (b & 127) * 16;
+                    const unsigned char* src = g.a + g.row * 16;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 2048) = *reinterpret_cast<const uint4*>(src + c * 2048);
+                }
+            }
+        }
+    } else
     for (uint32_t base = blockIdx.x * per_cta; base < B; base += gridDim.x * per_cta) {      // uniform trip count per CTA
         const uint32_t b = base + threadIdx.x;
         const bool valid = b < B;
@@ -779,7 +825,10 @@ int launch_render_tc(const ac_nsr_model* m, const ac_nsr_render_args* a, cudaStr
 int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uint32_t B, float bound, cudaStream_t st, uint32_t stencil_M,
                           float eps, float* out_fd, void* feat_cache) {
     const uint32_t per_cta = kGroups * 128;
-    const uint32_t want = (B + per_cta - 1) / per_cta;
+    // packed stencil rounds (see the kernel) when the section points fill whole 128-row tiles and the machine; AC_STENCIL_FWD=flat: A/B
+    static const bool flat = [] { const char* e = getenv("AC_STENCIL_FWD"); return e && e[0] == 'f'; }();
+    const uint32_t packed = (stencil_M && !flat && (stencil_M & 127u) == 0u) ? 1u : 0u;
+    const uint32_t want = packed ? (stencil_M >> 7) : (B + per_cta - 1) / per_cta;
     const uint32_t grid = want < (uint32_t)acb::sm_count() ? want : (uint32_t)acb::sm_count();
     SlotLease lease(m->mlp_blob, st);
     if (lease.rc) return lease.rc;
@@ -787,7 +836,7 @@ int launch_forward_sdf_tc(const ac_nsr_model* m, const float* x, float* out, uin
     ACB_SET_MAX_SMEM(forward_sdf_tc_kernel<S>, SM_TOTAL);                                                                       \
     forward_sdf_tc_kernel<S><<<grid, kWarpsTC * 32, SM_TOTAL, st>>>(reinterpret_cast<const float2*>(m->embeddings), m->offsets, \
         m->mlp_blob, m->log2_per_level_scale, m->base_resolution, x, out, B, bound, stencil_M, eps, out_fd,           \
-        reinterpret_cast<unsigned char*>(feat_cache))
+        reinterpret_cast<unsigned char*>(feat_cache), packed)
     AC_SLOT_SWITCH(lease.slot, AC_CALL)
 #undef AC_CALL
     const int rc = acb::launched();
