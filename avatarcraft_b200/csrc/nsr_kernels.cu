@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(256) pack_mlp_kernel(const PackArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256) debug_upsample_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+__global__ void __launch_bounds__(256) upsample_round_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                              const float* __restrict__ z, const float* __restrict__ sdf, uint32_t n,
                                                              uint32_t T, float inv_s, const float* __restrict__ alpha_in, float* alpha_out,
                                                              float* z_new_out, int32_t* bins, float* z_out, int32_t* order) {
@@ -660,7 +660,7 @@ int ac_nsr_debug_upsample(const float* rays_o, const float* rays_d, const float*
     if (!rays_o || !rays_d || !z || !sdf || !z_new || !bins || !z_out || !order) return AC_E_INVALID_ARG;
     if (T < 2 || T + 16 > (uint32_t)kMaxT) return AC_E_INVALID_ARG;
     if (n_rays == 0) return AC_OK;
-    debug_upsample_kernel<<<(n_rays + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+    upsample_round_kernel<<<(n_rays + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, z, sdf, n_rays, T, inv_s, alpha_in, alpha_out, z_new, bins, z_out, order);
     return acb::launched();
 }
