@@ -523,27 +523,38 @@ def measure_warp_frame(steps, dev, world, rank):
     def frame():
         return render_instantnsr_naive(net, o, d, 8192, render_can=False, perturb=False, verts=body["world_verts"], faces=body["faces"],
                                        Ts=body["Ts"], num_steps=32, upsample_steps=32, bound=BOUND)
-    for _ in range(3):
-        frame()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    def timed(n):
+        for _ in range(3):
+            frame()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            frame()
+        e1.record(); e1.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier(); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+    # the same frame with every masked-out sample searched to the end and evaluated (the flag off): reported beside the headline
+    skip = net.warp_skip_masked
+    net.warp_skip_masked = False
+    per_all = timed(max(3, steps // 2))
+    net.warp_skip_masked = skip
     l0 = _lib.lib().ac_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        frame()
-    e1.record(); e1.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.barrier(); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    per = float(ms) / steps
+    per = timed(steps)
+    l0 += 3 * (_lib.lib().ac_launch_count() - l0) // (steps + 3)          # the warm-up frames' launches are not in the timed region
     return {"metric": "warp_frame_rays_per_sec", "value": world * RAYS_PER_FRAME / per * 1e3, "unit": "rays/s", "ms_per_frame": per, "steps": steps,
             "closest_point_queries_per_sec": world * RAYS_PER_FRAME * 96 / per * 1e3, "gpu_launches": int(_lib.lib().ac_launch_count() - l0),
             "config": {"workload": "render_warp.py animate frame 256x256, 32+32 samples/ray, batch 8192, synthetic SMPL-shaped body "
                                    "(6890 verts / 13 776 faces), mesh prep + near/far + warp (96 closest-point queries/ray) + render",
                        "sdf_evals_per_ray": 496, "color_evals_per_ray": 64,
-                       "warp_skip_masked": bool(net.warp_skip_masked)}}
+                       "warp_skip_masked": bool(net.warp_skip_masked)},
+            "all_samples_evaluated": {"ms_per_frame": per_all, "value": world * RAYS_PER_FRAME / per_all * 1e3, "unit": "rays/s",
+                                      "what": "warp_skip_masked off: masked-out samples (alpha x 0) are searched to the end and evaluated "
+                                              "too; image, depth, opacity and weights are bit-identical either way"}}
 
 
 def run_train(args):
