@@ -253,7 +253,7 @@ class _UNetGraph:
         self.ctx.copy_(ctx)
         self.graph.replay()
         _lib.lib().ac_launch_count_add(self.launches)
-        return self.out
+        return self.out.clone()                       # [B,4,64,64]: the caller may keep it across calls
 
 
 def _weights_stamp(unet):
@@ -271,8 +271,8 @@ def unet_forward(unet, sample, timestep, encoder_hidden_states):
     """UNet2DConditionModel.forward on the native kernels: sample [B,Cin,H,W] -> [B,Cout,H,W] fp32.
     After GRAPH_WARMUP eager calls with one input signature the launch sequence (~700 kernels of this library and a few torch
     copies) is captured once and replayed: the kernels are identical, the CPU launch cost and the gaps between the small
-    kernels go away.  The returned tensor is the graph's output buffer: it is overwritten by the next call with the same
-    signature.  AC_SD_GRAPH=0 keeps every call eager."""
+    kernels go away.  The result is copied out of the graph's output buffer, so it stays valid across calls.
+    AC_SD_GRAPH=0 keeps every call eager."""
     if not sample.is_cuda:
         raise RuntimeError("sd_native.unet_forward needs CUDA tensors (no CPU path)")
     if not GRAPH or torch.cuda.is_current_stream_capturing():
