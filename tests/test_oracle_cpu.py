@@ -186,6 +186,41 @@ def test_warp_oracle_geometry():
     assert mask.all()
 
 
+def test_masked_samples_cannot_reach_the_warped_image():
+    """The premise of NeRFNetwork.warp_skip_masked, checked on the oracle (models/instant_nsr.py:245-248): alpha is multiplied by
+    the warp's mask, so replacing the canonical position of every masked-out SECTION sample by anything finite (here: the
+    un-warped point, which is what ac_warp_samples_to_canonical_masked returns) leaves image, depth, opacity, normals and
+    weights bit-identical."""
+    from oracle import warp_oracle as wo
+    body = syn.synthetic_body()
+    orc = OracleNSR(state_dict("trained", 43))
+    o, d = syn.pinhole_rays(syn.orbit_pose(10.0), 64, 64)
+    sel = torch.cat([torch.arange(64 * 30 + 20, 64 * 30 + 44, 3), torch.arange(64 * 30, 64 * 30 + 6)])     # torso rays + empty rays
+    o, d = o[sel].contiguous(), d[sel].contiguous()
+    kw = dict(verts=body["world_verts"], faces=body["faces"], Ts=body["Ts"])
+    exact = orc.run(o, d, 32, 1.6, 32, **kw)
+    real, calls, masked = wo.warp_samples_to_canonical, [0], [0]
+
+    def bounded(p, *a, **k):
+        out = list(real(p, *a, **k))
+        calls[0] += 1
+        if calls[0] == 2:                           # the section-point warp (the coarse warp feeds the importance sampling: exact)
+            off = ~np.asarray(out[1], bool)
+            masked[0] = int(off.sum())
+            out[0] = np.where(off[..., None], np.asarray(p, np.float64), out[0])
+        return tuple(out)
+    wo.warp_samples_to_canonical = bounded
+    try:
+        fast = orc.run(o, d, 32, 1.6, 32, **kw)
+    finally:
+        wo.warp_samples_to_canonical = real
+    assert calls[0] == 2 and masked[0] > 100
+    wsum = exact[2].reshape(-1)
+    assert float(wsum.max()) > 0.5 and float(wsum.min()) == 0.0                 # body rays and fully masked rays both present
+    for i, name in ((0, "depth"), (1, "weights"), (2, "weights_sum"), (3, "image"), (4, "normal_map"), (8, "alpha"), (9, "z_vals")):
+        assert torch.equal(exact[i], fast[i]), name
+
+
 def test_smpl_lbs_matches_reference_fixture():
     """avatarcraft_b200.models.smpl (host-side W3) == the reference's models/smpl.py::lbs on the synthetic
     SMPL-shaped model (fixture from /root/reference): per-vertex + joint transforms, posed vertices, joints."""
